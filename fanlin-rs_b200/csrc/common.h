@@ -1,0 +1,44 @@
+// Shared host/device definitions of the pixel-transform stage.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/fanlin_device.h"
+
+namespace fanlin {
+
+enum ColorOp : uint32_t { COLOR_NONE = 0, COLOR_GRAY = 1, COLOR_INVERT = 2 };
+enum Epilogue : uint32_t { EPI_PLAIN = 0, EPI_BLEND_FILL = 1, EPI_TO_RGBA = 2 };
+enum FilterKind : uint32_t { KIND_NEAREST = 0, KIND_LANCZOS3 = 1, KIND_GAUSSIAN = 100 };
+
+// One entry of an axis table: output index o reads source [left, left+count) with
+// weights tab_w[woff .. woff+count).
+struct TapEntry {
+    uint32_t left, count, woff;
+};
+
+// Device descriptor of one separable stage (resample or blur) of one job, or of a
+// compose-only stage (v_tab == NO_TABLE).  The ragged batch is an array of these.
+constexpr uint32_t NO_TABLE = 0xffffffffu;
+
+struct StageDesc {
+    const uint8_t *src;
+    uint8_t *dst;
+    float *tmp;           // exact path: [n_rows][tmp_pitch] f32
+    uint32_t src_pitch, src_w, src_h;
+    uint32_t c_mem;       // channels in memory at src
+    uint32_t c;           // channels after the colour op (what the filter sees)
+    uint32_t color_op;
+    uint32_t v_tab, h_tab;  // offsets (in TapEntry units) into the table arena
+    uint32_t oy0, n_rows;   // rows of the filtered image that are produced
+    uint32_t ox0, n_cols;   // columns of the filtered image that are produced
+    uint32_t sx0, n_sx;     // source columns the produced columns depend on
+    uint32_t sy0, n_sy;     // source rows the produced rows depend on
+    uint32_t tmp_pitch;     // floats per tmp row
+    uint32_t dst_pitch, c_out, canvas_w, canvas_h;
+    uint32_t dst_x, dst_y;  // where the produced rect lands on the canvas
+    uint32_t epi;
+    uint32_t fill;          // r | g<<8 | b<<16 | 255<<24
+    uint32_t v_max_taps, h_max_taps;
+};
+
+}  // namespace fanlin

@@ -1,0 +1,59 @@
+// Host-side planning: geometry of a job and the per-axis filter tables.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "common.h"
+
+namespace fanlin {
+
+void set_error(const std::string &msg);
+const char *get_error();
+
+// Filter taps of one axis (n_in -> n_out), built with the f32 recipe of
+// image-0.25.6 imageops/sample.rs.
+struct AxisTable {
+    uint32_t kind = 0, n_in = 0, n_out = 0;
+    float sigma = 0.f;
+    uint32_t max_taps = 0;
+    std::vector<TapEntry> entries;  // woff relative to `weights`
+    std::vector<float> weights;
+};
+
+using TableKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>;  // kind, sigma bits, n_in, n_out
+TableKey table_key(uint32_t kind, float sigma, uint32_t n_in, uint32_t n_out);
+std::shared_ptr<const AxisTable> build_axis_table(uint32_t kind, float sigma, uint32_t n_in, uint32_t n_out);
+
+// resize_dimensions of image-0.25.6 math/utils.rs.
+void resize_dimensions(uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, bool fill, uint32_t *ow, uint32_t *oh);
+
+// One device stage of a job, host view.
+struct StagePlan {
+    bool present = false;
+    bool separable = false;  // false: compose only (colour op / letterbox / to_rgba8 / copy)
+    bool src_is_input = true;  // else reads the previous stage's canvas
+    uint32_t in_w = 0, in_h = 0, c_mem = 0, c = 0, color_op = COLOR_NONE;
+    uint32_t v_kind = 0, h_kind = 0;
+    float sigma = 0.f;
+    uint32_t v_out = 0, h_out = 0;  // full filtered size (table n_out) per axis
+    uint32_t oy0 = 0, n_rows = 0, ox0 = 0, n_cols = 0;
+    uint32_t sx0 = 0, n_sx = 0, sy0 = 0, n_sy = 0;
+    uint32_t canvas_w = 0, canvas_h = 0, c_out = 0, dst_x = 0, dst_y = 0, epi = EPI_PLAIN, fill = 0;
+    std::shared_ptr<const AxisTable> vtab, htab;
+};
+
+struct JobPlan {
+    fanlin_plan pub{};
+    StagePlan a;  // colour op + resample + letterbox (+ to_rgba8), or compose
+    StagePlan b;  // blur
+};
+
+// Returns FANLIN_OK or FANLIN_EINVAL (message via set_error).  with_tables: also
+// build the axis tables (not needed for fanlin_plan_job).
+int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables);
+
+}  // namespace fanlin

@@ -1,0 +1,474 @@
+// Context, buffer pools, prepared (device-resident) batches and the blocking
+// host-buffer entry point.  No CPU fallback: every path ends in a CUDA launch or
+// an error status.
+#include "runtime.h"
+
+#include <algorithm>
+#include <cstring>
+#include <string>
+
+using namespace fanlin;
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            set_error(std::string("fanlin: CUDA error: ") + cudaGetErrorString(e_) + " in " #expr); \
+            return FANLIN_ECUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+namespace fanlin {
+
+// ---- pinned pool --------------------------------------------------------------
+
+static size_t size_class(size_t b) {
+    size_t c = 64 << 10;
+    while (c < b) c <<= 1;
+    return c;
+}
+
+PinnedPool::~PinnedPool() {
+    for (auto &kv : free_)
+        for (void *p : kv.second) cudaFreeHost(p);
+}
+
+void *PinnedPool::alloc(size_t bytes) {
+    const size_t cls = size_class(bytes);
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = free_.find(cls);
+        if (it != free_.end() && !it->second.empty()) {
+            void *p = it->second.back();
+            it->second.pop_back();
+            cached_ -= cls;
+            live_[p] = cls;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, cls, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    live_[p] = cls;
+    return p;
+}
+
+void PinnedPool::free(void *p) {
+    if (!p) return;
+    size_t cls = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        auto it = live_.find(p);
+        if (it == live_.end()) return;
+        cls = it->second;
+        live_.erase(it);
+        if (cached_ + cls <= limit_) {
+            free_[cls].push_back(p);
+            cached_ += cls;
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
+bool PinnedPool::owns(const void *p, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = live_.upper_bound(p);
+    if (it == live_.begin()) return false;
+    --it;
+    const char *base = static_cast<const char *>(it->first);
+    const char *q = static_cast<const char *>(p);
+    return q >= base && q + bytes <= base + it->second;
+}
+
+}  // namespace fanlin
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- context --------------------------------------------------------------------
+
+extern "C" int fanlin_abi_version(void) { return FANLIN_ABI_VERSION; }
+
+extern "C" const char *fanlin_last_error(void) { return get_error(); }
+
+extern "C" int fanlin_plan_job(const fanlin_job *job, fanlin_plan *plan) {
+    if (!job || !plan) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
+    JobPlan p;
+    const int rc = plan_job(*job, &p, false);
+    if (rc == FANLIN_OK) *plan = p.pub;
+    return rc;
+}
+
+extern "C" int fanlin_init(const int *device_ids, int n_devices, const fanlin_config *cfg, fanlin_ctx **out) {
+    if (!out) { set_error("fanlin: null out pointer"); return FANLIN_EINVAL; }
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_error("fanlin: no CUDA device available (this path has no CPU fallback)");
+        return FANLIN_ENODEVICE;
+    }
+    std::vector<int> ids;
+    if (n_devices <= 0 || !device_ids) {
+        for (int i = 0; i < count; i++) ids.push_back(i);
+    } else {
+        for (int i = 0; i < n_devices; i++) {
+            if (device_ids[i] < 0 || device_ids[i] >= count) { set_error("fanlin: bad device ordinal"); return FANLIN_EINVAL; }
+            ids.push_back(device_ids[i]);
+        }
+    }
+    std::unique_ptr<fanlin_ctx> ctx(new fanlin_ctx());
+    if (cfg) std::memcpy(&ctx->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(*cfg), sizeof(*cfg)));
+    if (!ctx->cfg.device_scratch_bytes) ctx->cfg.device_scratch_bytes = uint64_t(8) << 30;
+    if (!ctx->cfg.pinned_bytes) ctx->cfg.pinned_bytes = uint64_t(2) << 30;
+    if (!ctx->cfg.batch_window_us) ctx->cfg.batch_window_us = 200;
+    if (!ctx->cfg.max_batch_jobs) ctx->cfg.max_batch_jobs = 4096;
+    ctx->pinned.set_limit(ctx->cfg.pinned_bytes);
+    for (int id : ids) {
+        CUDA_TRY(cudaSetDevice(id));
+        std::unique_ptr<DeviceState> d(new DeviceState());
+        d->ordinal = id;
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d->copy_out, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the device side of the buffer pool
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        ctx->devs.push_back(std::move(d));
+    }
+    *out = ctx.release();
+    return FANLIN_OK;
+}
+
+extern "C" void fanlin_shutdown(fanlin_ctx *ctx) {
+    if (!ctx) return;
+    ctx->down = true;
+    for (auto &d : ctx->devs) {
+        {
+            std::lock_guard<std::mutex> lk(d->qmu);
+            d->stop = true;
+        }
+        d->qcv.notify_all();
+        if (d->worker.joinable()) d->worker.join();
+        cudaSetDevice(d->ordinal);
+        cudaStreamSynchronize(d->stream);
+        cudaStreamDestroy(d->stream);
+        cudaStreamDestroy(d->copy_in);
+        cudaStreamDestroy(d->copy_out);
+    }
+    delete ctx;
+}
+
+extern "C" int fanlin_device_count(const fanlin_ctx *ctx) { return ctx ? int(ctx->devs.size()) : 0; }
+
+extern "C" int fanlin_get_stats(const fanlin_ctx *ctx, fanlin_stats *out) {
+    if (!ctx || !out) return FANLIN_EINVAL;
+    out->kernel_launches = ctx->kernel_launches.load();
+    out->jobs = ctx->jobs.load();
+    out->batches = ctx->batches.load();
+    out->h2d_bytes = ctx->h2d_bytes.load();
+    out->d2h_bytes = ctx->d2h_bytes.load();
+    return FANLIN_OK;
+}
+
+extern "C" void *fanlin_host_alloc(fanlin_ctx *ctx, size_t bytes) {
+    if (!ctx || !bytes) return nullptr;
+    return ctx->pinned.alloc(bytes);
+}
+extern "C" void fanlin_host_free(fanlin_ctx *ctx, void *p) {
+    if (ctx) ctx->pinned.free(p);
+}
+
+// ---- prepared batches -------------------------------------------------------------
+
+namespace {
+
+struct JobScratch {
+    size_t inter = 0, tmp = 0;          // bytes
+    size_t inter_off = 0, tmp_off = 0;  // offsets inside the chunk's scratch
+};
+
+void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t *inter, float *tmp,
+               const std::map<const AxisTable *, uint32_t> &tab_base, bool last_stage) {
+    std::memset(d, 0, sizeof(*d));
+    if (s.src_is_input) {
+        d->src = job.src;
+        d->src_pitch = job.src_pitch ? job.src_pitch : job.src_w * job.src_channels;
+    } else {
+        d->src = inter;
+        d->src_pitch = s.in_w * s.c_mem;
+    }
+    d->dst = last_stage ? job.dst : inter;
+    d->tmp = tmp;
+    d->src_w = s.in_w; d->src_h = s.in_h;
+    d->c_mem = s.c_mem; d->c = s.c; d->color_op = s.color_op;
+    d->v_tab = s.vtab ? tab_base.at(s.vtab.get()) : NO_TABLE;
+    d->h_tab = s.htab ? tab_base.at(s.htab.get()) : NO_TABLE;
+    d->v_max_taps = s.vtab ? s.vtab->max_taps : 0;
+    d->h_max_taps = s.htab ? s.htab->max_taps : 0;
+    d->oy0 = s.oy0; d->n_rows = s.n_rows; d->ox0 = s.ox0; d->n_cols = s.n_cols;
+    d->sx0 = s.sx0; d->n_sx = s.n_sx; d->sy0 = s.sy0; d->n_sy = s.n_sy;
+    d->tmp_pitch = s.n_sx * s.c;
+    d->dst_pitch = s.canvas_w * s.c_out; d->c_out = s.c_out;
+    d->canvas_w = s.canvas_w; d->canvas_h = s.canvas_h;
+    d->dst_x = s.dst_x; d->dst_y = s.dst_y; d->epi = s.epi; d->fill = s.fill;
+}
+
+void geom_add(LaunchGeom *g, const StageDesc &d) {
+    g->n_jobs++;
+    g->max_n_rows = std::max(g->max_n_rows, d.n_rows);
+    g->max_n_sx = std::max(g->max_n_sx, d.n_sx);
+    g->max_n_cols = std::max(g->max_n_cols, d.n_cols);
+    g->max_canvas_w = std::max(g->max_canvas_w, d.canvas_w);
+    g->max_canvas_h = std::max(g->max_canvas_h, d.canvas_h);
+}
+
+}  // namespace
+
+extern "C" void fanlin_batch_free(fanlin_batch *b) {
+    if (!b) return;
+    if (b->dev) cudaSetDevice(b->dev->ordinal);
+    if (b->d_meta) cudaFree(b->d_meta);
+    if (b->d_scratch) cudaFree(b->d_scratch);
+    delete b;
+}
+
+extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fanlin_job *jobs, uint32_t n_jobs,
+                                    fanlin_plan *plans_out, fanlin_batch **out) {
+    if (!ctx || !out || (!jobs && n_jobs)) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
+    *out = nullptr;
+    if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
+    if (device_index < 0 || device_index >= int(ctx->devs.size())) { set_error("fanlin: bad device index"); return FANLIN_EINVAL; }
+    DeviceState *dev = ctx->devs[device_index].get();
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    std::unique_ptr<fanlin_batch, void (*)(fanlin_batch *)> b(new fanlin_batch(), fanlin_batch_free);
+    b->ctx = ctx;
+    b->dev = dev;
+    b->n_jobs = n_jobs;
+    b->plans.resize(n_jobs);
+    const bool exact = true;  // fast kernels select themselves per stage below once present
+
+    // 1. plans + table arena
+    std::map<const AxisTable *, uint32_t> tab_base;
+    std::vector<TapEntry> entries;
+    std::vector<float> weights;
+    auto add_table = [&](const std::shared_ptr<const AxisTable> &t) {
+        if (!t || tab_base.count(t.get())) return;
+        tab_base[t.get()] = uint32_t(entries.size());
+        const uint32_t wb = uint32_t(weights.size());
+        for (const TapEntry &e : t->entries) entries.push_back(TapEntry{e.left, e.count, e.woff + wb});
+        weights.insert(weights.end(), t->weights.begin(), t->weights.end());
+    };
+    for (uint32_t i = 0; i < n_jobs; i++) {
+        const int rc = plan_job(jobs[i], &b->plans[i], true);
+        if (rc != FANLIN_OK) return rc;
+        if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
+        if (jobs[i].dst_capacity < b->plans[i].pub.out_bytes) {
+            set_error("fanlin: dst_capacity smaller than the planned output");
+            return FANLIN_ECAPACITY;
+        }
+        if (plans_out) plans_out[i] = b->plans[i].pub;
+        add_table(b->plans[i].a.vtab); add_table(b->plans[i].a.htab);
+        add_table(b->plans[i].b.vtab); add_table(b->plans[i].b.htab);
+    }
+
+    // 2. scratch layout, chunked so one chunk fits the scratch budget
+    std::vector<JobScratch> js(n_jobs);
+    std::vector<uint32_t> chunk_end;
+    size_t scratch_bytes = 0;
+    {
+        size_t cur = 0;
+        for (uint32_t i = 0; i < n_jobs; i++) {
+            const JobPlan &p = b->plans[i];
+            if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_w) * p.a.canvas_h * p.a.c_out, 256);
+            size_t ta = 0, tb = 0;
+            if (exact && p.a.present && p.a.separable) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
+            if (exact && p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;
+            js[i].tmp = align_up(std::max(ta, tb), 256);
+            const size_t need = js[i].inter + js[i].tmp;
+            if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
+                chunk_end.push_back(i);
+                cur = 0;
+            }
+            js[i].inter_off = cur;
+            js[i].tmp_off = cur + js[i].inter;
+            cur += need;
+            scratch_bytes = std::max(scratch_bytes, cur);
+        }
+        chunk_end.push_back(n_jobs);
+    }
+    if (scratch_bytes) CUDA_TRY(cudaMalloc(&b->d_scratch, scratch_bytes));
+
+    // 3. descriptors per chunk and stage kind
+    std::vector<StageDesc> descs;
+    struct HostStep { int kind; size_t first; LaunchGeom g; };
+    std::vector<HostStep> hsteps;
+    uint32_t begin = 0;
+    for (uint32_t end : chunk_end) {
+        for (int pass = 0; pass < 3; pass++) {  // 0: A separable, 1: A compose, 2: B separable
+            HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}};
+            for (uint32_t i = begin; i < end; i++) {
+                const JobPlan &p = b->plans[i];
+                const StagePlan &s = pass == 2 ? p.b : p.a;
+                if (!s.present) continue;
+                if (pass == 0 && !s.separable) continue;
+                if (pass == 1 && s.separable) continue;
+                uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
+                float *tmp = js[i].tmp ? reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off) : nullptr;
+                StageDesc d;
+                const bool last = pass == 2 || !p.b.present;
+                fill_desc(&d, s, jobs[i], inter, tmp, tab_base, last);
+                geom_add(&hs.g, d);
+                descs.push_back(d);
+            }
+            if (hs.g.n_jobs) hsteps.push_back(hs);
+        }
+        begin = end;
+    }
+
+    // 4. upload descriptors + tables in one block
+    const size_t off_tab = align_up(descs.size() * sizeof(StageDesc), 256);
+    const size_t off_w = off_tab + align_up(entries.size() * sizeof(TapEntry), 256);
+    const size_t meta_bytes = off_w + align_up(weights.size() * sizeof(float), 256) + 256;
+    std::vector<uint8_t> meta(meta_bytes, 0);
+    if (!descs.empty()) std::memcpy(meta.data(), descs.data(), descs.size() * sizeof(StageDesc));
+    if (!entries.empty()) std::memcpy(meta.data() + off_tab, entries.data(), entries.size() * sizeof(TapEntry));
+    if (!weights.empty()) std::memcpy(meta.data() + off_w, weights.data(), weights.size() * sizeof(float));
+    CUDA_TRY(cudaMalloc(&b->d_meta, meta_bytes));
+    CUDA_TRY(cudaMemcpyAsync(b->d_meta, meta.data(), meta_bytes, cudaMemcpyHostToDevice, dev->stream));
+    CUDA_TRY(cudaStreamSynchronize(dev->stream));
+    const uint8_t *mbase = static_cast<const uint8_t *>(b->d_meta);
+    b->d_tab = reinterpret_cast<const TapEntry *>(mbase + off_tab);
+    b->d_w = reinterpret_cast<const float *>(mbase + off_w);
+    for (const HostStep &hs : hsteps) {
+        // grid.y carries the job index: split launches above the 65535 limit
+        for (uint32_t o = 0; o < hs.g.n_jobs; o += 65535) {
+            fanlin_batch::Step st;
+            st.kind = hs.kind;
+            st.descs = reinterpret_cast<const StageDesc *>(mbase) + hs.first + o;
+            st.geom = hs.g;
+            st.geom.n_jobs = std::min<uint32_t>(65535, hs.g.n_jobs - o);
+            b->steps.push_back(st);
+            b->launches_per_run += st.kind == 0 ? 2 : 1;
+        }
+    }
+    *out = b.release();
+    return FANLIN_OK;
+}
+
+extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
+    if (!b) { set_error("fanlin: null batch"); return FANLIN_EINVAL; }
+    CUDA_TRY(cudaSetDevice(b->dev->ordinal));
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->dev->stream;
+    int n = 0;
+    for (const fanlin_batch::Step &s : b->steps) {
+        if (s.kind == 1) n += launch_compose(s.descs, s.geom, st);
+        else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, st);
+    }
+    CUDA_TRY(cudaGetLastError());
+    b->ctx->kernel_launches += uint64_t(n);
+    b->ctx->jobs += b->n_jobs;
+    b->ctx->batches += 1;
+    return FANLIN_OK;
+}
+
+extern "C" int fanlin_batch_launch_count(const fanlin_batch *b) { return b ? b->launches_per_run : 0; }
+
+// ---- host-buffer entry point -------------------------------------------------------
+
+namespace {
+
+// Runs jobs[first, last) (host pointers) on one device: stage in, launch, stage out.
+int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32_t n, fanlin_plan *plans) {
+    DeviceState *dev = ctx->devs[dev_index].get();
+    std::lock_guard<std::mutex> lk(dev->mu);
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    std::vector<fanlin_job> djobs(jobs, jobs + n);
+    std::vector<fanlin_plan> pl(n);
+    size_t in_bytes = 0, out_bytes = 0;
+    std::vector<size_t> in_off(n), out_off(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const int rc = fanlin_plan_job(&jobs[i], &pl[i]);
+        if (rc != FANLIN_OK) return rc;
+        if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
+        if (jobs[i].dst_capacity < pl[i].out_bytes) { set_error("fanlin: dst_capacity smaller than the planned output"); return FANLIN_ECAPACITY; }
+        in_off[i] = in_bytes;
+        in_bytes += align_up(size_t(jobs[i].src_w) * jobs[i].src_channels * jobs[i].src_h, 256);
+        out_off[i] = out_bytes;
+        out_bytes += align_up(pl[i].out_bytes, 256);
+    }
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_in), in_bytes + 256, dev->stream));
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_out), out_bytes + 256, dev->stream));
+    int rc = FANLIN_OK;
+    fanlin_batch *batch = nullptr;
+    do {
+        for (uint32_t i = 0; i < n && rc == FANLIN_OK; i++) {
+            const size_t row = size_t(jobs[i].src_w) * jobs[i].src_channels;
+            const size_t pitch = jobs[i].src_pitch ? jobs[i].src_pitch : row;
+            cudaError_t e = cudaMemcpy2DAsync(d_in + in_off[i], row, jobs[i].src, pitch, row, jobs[i].src_h,
+                                              cudaMemcpyHostToDevice, dev->stream);
+            if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; }
+            djobs[i].src = d_in + in_off[i];
+            djobs[i].src_pitch = 0;
+            djobs[i].dst = d_out + out_off[i];
+            djobs[i].dst_capacity = pl[i].out_bytes;
+            ctx->h2d_bytes += row * jobs[i].src_h;
+        }
+        if (rc != FANLIN_OK) break;
+        rc = fanlin_batch_prepare(ctx, dev_index, djobs.data(), n, nullptr, &batch);
+        if (rc != FANLIN_OK) break;
+        rc = fanlin_batch_launch(batch, dev->stream);
+        if (rc != FANLIN_OK) break;
+        for (uint32_t i = 0; i < n; i++) {
+            cudaError_t e = cudaMemcpyAsync(jobs[i].dst, d_out + out_off[i], pl[i].out_bytes, cudaMemcpyDeviceToHost, dev->stream);
+            if (e != cudaSuccess) { set_error(std::string("fanlin: D2H failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; break; }
+            ctx->d2h_bytes += pl[i].out_bytes;
+        }
+    } while (false);
+    cudaError_t se = cudaStreamSynchronize(dev->stream);
+    if (rc == FANLIN_OK && se != cudaSuccess) {
+        set_error(std::string("fanlin: CUDA error: ") + cudaGetErrorString(se));
+        rc = FANLIN_ECUDA;
+    }
+    if (batch) fanlin_batch_free(batch);
+    cudaFreeAsync(d_in, dev->stream);
+    cudaFreeAsync(d_out, dev->stream);
+    if (rc == FANLIN_OK && plans) std::copy(pl.begin(), pl.end(), plans);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" int fanlin_run(fanlin_ctx *ctx, const fanlin_job *jobs, uint32_t n_jobs, fanlin_plan *plans) {
+    if (!ctx || (!jobs && n_jobs)) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
+    if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
+    if (n_jobs == 0) return FANLIN_OK;
+    const int nd = int(ctx->devs.size());
+    if (nd == 1 || n_jobs == 1) {
+        const int dev = nd == 1 ? 0 : int(ctx->rr++ % uint32_t(nd));
+        return run_on_device(ctx, dev, jobs, n_jobs, plans);
+    }
+    // shard by image index: contiguous blocks, one host thread per device, no collective
+    std::vector<std::thread> th;
+    std::vector<int> rcs(nd, FANLIN_OK);
+    std::vector<std::string> errs(nd);
+    const uint32_t per = (n_jobs + nd - 1) / nd;
+    for (int d = 0; d < nd; d++) {
+        const uint32_t lo = std::min<uint32_t>(n_jobs, d * per), hi = std::min<uint32_t>(n_jobs, lo + per);
+        if (lo == hi) continue;
+        th.emplace_back([&, d, lo, hi] {
+            rcs[d] = run_on_device(ctx, d, jobs + lo, hi - lo, plans ? plans + lo : nullptr);
+            if (rcs[d] != FANLIN_OK) errs[d] = get_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < nd; d++)
+        if (rcs[d] != FANLIN_OK) { set_error(errs[d]); return rcs[d]; }
+    return FANLIN_OK;
+}

@@ -1,0 +1,77 @@
+// Context, per-device state and prepared batches.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "kernels.h"
+#include "plan.h"
+
+namespace fanlin {
+
+// Size-class pool of pinned host buffers (cudaHostAlloc is milliseconds; reuse).
+class PinnedPool {
+   public:
+    ~PinnedPool();
+    void *alloc(size_t bytes);
+    void free(void *p);
+    bool owns(const void *p, size_t bytes);
+    void set_limit(size_t bytes) { limit_ = bytes; }
+
+   private:
+    std::mutex mu_;
+    std::map<size_t, std::vector<void *>> free_;  // class size -> buffers
+    std::map<const void *, size_t> live_;         // base -> class size
+    size_t cached_ = 0, limit_ = size_t(2) << 30;
+};
+
+struct Request;
+
+struct DeviceState {
+    int ordinal = 0;
+    cudaStream_t stream = nullptr;   // context stream (prepare uploads, default launches)
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    std::mutex mu;                   // serialises host-path batches on this device
+    // request batcher
+    std::mutex qmu;
+    std::condition_variable qcv;
+    std::deque<Request *> queue;
+    std::thread worker;
+    bool stop = false;
+};
+
+}  // namespace fanlin
+
+struct fanlin_ctx {
+    std::vector<std::unique_ptr<fanlin::DeviceState>> devs;
+    fanlin_config cfg{};
+    fanlin::PinnedPool pinned;
+    std::atomic<uint64_t> kernel_launches{0}, jobs{0}, batches{0}, h2d_bytes{0}, d2h_bytes{0};
+    std::atomic<uint32_t> rr{0};
+    std::atomic<bool> down{false};
+};
+
+struct fanlin_batch {
+    fanlin_ctx *ctx = nullptr;
+    fanlin::DeviceState *dev = nullptr;
+    uint32_t n_jobs = 0;
+    std::vector<fanlin::JobPlan> plans;
+    struct Step {
+        int kind;  // 0 separable exact, 1 compose, 2 separable fast
+        const fanlin::StageDesc *descs;
+        fanlin::LaunchGeom geom;
+    };
+    std::vector<Step> steps;
+    void *d_meta = nullptr;     // descriptors + tables
+    void *d_scratch = nullptr;  // intermediates (reused across chunks)
+    const fanlin::TapEntry *d_tab = nullptr;
+    const float *d_w = nullptr;
+    int launches_per_run = 0;
+};

@@ -1,0 +1,55 @@
+"""Host-side mirror of the reference's two callers of the stage:
+process_image's pixel section (src/handler.rs:224-255) and process_gif's
+per-frame closure (src/handler.rs:321-357).  Decode and encode stay outside; these
+take and return decoded pixels, like the DynamicImage the Rust code holds."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .device import Device, Job, lib, plan_job
+from .query import Query
+
+
+def _as_img(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    if a.ndim != 3 or not 1 <= a.shape[2] <= 4:
+        raise ValueError("image must be (H, W) or (H, W, C<=4) u8")
+    return a
+
+
+def make_job(img: np.ndarray, params: Query, *, gif: bool = False) -> Job:
+    a = _as_img(img)
+    j = Job()
+    lib().fanlin_job_from_query(C.byref(params._q), int(gif), C.byref(j))
+    j.src = a.ctypes.data
+    j.src_h, j.src_w, j.src_channels = a.shape
+    j._keep = a
+    return j
+
+
+def _run(dev: Device, jobs):
+    outs = []
+    for j in jobs:
+        p = plan_job(j)
+        o = np.empty((p.out_h, p.out_w, p.out_channels), np.uint8)
+        j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
+        outs.append(o)
+    arr = (Job * len(jobs))()
+    for i, j in enumerate(jobs):
+        C.memmove(C.byref(arr, i * C.sizeof(Job)), C.byref(j), C.sizeof(Job))
+    dev.run(arr)
+    return outs
+
+
+def process_image(dev: Device, img: np.ndarray, params: Query) -> np.ndarray:
+    """Pixel section of State::process_image: decoded pixels in, transformed pixels out."""
+    return _run(dev, [make_job(img, params)])[0]
+
+
+def process_gif_frames(dev: Device, frames, params: Query):
+    """All composited RGBA8 frames of a GIF in one ragged launch; RGBA8 frames out."""
+    return _run(dev, [make_job(f, params, gif=True) for f in frames])

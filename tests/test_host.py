@@ -1,0 +1,161 @@
+"""CPU-side tests of the product's host logic: the C-ABI library loads and exports
+every symbol include/fanlin_device.h declares, the query::Query mirror follows the
+reference's own test table (src/query.rs:100-405), and the planner reproduces the
+oracle's output geometry.  No compute calls: there is no GPU here."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from synth import synth_image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(fanlin):
+    hdr = open(os.path.join(ROOT, "include", "fanlin_device.h")).read()
+    names = re.findall(r"FANLIN_API [^;(]*?\b(fanlin_\w+)\(", hdr)
+    assert len(names) >= 20
+    L = C.CDLL(fanlin.lib_path())
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.fanlin_abi_version() == 1
+
+
+def test_no_device_is_an_error_not_a_fallback(fanlin):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(fanlin.FanlinError) as ei:
+        fanlin.Device([0])
+    assert ei.value.status == 5  # FANLIN_ENODEVICE
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "fanlin-rs_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                assert "oracle" not in txt.lower(), os.path.join(dp, fn)
+
+
+# ---- query::Query mirror: the reference's table, src/query.rs:108-381 -------------
+
+U = "http://127.0.0.1:3000"
+QUERY_CASES = [
+    (U, False, {}, dict(dimensions=None, fill_color=(32, 32, 32), quality=75, cropping=False, blur=0.0, grayscale=False,
+                        inverse=False, use_avif=False, use_webp=False, as_is=True, unsupported_scale_size=False)),
+    (U + "?w=", True, {}, {}),
+    (U + "?unknown=1", False, {}, {}),
+    (U + "?w=2000&h=1000", False, dict(w=2000, h=1000), dict(dimensions=(2000, 1000), as_is=False, unsupported_scale_size=False)),
+    (U + "?w=1618", False, dict(w=1618), dict(dimensions=None, as_is=True, unsupported_scale_size=False)),
+    (U + "?w=2001&h=1001", False, dict(w=2001, h=1001), dict(dimensions=(2001, 1001), as_is=False, unsupported_scale_size=True)),
+    (U + "?w=foo&h=bar", True, {}, {}),
+    (U + "?rgb=255,255,255", False, dict(rgb="255,255,255"), dict(fill_color=(255, 255, 255), as_is=True)),
+    (U + "?rgb=255,255,255,255", False, dict(rgb="255,255,255,255"), dict(fill_color=(255, 255, 255), as_is=True)),
+    (U + "?rgb=255,255", False, dict(rgb="255,255"), dict(fill_color=(32, 32, 32), as_is=True)),
+    (U + "?rgb=foo,bar,baz", False, dict(rgb="foo,bar,baz"), dict(fill_color=(32, 32, 32), as_is=True)),
+    (U + "?quality=50", False, dict(quality=50), dict(quality=50, as_is=True)),
+    (U + "?quality=foo", True, {}, {}),
+    (U + "?crop=true", False, dict(crop=True), dict(cropping=True, as_is=True)),
+    (U + "?crop=foo", True, {}, {}),
+    (U + "?blur=10", False, dict(blur=10), dict(blur=10.0, as_is=False)),
+    (U + "?blur=foo", True, {}, {}),
+    (U + "?grayscale=true", False, dict(grayscale=True), dict(grayscale=True, as_is=False)),
+    (U + "?grayscale=foo", True, {}, {}),
+    (U + "?inverse=true", False, dict(inverse=True), dict(inverse=True, as_is=False)),
+    (U + "?inverse=foo", True, {}, {}),
+    (U + "?avif=true", False, dict(avif=True), dict(use_avif=True, as_is=False)),
+    (U + "?avif=foo", True, {}, {}),
+    (U + "?webp=true", False, dict(webp=True), dict(use_webp=True, as_is=False)),
+    (U + "?webp=foo", True, {}, {}),
+]
+
+
+@pytest.mark.parametrize("uri,error,want,asserts", QUERY_CASES, ids=[c[0][len(U):] or "none" for c in QUERY_CASES])
+def test_query(fanlin, uri, error, want, asserts):
+    got, err = fanlin.Query.try_from_uri(uri)
+    if error:
+        assert got is None and err is not None, uri
+        return
+    assert err is None, uri
+    assert got.fields() == want
+    for name, val in asserts.items():
+        assert getattr(got, name)() == val, (uri, name)
+
+
+def test_query_blur_clamps_and_rgb_quirks(fanlin):
+    Q = fanlin.Query
+    assert Q("blur=1").blur() == 10.0 and Q("blur=15").blur() == 15.0 and Q("blur=200").blur() == 20.0  # query.rs:59-62
+    assert Q.try_from_uri("?blur=256")[0] is None  # u8 overflow is a parse error
+    assert Q("rgb=1,foo,3").fill_color() == (1, 32, 3)
+    assert Q("rgb=256,0,0").fill_color() == (32, 0, 0)
+    assert Q("rgb=10%2C20%2C30").fill_color() == (10, 20, 30)
+
+
+# ---- planner vs oracle geometry -------------------------------------------------------
+
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["cases"]
+
+
+def _qs(p):
+    parts = []
+    for k in ("w", "h"):
+        if k in p:
+            parts.append(f"{k}={p[k]}")
+    if "rgb" in p:
+        parts.append("rgb=" + ",".join(map(str, p["rgb"])))
+    if p.get("crop"):
+        parts.append("crop=true")
+    if p.get("blur"):
+        parts.append(f"blur={int(p['blur'])}")
+    if p.get("grayscale"):
+        parts.append("grayscale=true")
+    if p.get("inverse"):
+        parts.append("inverse=true")
+    return "&".join(parts)
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+def test_plan_matches_oracle_geometry(fanlin, case):
+    if case["input"] == "lenna":
+        h, w, c = 512, 512, 3
+    else:
+        _, h, w, c = case["input"]
+    img = np.zeros((h, w, c), np.uint8)
+    j = fanlin.make_job(img, fanlin.Query(_qs(case["params"])), gif=case["params"].get("gif", False))
+    p = fanlin.plan_job(j)
+    assert (p.out_h, p.out_w, p.out_channels) == (case["out_h"], case["out_w"], case["out_c"])
+    assert p.out_bytes == case["out_h"] * case["out_w"] * case["out_c"]
+
+
+@pytest.mark.parametrize("src,c,qs,alg", [
+    ((1920, 1080), 3, "w=300&h=200", 6460800),            # C2
+    ((512, 512), 3, "w=300&h=200&rgb=32,32,32", 1026432),  # C1
+    ((3840, 2160), 4, "w=1618&h=1000&crop=true&blur=10", 36763840),  # C3: cols 167..3672
+    ((4000, 3000), 3, "w=1618&h=1000&crop=true&grayscale=true&blur=10", 31426000),  # C5 crop
+    ((4000, 3000), 3, "w=1618&h=1000&grayscale=true&blur=10", 42472000),  # C5 fit
+])
+def test_algorithmic_bytes_match_survey(fanlin, src, c, qs, alg):
+    j = fanlin.Job()
+    C.memset(C.byref(j), 0, C.sizeof(j))
+    q = fanlin.Query(qs)
+    fanlin.lib().fanlin_job_from_query(C.byref(q._q), 0, C.byref(j))
+    j.src_w, j.src_h, j.src_channels = src[0], src[1], c
+    assert fanlin.plan_job(j).algorithmic_bytes == alg
+
+
+def test_plan_rejects_bad_jobs(fanlin):
+    j = fanlin.Job()
+    j.src_w, j.src_h, j.src_channels = 0, 10, 3
+    with pytest.raises(fanlin.FanlinError):
+        fanlin.plan_job(j)
+    j.src_w, j.src_channels = 10, 5
+    with pytest.raises(fanlin.FanlinError):
+        fanlin.plan_job(j)

@@ -1,0 +1,159 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star): crop, fill, grayscale, inverse and Nearest are
+bit-exact; Lanczos3 resize and blur are within 1 LSB per u8 channel, with the
+mismatch histogram reported.  The context's `exact` mode must be bit-exact
+everywhere (same operation order as the crate, no FMA contraction)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from synth import synth_image
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["cases"]
+
+
+def _qs(p):
+    parts = []
+    for k in ("w", "h"):
+        if k in p:
+            parts.append(f"{k}={p[k]}")
+    if "rgb" in p:
+        parts.append("rgb=" + ",".join(map(str, p["rgb"])))
+    if p.get("crop"):
+        parts.append("crop=true")
+    if p.get("blur"):
+        parts.append(f"blur={int(p['blur'])}")
+    if p.get("grayscale"):
+        parts.append("grayscale=true")
+    if p.get("inverse"):
+        parts.append("inverse=true")
+    return "&".join(parts)
+
+
+def _okw(params):
+    return {k: (tuple(v) if k == "rgb" else v) for k, v in params.items()}
+
+
+def _input(spec, lenna):
+    if spec == "lenna":
+        return lenna
+    seed, h, w, c = spec
+    return synth_image(seed, h, w, c)
+
+
+def hist(a, b):
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    return {0: int((d == 0).sum()), 1: int((d == 1).sum()), ">=2": int((d >= 2).sum())}
+
+
+@pytest.fixture(scope="module")
+def dev_exact(fanlin):
+    d = fanlin.Device([0], exact=True)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
+def dev(fanlin):
+    d = fanlin.Device([0])
+    yield d
+    d.close()
+
+
+def _is_interp(params):
+    """Lanczos3 or blur on the path -> 1-LSB bar; everything else bit-exact."""
+    return (not params.get("gif")) and (("w" in params and "h" in params) or params.get("blur", 0) > 0)
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+def test_golden_cases_exact_mode_bit_exact(fanlin, dev_exact, lenna, case):
+    img = _input(case["input"], lenna)
+    got = fanlin.process_image(dev_exact, img, fanlin.Query(_qs(case["params"]))) if not case["params"].get("gif") \
+        else fanlin.process_gif_frames(dev_exact, [img], fanlin.Query(_qs(case["params"])))[0]
+    assert got.shape == (case["out_h"], case["out_w"], case["out_c"])
+    assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256"], hist(got, O.process(img, **_okw(case["params"])))
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+def test_golden_cases_fast_mode(fanlin, dev, lenna, case):
+    img = _input(case["input"], lenna)
+    want = O.process(img, **_okw(case["params"]))
+    got = fanlin.process_image(dev, img, fanlin.Query(_qs(case["params"]))) if not case["params"].get("gif") \
+        else fanlin.process_gif_frames(dev, [img], fanlin.Query(_qs(case["params"])))[0]
+    assert got.shape == want.shape
+    h = hist(got, want)
+    print(case["name"], "mismatch histogram", h)
+    if _is_interp(case["params"]):
+        assert h[">=2"] == 0, h
+    else:
+        assert h[1] == 0 and h[">=2"] == 0, h
+
+
+def test_ragged_batch_one_call(fanlin, dev):
+    """Many differently-shaped jobs in one fanlin_run: per-image descriptors."""
+    import ctypes as C
+
+    rng = np.random.default_rng(5)
+    qs = ["w=64&h=48", "w=50&h=50&crop=true", "w=80&h=30&rgb=1,2,3&grayscale=true", "blur=10", "inverse=true",
+          "w=33&h=77&crop=true&blur=12", "w=120&h=90&inverse=true", "grayscale=true"]
+    imgs, jobs, outs, wants = [], [], [], []
+    for i in range(24):
+        h, w, c = int(rng.integers(20, 140)), int(rng.integers(20, 140)), int(rng.integers(1, 5))
+        img = synth_image(900 + i, h, w, c)
+        q = fanlin.Query(qs[i % len(qs)])
+        j = fanlin.make_job(img, q)
+        p = fanlin.plan_job(j)
+        o = np.zeros((p.out_h, p.out_w, p.out_channels), np.uint8)
+        j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
+        imgs.append(img); jobs.append(j); outs.append(o)
+        kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+        if q.dimensions():
+            kw["w"], kw["h"] = q.dimensions()
+        wants.append(O.process(img, **kw))
+    dev.run(jobs)
+    for o, wnt, q in zip(outs, wants, [qs[i % len(qs)] for i in range(24)]):
+        assert o.shape == wnt.shape
+        h = hist(o, wnt)
+        assert h[">=2"] == 0, (q, h)
+
+
+def test_gif_frame_batch_c4(fanlin, dev):
+    """C4: 200 frames 480x270 RGBA, literal request (w only -> no resize; grayscale wins) and C4' with h."""
+    frames = [synth_image(4000 + i, 270, 480, 4) for i in range(200)]
+    for qs, kw in [("w=200&grayscale=true&inverse=true", dict(grayscale=True, inverse=True)),
+                   ("w=200&h=113&grayscale=true&inverse=true", dict(w=200, h=113, grayscale=True, inverse=True)),
+                   ("w=200&h=200&inverse=true", dict(w=200, h=200, inverse=True))]:
+        gots = fanlin.process_gif_frames(dev, frames, fanlin.Query(qs))
+        for i in (0, 7, 15, 199):
+            assert np.array_equal(gots[i], O.process(frames[i], gif=True, **kw)), (qs, i)
+
+
+def test_errors_map_to_status_codes(fanlin, dev):
+    img = synth_image(1, 32, 32, 3)
+    j = fanlin.make_job(img, fanlin.Query("w=20&h=20"))
+    o = np.zeros(10, np.uint8)
+    j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
+    with pytest.raises(fanlin.FanlinError) as ei:
+        dev.run([j])
+    assert ei.value.status == 3  # FANLIN_ECAPACITY
+
+
+def test_full_size_c2_properties(fanlin, dev):
+    """C2 shape at full size (1080p -> 300x200): bars exact, interior within 1 LSB on a sample."""
+    imgs = [synth_image(2000 + i, 1080, 1920, 3) for i in range(4)]
+    q = fanlin.Query("w=300&h=200")
+    gots = [fanlin.process_image(dev, im, q) for im in imgs]
+    for im, g in zip(imgs, gots):
+        assert g.shape == (200, 300, 4)
+        assert (g[:15] == (32, 32, 32, 255)).all() and (g[184:] == (32, 32, 32, 255)).all()
+        assert (g[..., 3] == 255).all()
+    want = O.process(imgs[0], w=300, h=200)
+    h = hist(gots[0], want)
+    assert h[">=2"] == 0, h
