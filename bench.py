@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the pixel-transform stage (BASELINE.json metric: output Mpix/s of the
+fused resize+fill(+blur) pipeline, and % of HBM peak).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (config.workload): BASELINE.json configs[1] -- a batch of 4096 synthetic
+1920x1080 RGB images -> w=300&h=200 aspect-fit + letterbox fill, per GPU (weak
+scaling: every rank owns its own 4096 images; images are independent, so there is
+no collective on the data path).  A step is one pass of the stage over the batch.
+
+  value   device-resident throughput (inputs in HBM before the timed region),
+          CUDA events on the launching stream, max over ranks.
+  e2e     the same metric through the C ABI's blocking host entry point
+          (fanlin_run) with pinned HOST buffers: H2D of the inputs and D2H of the
+          results inside the timed region.
+  roofline  dominant kernel: algorithmic bytes per launch / its average device
+          time (CUDA events bracketing the kernel), against MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (C restatement of the image-crate path the
+          reference calls) on the host cores, on a bounded sample.
+`--impl reference` times that CPU path alone, as the reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SRC_W, SRC_H, SRC_C = 1920, 1080, 3
+REQ = "w=300&h=200"
+OUT_W, OUT_H, OUT_C = 300, 200, 4
+BATCH = 4096
+MPIX_PER_IMAGE = OUT_W * OUT_H / 1e6
+WORKLOAD = "C2: 4096 x 1920x1080 RGB -> w=300&h=200 fit + letterbox fill (RGBA8 300x200)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.p = gpu_index, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load: the upper half (idle samples before/after the region pull the median down)
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch_on_device(torch, n, seed, device):
+    """u8 noise blended 50/50 with a smooth gradient, generated on the device."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, SRC_H, SRC_W, SRC_C), dtype=torch.uint8, device=device)
+    yy = torch.arange(SRC_H, device=device, dtype=torch.int32).view(SRC_H, 1, 1)
+    xx = torch.arange(SRC_W, device=device, dtype=torch.int32).view(1, SRC_W, 1)
+    k = torch.arange(SRC_C, device=device, dtype=torch.int32).view(1, 1, SRC_C)
+    grad = (xx * (k + 1) * 255 // (SRC_W - 1) + yy * (3 - k % 3) * 255 // (SRC_H - 1)) % 511
+    grad = torch.where(grad > 255, 510 - grad, grad).to(torch.int16)
+    chunk = 64
+    for i in range(0, n, chunk):
+        m = min(chunk, n - i)
+        noise = torch.randint(0, 256, (m, SRC_H, SRC_W, SRC_C), dtype=torch.int16, device=device, generator=g)
+        out[i:i + m] = ((noise + grad + 1) // 2).to(torch.uint8)
+    return out
+
+
+def cpu_baseline(n_images, threads, steps=1):
+    """The CPU oracle on `n_images` C2 images over `threads` host threads; returns (Mpix/s, seconds/step)."""
+    import numpy as np
+    from oracle import oracle as O
+    from synth import synth_image
+
+    O.build()
+    base = [synth_image(2000 + i, SRC_H, SRC_W, SRC_C) for i in range(min(n_images, 8))]
+    imgs = [base[i % len(base)] for i in range(n_images)]
+    O.process_batch(imgs[:threads], n_threads=threads, w=OUT_W, h=OUT_H)  # warm-up (page faults, thread start)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        outs = O.process_batch(imgs, n_threads=threads, w=OUT_W, h=OUT_H)
+        ts.append(time.perf_counter() - t0)
+    assert outs[0].shape == (OUT_H, OUT_W, OUT_C)
+    dt = sum(ts) / len(ts)
+    return n_images * MPIX_PER_IMAGE / dt, dt
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU implementation of the path (the oracle port: the
+    image crate cannot be built here) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = max(16 * cores, 64)
+    for _ in range(args.warmup):
+        cpu_baseline(cores, cores)
+    v, dt = cpu_baseline(n, cores, steps=args.steps)
+    sample = f"{n} of the {BATCH} C2 images per step, one image per thread"
+    line = {
+        "impl": "reference", "metric": "output Mpix/s, fused resize+fill pipeline", "value": v, "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step (default: the C2 batch)")
+    ap.add_argument("--e2e-pool", type=int, default=1024, help="distinct pinned host images cycled by the e2e leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exact", action="store_true", help="bit-exact kernels (crate operation order)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import __graft_entry__ as G
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    pkg = G.load_package()
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=device)
+    peak, peak_src = load_peaks()
+    warm = max(args.warmup, 3)
+
+    dev = pkg.Device([local_rank], exact=args.exact)
+    n = args.batch
+    src = synth_batch_on_device(torch, n, 2000 + rank, device)
+    dst = torch.zeros((n, OUT_H, OUT_W, OUT_C), dtype=torch.uint8, device=device)
+    q = pkg.Query(REQ)
+    jobs = (pkg.Job * n)()
+    img_bytes, out_bytes = SRC_H * SRC_W * SRC_C, OUT_H * OUT_W * OUT_C
+    proto = pkg.Job()
+    pkg.lib().fanlin_job_from_query(C.byref(q._q), 0, C.byref(proto))
+    for i in range(n):
+        C.memmove(C.byref(jobs, i * C.sizeof(pkg.Job)), C.byref(proto), C.sizeof(pkg.Job))
+        jobs[i].src = src.data_ptr() + i * img_bytes
+        jobs[i].src_w, jobs[i].src_h, jobs[i].src_channels = SRC_W, SRC_H, SRC_C
+        jobs[i].dst = dst.data_ptr() + i * out_bytes
+        jobs[i].dst_capacity = out_bytes
+    batch = dev.prepare(jobs, 0)
+    alg_bytes = sum(p.algorithmic_bytes for p in batch.plans)
+    assert batch.plans[0].out_w == OUT_W and batch.plans[0].out_h == OUT_H and batch.plans[0].out_channels == OUT_C
+    stream = torch.cuda.Stream(device)  # a real handle: NULL would select the library's own stream
+    assert stream.cuda_stream != 0
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident leg ------------------------------------------------------------
+    batch.set_timing(True)
+    for _ in range(warm):
+        batch.launch(stream.cuda_stream)
+    torch.cuda.synchronize(device)
+    batch.kernel_times()  # drop the warm-up record
+    ktimes = {}
+    launches0 = dev.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    stream.synchronize()
+    ev[0].record(stream)
+    for s in range(args.steps):
+        batch.launch(stream.cuda_stream)
+        ev[s + 1].record(stream)
+    barrier()
+    clocks = sampler.stop()
+    for name, ms in batch.kernel_times():  # every kernel of the K timed launches, bracketed by events
+        ktimes.setdefault(name, []).append(ms)
+    total_ms = ev[0].elapsed_time(ev[-1])
+    gpu_launches = dev.stats()["kernel_launches"] - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n * MPIX_PER_IMAGE / (ms_per_step * 1e-3)
+
+    # parity spot check at full size: a few images of the batch against the oracle
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+
+        d2 = 0
+        d1 = 0
+        for i in (0, n // 2, n - 1):
+            want = O.process(src[i].cpu().numpy(), w=OUT_W, h=OUT_H)
+            got = dst[i].cpu().numpy()
+            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            d1 += int((d == 1).sum()); d2 += int((d >= 2).sum())
+        parity = {"images_checked": 3, "diff1": d1, "diff_ge2": d2}
+        assert d2 == 0, parity
+
+    # dominant kernel and its roofline
+    dom = max(ktimes, key=lambda k: sum(ktimes[k])) if ktimes else None
+    roofline = None
+    if dom:
+        avg_ms = sum(ktimes[dom]) / len(ktimes[dom])
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "kernel_share_of_step": avg_ms / ms_per_step,
+                    "all_kernels_ms": {k: sum(v) / len(v) for k, v in ktimes.items()}}
+    batch.set_timing(False)
+
+    # ---- end-to-end leg: pinned host buffers through fanlin_run ------------------------
+    e2e = None
+    if not args.no_e2e:
+        pool = min(args.e2e_pool, n)
+        hin = dev.host_alloc(pool * img_bytes)
+        hout = dev.host_alloc(n * out_bytes)
+        hin_t = torch.from_numpy(hin).view(pool, SRC_H, SRC_W, SRC_C)
+        hin_t.copy_(src[:pool])  # same synthetic images, now host-resident
+        hjobs = (pkg.Job * n)()
+        for i in range(n):
+            C.memmove(C.byref(hjobs, i * C.sizeof(pkg.Job)), C.byref(proto), C.sizeof(pkg.Job))
+            hjobs[i].src = hin.ctypes.data + (i % pool) * img_bytes
+            hjobs[i].src_w, hjobs[i].src_h, hjobs[i].src_channels = SRC_W, SRC_H, SRC_C
+            hjobs[i].dst = hout.ctypes.data + i * out_bytes
+            hjobs[i].dst_capacity = out_bytes
+        e_steps = max(1, min(args.steps, 5))
+        e_warm = 1
+        for _ in range(e_warm):
+            dev.run(hjobs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            dev.run(hjobs)
+        torch.cuda.synchronize(device)
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if dist:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * n * MPIX_PER_IMAGE * e_steps / dt, "unit": "Mpix/s",
+               "h2d_bytes_per_step": n * img_bytes, "d2h_bytes_per_step": n * out_bytes,
+               "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "host_pool_images": pool,
+               "api": "fanlin_run (C ABI), pinned host buffers from fanlin_host_alloc"}
+        got = hout[:out_bytes].reshape(OUT_H, OUT_W, OUT_C)
+        assert np.array_equal(got, dst[0].cpu().numpy()), "e2e output differs from the device-resident leg"
+        dev.host_free(hin)
+        dev.host_free(hout)
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        ns = max(16 * cores, 64)
+        v, dt = cpu_baseline(ns, cores)
+        cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
+               "sample": f"{ns} of the {n} C2 images, one image per thread, {dt:.2f} s"}
+
+    batch.free()
+    dev.close()
+    if rank == 0:
+        line = {
+            "metric": "output Mpix/s, fused resize+fill pipeline", "value": value, "unit": "Mpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images_per_gpu": n, "l2": "inputs (25.5 GB/GPU) larger than L2",
+                       "sharding": "by image index, no collective", "exact_mode": bool(args.exact),
+                       "hbm_frac_whole_step": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
+            "clocks": clocks, "parity": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

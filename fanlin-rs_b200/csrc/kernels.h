@@ -2,9 +2,34 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "common.h"
 
 namespace fanlin {
+
+// Stream plus optional event bracketing of every kernel (fanlin_batch_set_timing).
+struct LaunchCtx {
+    cudaStream_t st = nullptr;
+    std::vector<cudaEvent_t> *events = nullptr;  // pairs (begin, end) per kernel, grown on demand
+    std::vector<const char *> *names = nullptr;
+    size_t used = 0;
+    void begin(const char *name) {
+        if (!events) return;
+        while (events->size() < used + 2) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            events->push_back(e);
+        }
+        names->push_back(name);
+        cudaEventRecord((*events)[used], st);
+    }
+    void end() {
+        if (!events) return;
+        cudaEventRecord((*events)[used + 1], st);
+        used += 2;
+    }
+};
 
 struct LaunchGeom {
     uint32_t n_jobs;
@@ -15,8 +40,8 @@ struct LaunchGeom {
 // Exact path (crate operation order, no FMA contraction): vertical pass to an f32
 // intermediate in HBM, then horizontal pass + epilogue.  Returns kernels launched.
 int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const float *d_w, const LaunchGeom &g,
-                     cudaStream_t st);
+                     LaunchCtx &lc);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
-int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, cudaStream_t st);
+int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 
 }  // namespace fanlin

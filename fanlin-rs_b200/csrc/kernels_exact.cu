@@ -89,21 +89,33 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
 }  // namespace
 
 int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const float *d_w, const LaunchGeom &g,
-                     cudaStream_t st) {
+                     LaunchCtx &lc) {
     if (g.n_jobs == 0) return 0;
     const uint32_t vx = g.max_n_rows * ((g.max_n_sx + TX - 1) / TX);
     const uint32_t hx = g.max_canvas_h * ((g.max_canvas_w + TX - 1) / TX);
     int n = 0;
-    if (vx) { vpass_exact_kernel<<<dim3(vx, g.n_jobs), TX, 0, st>>>(d_descs, d_tab, d_w); n++; }
-    if (hx) { hpass_exact_kernel<<<dim3(hx, g.n_jobs), TX, 0, st>>>(d_descs, d_tab, d_w); n++; }
+    if (vx) {
+        lc.begin("vpass_exact_kernel");
+        vpass_exact_kernel<<<dim3(vx, g.n_jobs), TX, 0, lc.st>>>(d_descs, d_tab, d_w);
+        lc.end();
+        n++;
+    }
+    if (hx) {
+        lc.begin("hpass_exact_kernel");
+        hpass_exact_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs, d_tab, d_w);
+        lc.end();
+        n++;
+    }
     return n;
 }
 
-int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, cudaStream_t st) {
+int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0) return 0;
     const uint32_t hx = g.max_canvas_h * ((g.max_canvas_w + TX - 1) / TX);
     if (!hx) return 0;
-    compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, st>>>(d_descs);
+    lc.begin("compose_kernel");
+    compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs);
+    lc.end();
     return 1;
 }
 

@@ -235,6 +235,7 @@ extern "C" void fanlin_batch_free(fanlin_batch *b) {
     if (b->dev) cudaSetDevice(b->dev->ordinal);
     if (b->d_meta) cudaFree(b->d_meta);
     if (b->d_scratch) cudaFree(b->d_scratch);
+    for (cudaEvent_t e : b->events) cudaEventDestroy(e);
     delete b;
 }
 
@@ -366,10 +367,18 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
     CUDA_TRY(cudaSetDevice(b->dev->ordinal));
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : b->dev->stream;
     int n = 0;
-    for (const fanlin_batch::Step &s : b->steps) {
-        if (s.kind == 1) n += launch_compose(s.descs, s.geom, st);
-        else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, st);
+    LaunchCtx lc;
+    lc.st = st;
+    if (b->timing) {  // events accumulate over launches until fanlin_batch_kernel_times reads them
+        lc.events = &b->events;
+        lc.names = &b->ev_names;
+        lc.used = b->ev_used;
     }
+    for (const fanlin_batch::Step &s : b->steps) {
+        if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
+        else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, lc);
+    }
+    if (b->timing) b->ev_used = lc.used;
     CUDA_TRY(cudaGetLastError());
     b->ctx->kernel_launches += uint64_t(n);
     b->ctx->jobs += b->n_jobs;
@@ -378,6 +387,26 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
 }
 
 extern "C" int fanlin_batch_launch_count(const fanlin_batch *b) { return b ? b->launches_per_run : 0; }
+
+extern "C" int fanlin_batch_set_timing(fanlin_batch *b, int enable) {
+    if (!b) return FANLIN_EINVAL;
+    b->timing = enable != 0;
+    return FANLIN_OK;
+}
+
+extern "C" int fanlin_batch_kernel_times(fanlin_batch *b, const char **names, float *ms, int cap) {
+    if (!b) return 0;
+    const int n = int(b->ev_used / 2);
+    for (int i = 0; i < n && i < cap; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, b->events[2 * i], b->events[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+        if (ms) ms[i] = t;
+        if (names) names[i] = b->ev_names[i];
+    }
+    b->ev_used = 0;
+    b->ev_names.clear();
+    return n;
+}
 
 // ---- host-buffer entry point -------------------------------------------------------
 

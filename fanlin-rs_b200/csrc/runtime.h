@@ -74,4 +74,8 @@ struct fanlin_batch {
     const fanlin::TapEntry *d_tab = nullptr;
     const float *d_w = nullptr;
     int launches_per_run = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> events;
+    std::vector<const char *> ev_names;
+    size_t ev_used = 0;
 };

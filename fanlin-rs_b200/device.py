@@ -98,6 +98,8 @@ def lib():
         L.fanlin_batch_launch_count.argtypes = [vp]
         L.fanlin_batch_free.argtypes = [vp]
         L.fanlin_batch_free.restype = None
+        L.fanlin_batch_set_timing.argtypes = [vp, C.c_int]
+        L.fanlin_batch_kernel_times.argtypes = [vp, P(C.c_char_p), P(C.c_float), C.c_int]
         L.fanlin_host_alloc.argtypes = [vp, C.c_size_t]
         L.fanlin_host_alloc.restype = vp
         L.fanlin_host_free.argtypes = [vp, vp]
@@ -142,6 +144,16 @@ class DeviceBatch:
     @property
     def launches_per_run(self) -> int:
         return lib().fanlin_batch_launch_count(self._h)
+
+    def set_timing(self, enable: bool = True):
+        check(lib().fanlin_batch_set_timing(self._h, int(enable)))
+
+    def kernel_times(self):
+        """[(kernel name, ms)] of the launches since the last call; synchronise their stream first."""
+        cap = 8192
+        names, ms = (C.c_char_p * cap)(), (C.c_float * cap)()
+        n = lib().fanlin_batch_kernel_times(self._h, names, ms, cap)
+        return [(names[i].decode(), float(ms[i])) for i in range(min(n, cap))]
 
     def free(self):
         if self._h:

@@ -128,6 +128,13 @@ FANLIN_API int fanlin_batch_launch(fanlin_batch *batch, void *cuda_stream);
 /* Kernels one launch enqueues, and the name-independent index of the dominant one. */
 FANLIN_API int fanlin_batch_launch_count(const fanlin_batch *batch);
 FANLIN_API void fanlin_batch_free(fanlin_batch *batch);
+/* Per-kernel device times of a batch (benchmarks): when enabled, fanlin_batch_launch
+ * brackets every kernel with CUDA events on the launching stream;
+ * fanlin_batch_kernel_times returns, after the caller synchronised that stream,
+ * the kernels launched since the previous call (name + milliseconds), up to cap,
+ * and resets the record; the return value is the number of kernels recorded. */
+FANLIN_API int fanlin_batch_set_timing(fanlin_batch *batch, int enable);
+FANLIN_API int fanlin_batch_kernel_times(fanlin_batch *batch, const char **names, float *ms, int cap);
 
 /* Pinned host buffers from the context's pool, so decoders can write pixels
  * where the copy engine can read them without a staging memcpy. */
