@@ -41,6 +41,10 @@ struct LaunchGeom {
 // intermediate in HBM, then horizontal pass + epilogue.  Returns kernels launched.
 int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const float *d_w, const LaunchGeom &g,
                      LaunchCtx &lc);
+// Fused separable resample (kernels_fused.cu); items of one (c, c_mem, colour op) variant.
+struct FusedItem;
+int launch_fused(const FusedItem *d_items, uint32_t n_items, uint32_t variant, uint32_t max_band_rows,
+                 const float *d_w, const uint32_t *d_info, LaunchCtx &lc);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 

@@ -3,6 +3,8 @@
 // an error status.
 #include "runtime.h"
 
+#include "fused.h"
+
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -252,7 +254,10 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     b->dev = dev;
     b->n_jobs = n_jobs;
     b->plans.resize(n_jobs);
-    const bool exact = true;  // fast kernels select themselves per stage below once present
+    const bool exact = ctx->cfg.exact != 0;
+    std::unique_ptr<FusedCache, void (*)(FusedCache *)> fcache(fused_cache_new(), fused_cache_free);
+    FusedTables ftabs;
+    std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A takes the fused resample kernel
 
     // 1. plans + table arena
     std::map<const AxisTable *, uint32_t> tab_base;
@@ -274,8 +279,10 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
             return FANLIN_ECAPACITY;
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
-        add_table(b->plans[i].a.vtab); add_table(b->plans[i].a.htab);
-        add_table(b->plans[i].b.vtab); add_table(b->plans[i].b.htab);
+        const JobPlan &p = b->plans[i];
+        fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
+        if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
+        add_table(p.b.vtab); add_table(p.b.htab);
     }
 
     // 2. scratch layout, chunked so one chunk fits the scratch budget
@@ -288,8 +295,8 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
             const JobPlan &p = b->plans[i];
             if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_w) * p.a.canvas_h * p.a.c_out, 256);
             size_t ta = 0, tb = 0;
-            if (exact && p.a.present && p.a.separable) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
-            if (exact && p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;
+            if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
+            if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;
             js[i].tmp = align_up(std::max(ta, tb), 256);
             const size_t need = js[i].inter + js[i].tmp;
             if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
@@ -307,17 +314,35 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
 
     // 3. descriptors per chunk and stage kind
     std::vector<StageDesc> descs;
-    struct HostStep { int kind; size_t first; LaunchGeom g; };
+    std::vector<FusedItem> fitems;
+    struct HostStep { int kind; size_t first; LaunchGeom g; uint32_t variant, n_items, max_band; };
     std::vector<HostStep> hsteps;
     uint32_t begin = 0;
     for (uint32_t end : chunk_end) {
-        for (int pass = 0; pass < 3; pass++) {  // 0: A separable, 1: A compose, 2: B separable
-            HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}};
+        // stage A through the fused kernel, one launch per (channels, colour op) variant
+        std::map<uint32_t, std::vector<uint32_t>> by_variant;
+        for (uint32_t i = begin; i < end; i++)
+            if (fused_a[i]) by_variant[fused_variant(b->plans[i].a)].push_back(i);
+        for (auto &kv : by_variant) {
+            HostStep hs{2, fitems.size(), LaunchGeom{}, kv.first, 0, 0};
+            for (uint32_t i : kv.second) {
+                const JobPlan &p = b->plans[i];
+                uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
+                const uint32_t pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
+                const int rc = fused_build(p.a, jobs[i].src, pitch, p.b.present ? inter : jobs[i].dst, fcache.get(), &ftabs, &fitems);
+                if (rc != FANLIN_OK) { set_error("fanlin: internal: fused tables"); return rc; }
+            }
+            hs.n_items = uint32_t(fitems.size() - hs.first);
+            for (size_t k = hs.first; k < fitems.size(); k++) hs.max_band = std::max(hs.max_band, fitems[k].band_rows);
+            if (hs.n_items) hsteps.push_back(hs);
+        }
+        for (int pass = 0; pass < 3; pass++) {  // 0: A separable (generic), 1: A compose, 2: B separable
+            HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}, 0, 0, 0};
             for (uint32_t i = begin; i < end; i++) {
                 const JobPlan &p = b->plans[i];
                 const StagePlan &s = pass == 2 ? p.b : p.a;
                 if (!s.present) continue;
-                if (pass == 0 && !s.separable) continue;
+                if (pass == 0 && (!s.separable || fused_a[i])) continue;
                 if (pass == 1 && s.separable) continue;
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 float *tmp = js[i].tmp ? reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off) : nullptr;
@@ -335,8 +360,14 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     // 4. upload descriptors + tables in one block
     const size_t off_tab = align_up(descs.size() * sizeof(StageDesc), 256);
     const size_t off_w = off_tab + align_up(entries.size() * sizeof(TapEntry), 256);
-    const size_t meta_bytes = off_w + align_up(weights.size() * sizeof(float), 256) + 256;
+    const size_t off_fi = off_w + align_up(weights.size() * sizeof(float), 256);
+    const size_t off_fw = off_fi + align_up(fitems.size() * sizeof(FusedItem), 256);
+    const size_t off_fn = off_fw + align_up(ftabs.w.size() * sizeof(float), 256);
+    const size_t meta_bytes = off_fn + align_up(ftabs.info.size() * sizeof(uint32_t), 256) + 256;
     std::vector<uint8_t> meta(meta_bytes, 0);
+    if (!fitems.empty()) std::memcpy(meta.data() + off_fi, fitems.data(), fitems.size() * sizeof(FusedItem));
+    if (!ftabs.w.empty()) std::memcpy(meta.data() + off_fw, ftabs.w.data(), ftabs.w.size() * sizeof(float));
+    if (!ftabs.info.empty()) std::memcpy(meta.data() + off_fn, ftabs.info.data(), ftabs.info.size() * sizeof(uint32_t));
     if (!descs.empty()) std::memcpy(meta.data(), descs.data(), descs.size() * sizeof(StageDesc));
     if (!entries.empty()) std::memcpy(meta.data() + off_tab, entries.data(), entries.size() * sizeof(TapEntry));
     if (!weights.empty()) std::memcpy(meta.data() + off_w, weights.data(), weights.size() * sizeof(float));
@@ -346,10 +377,23 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     const uint8_t *mbase = static_cast<const uint8_t *>(b->d_meta);
     b->d_tab = reinterpret_cast<const TapEntry *>(mbase + off_tab);
     b->d_w = reinterpret_cast<const float *>(mbase + off_w);
+    b->d_fw = reinterpret_cast<const float *>(mbase + off_fw);
+    b->d_finfo = reinterpret_cast<const uint32_t *>(mbase + off_fn);
     for (const HostStep &hs : hsteps) {
+        if (hs.kind == 2) {
+            fanlin_batch::Step st{};
+            st.kind = 2;
+            st.items = reinterpret_cast<const FusedItem *>(mbase + off_fi) + hs.first;
+            st.n_items = hs.n_items;
+            st.variant = hs.variant;
+            st.max_band = hs.max_band;
+            b->steps.push_back(st);
+            b->launches_per_run += 1;
+            continue;
+        }
         // grid.y carries the job index: split launches above the 65535 limit
         for (uint32_t o = 0; o < hs.g.n_jobs; o += 65535) {
-            fanlin_batch::Step st;
+            fanlin_batch::Step st{};
             st.kind = hs.kind;
             st.descs = reinterpret_cast<const StageDesc *>(mbase) + hs.first + o;
             st.geom = hs.g;
@@ -375,7 +419,11 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
         lc.used = b->ev_used;
     }
     for (const fanlin_batch::Step &s : b->steps) {
-        if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
+        if (s.kind == 2) {
+            const int k = launch_fused(s.items, s.n_items, s.variant, s.max_band, b->d_fw, b->d_finfo, lc);
+            if (k < 0) { set_error("fanlin: internal: no fused kernel variant"); return FANLIN_EINVAL; }
+            n += k;
+        } else if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
         else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, lc);
     }
     if (b->timing) b->ev_used = lc.used;

@@ -64,15 +64,19 @@ struct fanlin_batch {
     uint32_t n_jobs = 0;
     std::vector<fanlin::JobPlan> plans;
     struct Step {
-        int kind;  // 0 separable exact, 1 compose, 2 separable fast
+        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample
         const fanlin::StageDesc *descs;
         fanlin::LaunchGeom geom;
+        const fanlin::FusedItem *items;
+        uint32_t n_items, variant, max_band;
     };
     std::vector<Step> steps;
     void *d_meta = nullptr;     // descriptors + tables
     void *d_scratch = nullptr;  // intermediates (reused across chunks)
     const fanlin::TapEntry *d_tab = nullptr;
     const float *d_w = nullptr;
+    const float *d_fw = nullptr;        // fused scatter tables
+    const uint32_t *d_finfo = nullptr;
     int launches_per_run = 0;
     bool timing = false;
     std::vector<cudaEvent_t> events;
