@@ -94,12 +94,12 @@ static const GeomTab &geom_of(const StagePlan &s, FusedCache *cache, FusedTables
             std::vector<uint32_t> band_info(bt.n_y, 0u);
             ok = scatter(*s.vtab, o_first, bt.rows, o_first, bt.y0, bt.n_y, 0.f, nullptr, band_info.data());  // <= 8 live?
             if (!ok) break;
-            const uint32_t rpw = (bt.rows + FUSED_WARPS - 1) / FUSED_WARPS;
+            const uint32_t rq = bt.rows / FUSED_WARPS, rrem = bt.rows % FUSED_WARPS;  // balanced split
             uint32_t max_n = 0;
             struct WarpRange { uint32_t ra, rb, ya, yb; } wr[FUSED_WARPS];
             for (uint32_t w = 0; w < FUSED_WARPS; w++) {
-                wr[w].ra = std::min(w * rpw, bt.rows);
-                wr[w].rb = std::min((w + 1) * rpw, bt.rows);
+                wr[w].ra = w * rq + std::min(w, rrem);
+                wr[w].rb = wr[w].ra + rq + (w < rrem ? 1 : 0);
                 wr[w].ya = wr[w].yb = 0;
                 if (wr[w].rb > wr[w].ra) {
                     wr[w].ya = s.vtab->entries[o_first + wr[w].ra].left;

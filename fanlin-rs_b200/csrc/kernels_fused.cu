@@ -144,11 +144,26 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_kernel(const FusedItem *
         }
     }
 
+    // ---- item fields used inside the loops, in registers
+    const uint32_t pitch = it.src_pitch, chunk_px = it.chunk_px, n_px = it.n_px, n_chunks = it.n_chunks;
+
     // ---- vertical-stage role of this warp: a sub-band of output rows
     const uint32_t *vi = tinfo + it.vinfo_off + warp * it.vinfo_stride;
-    const uint32_t v_yrel = vi[0], v_ny = vi[1], v_r0 = vi[2];
+    const uint32_t v_ny = vi[1], v_r0 = vi[2];
     const float *vw = tw + vi[3];  // this warp's weights [v_ny][8]
-    const uint8_t *vsrc = it.src + size_t(it.y0 + v_yrel) * it.src_pitch;
+    const uint8_t *vsrc = it.src + size_t(it.y0 + vi[0]) * pitch;
+    constexpr int NW = Raw<C, CMEM>::NW;
+    constexpr uint32_t RW = ring_row_words(NW);            // words per ring row
+    constexpr uint32_t EB = (NW == 1 ? 1 : NW == 3 ? 3 : 2);  // source bytes per element
+    // ring row: [A words of the 32 lanes][B words of the 32 lanes] (4-byte lane stride: the
+    // cp.async writes stay bank-conflict free), then 8 weights + info
+    uint32_t *ring_w = ring + size_t(warp) * P * RW;
+    const uint32_t *ring_l = ring_w + lane * NW;
+    const uint32_t ring_sa = uint32_t(__cvta_generic_to_shared(ring_l));
+    const uint32_t tab_lane = lane < 9 ? lane : 8;  // lanes 0-7 copy the weights, lane 8 (and up, redundantly) the info word
+    const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(ring_w + 64 * NW + tab_lane));
+    const uint32_t *tab_g0 = tab_lane < 8 ? reinterpret_cast<const uint32_t *>(vw) + tab_lane : vi + 4;
+    const uint32_t tab_step = tab_lane < 8 ? S : 1;
 
     // ---- horizontal-stage role of this thread: one output row of the band
     const bool h_active = threadIdx.x < it.band_rows;
@@ -161,13 +176,13 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_kernel(const FusedItem *
     const float *hw = tw + it.hw_off;
     const uint32_t *hinfo = tinfo + it.hinfo_off;
     const float *trow = tmp + size_t(threadIdx.x) * XEP;
-    const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(it.chunk_px) * S);
-    const uint32_t cy = it.dst_y + it.band_r0 + threadIdx.x;
+    const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
+    const uint32_t h_cx0 = it.dst_x, h_cy = it.dst_y + it.band_r0 + threadIdx.x;
 
-    for (uint32_t chunk = 0; chunk < it.n_chunks; chunk++) {
-        const uint32_t cpx0 = chunk * it.chunk_px;                       // window-relative first pixel
-        const uint32_t npx = min(it.chunk_px, it.n_px - cpx0);
-        const uint32_t xe = (npx * C + 3) & ~3u;                          // elements, whole words
+    for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+        const uint32_t cpx0 = chunk * chunk_px;  // window-relative first pixel
+        const uint32_t npx = min(chunk_px, n_px - cpx0);
+        const uint32_t xe = (npx * C + 3) & ~3u;  // elements, whole words
         // the chunk's slice of the horizontal table -> shared memory (lands during the vertical stage)
         {
             const uint32_t sa_w = uint32_t(__cvta_generic_to_shared(hw_s)), sa_i = uint32_t(__cvta_generic_to_shared(hinfo_s));
@@ -177,84 +192,80 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_kernel(const FusedItem *
             cp_async_commit();
         }
         // ================= vertical stage =================
-        // Each warp streams the source rows of its sub-band top to bottom; lane l owns
-        // elements [4l, 4l+4) and [128+4l, 128+4l+4) of the chunk.  Loads run P rows
-        // ahead of the FMAs (register queue) to cover HBM latency with 8 warps per SM.
+        // Each warp streams the source rows of its sub-band top to bottom; lane l owns elements
+        // [4l, 4l+4) and [128+4l, 128+4l+4) of the chunk.  Rows are copied P ahead of the FMAs
+        // into the warp's ring with cp.async, together with that row's weights and info word.
         {
             const uint32_t e_row = (it.px0 + cpx0) * C;  // element index in the source row
             const uint32_t ea = 4 * lane, eb = 128 + 4 * lane;
             const bool a_on = ea < xe, b_on = eb < xe;
+            // lanes past the chunk copy (and ignore) a valid word instead of being predicated
+            const uint8_t *pa = vsrc + size_t(e_row + (a_on ? ea : 0)) * EB;
+            const uint8_t *pb = vsrc + size_t(e_row + (b_on ? eb : 0)) * EB;
+            const uint32_t *pt = tab_g0;
             float acc[S][8];
 #pragma unroll
             for (int j = 0; j < S; j++)
 #pragma unroll
                 for (int k = 0; k < 8; k++) acc[j][k] = 0.f;
             uint32_t next_r = v_r0;
-            // ring slot of this lane: [row p][A words | B words], NW words each
-            constexpr int NW = Raw<C, CMEM>::NW;
-            constexpr uint32_t RW = ring_row_words(NW);
-            uint32_t *ring_w = ring + size_t(warp) * P * RW;  // this warp's ring
-            uint32_t *ring_l = ring_w + lane * NW;
-            const uint32_t ring_sa = uint32_t(__cvta_generic_to_shared(ring_l));
-            const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(ring_w + 64 * NW + lane));
-            const uint32_t *tab_g = lane < 8 ? reinterpret_cast<const uint32_t *>(vw) + lane : vi + 4;  // lanes 0-7 weights, lane 8 info
-            const uint32_t tab_step = lane < 8 ? S : 1;
 #pragma unroll
             for (int p = 0; p < P; p++) {
-                const bool on = uint32_t(p) < v_ny;
-                const uint8_t *nrow = vsrc + size_t(p) * it.src_pitch;
-                fetch4_async<C, CMEM>(ring_sa + p * RW * 4, nrow, e_row + ea, on && a_on);
-                fetch4_async<C, CMEM>(ring_sa + (p * RW + 32 * NW) * 4, nrow, e_row + eb, on && b_on);
-                cp_async4(tab_sa + p * RW * 4, tab_g + size_t(p) * tab_step, on && lane < 9);
+                if (uint32_t(p) < v_ny) {
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        cp_async4(ring_sa + (p * RW + k) * 4, pa + 4 * k, true);
+                        cp_async4(ring_sa + (p * RW + 32 * NW + k) * 4, pb + 4 * k, true);
+                    }
+                    cp_async4(tab_sa + p * RW * 4, pt, true);
+                    pa += pitch; pb += pitch; pt += tab_step;
+                }
                 cp_async_commit();
             }
-            for (uint32_t i0 = 0; i0 < v_ny; i0 += P) {
+            uint32_t slot = 0;  // word offset of row i in the ring
+#pragma unroll 2
+            for (uint32_t i = 0; i < v_ny; i++) {
+                cp_async_wait<P - 1>();  // the group of row i has landed
+                Raw<C, CMEM> qa, qb;
+                read4<C, CMEM>(ring_l + slot, qa);
+                read4<C, CMEM>(ring_l + slot + 32 * NW, qb);
+                const uint32_t *trow_s = ring_w + slot + 64 * NW;
+                const float4 w0 = *reinterpret_cast<const float4 *>(trow_s);
+                const float4 w1 = *reinterpret_cast<const float4 *>(trow_s + 4);
+                const uint32_t info = trow_s[8];
+                float f[8];
+                decode4<C, CMEM, OP>(qa, f);
+                decode4<C, CMEM, OP>(qb, f + 4);
+                if (i + P < v_ny) {  // refill this slot with row i + P (the reads above are consumed)
 #pragma unroll
-                for (int p = 0; p < P; p++) {
-                    const uint32_t i = i0 + p;
-                    if (i < v_ny) {
-                        cp_async_wait<P - 1>();  // the group of row i has landed
-                        Raw<C, CMEM> qa, qb;
-                        read4<C, CMEM>(ring_l + p * RW, qa);
-                        read4<C, CMEM>(ring_l + p * RW + 32 * NW, qb);
-                        const uint32_t *trow_s = ring_w + p * RW + 64 * NW;
-                        const float4 w0 = *reinterpret_cast<const float4 *>(trow_s);
-                        const float4 w1 = *reinterpret_cast<const float4 *>(trow_s + 4);
-                        const uint32_t info = trow_s[8];
-                        float f[8];
-                        decode4<C, CMEM, OP>(qa, f);
-                        decode4<C, CMEM, OP>(qb, f + 4);
-                        if (!a_on) { f[0] = f[1] = f[2] = f[3] = 0.f; }
-                        if (!b_on) { f[4] = f[5] = f[6] = f[7] = 0.f; }
-                        {   // refill this slot with row i + P (after the reads above have been consumed)
-                            const bool on = i + P < v_ny;
-                            const uint8_t *nrow = vsrc + size_t(i + P) * it.src_pitch;
-                            fetch4_async<C, CMEM>(ring_sa + p * RW * 4, nrow, e_row + ea, on && a_on);
-                            fetch4_async<C, CMEM>(ring_sa + (p * RW + 32 * NW) * 4, nrow, e_row + eb, on && b_on);
-                            cp_async4(tab_sa + p * RW * 4, tab_g + size_t(i + P) * tab_step, on && lane < 9);
-                            cp_async_commit();
-                        }
-                        const float w[S] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    for (int k = 0; k < NW; k++) {
+                        cp_async4(ring_sa + (slot + k) * 4, pa + 4 * k, true);
+                        cp_async4(ring_sa + (slot + 32 * NW + k) * 4, pb + 4 * k, true);
+                    }
+                    cp_async4(tab_sa + slot * 4, pt, true);
+                    pa += pitch; pb += pitch; pt += tab_step;
+                }
+                cp_async_commit();
+                slot = slot + RW == P * RW ? 0 : slot + RW;
+                const float w[S] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                        for (int j = 0; j < S; j++)  // dead slots carry weight 0 and an accumulator at 0
+                for (int j = 0; j < S; j++)  // dead slots carry weight 0 and an accumulator at 0
 #pragma unroll
-                            for (int k = 0; k < 8; k++) acc[j][k] = fmaf(f[k], w[j], acc[j][k]);
-                        const uint32_t fl = (info >> 8) & 0xffu;
-                        if (fl) {
+                    for (int k = 0; k < 8; k++) acc[j][k] = fmaf(f[k], w[j], acc[j][k]);
+                const uint32_t fl = (info >> 8) & 0xffu;
+                if (fl) {
 #pragma unroll
-                            for (int j = 0; j < S; j++) {
-                                if (fl & (1u << j)) {
-                                    const uint32_t r = next_r + ((uint32_t(j) - next_r) & (S - 1));
-                                    float *t = tmp + size_t(r) * XEP;
-                                    if (a_on) *reinterpret_cast<float4 *>(t + ea) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                                    if (b_on) *reinterpret_cast<float4 *>(t + eb) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+                    for (int j = 0; j < S; j++) {
+                        if (fl & (1u << j)) {
+                            const uint32_t r = next_r + ((uint32_t(j) - next_r) & (S - 1));
+                            float *t = tmp + size_t(r) * XEP;
+                            if (a_on) *reinterpret_cast<float4 *>(t + ea) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                            if (b_on) *reinterpret_cast<float4 *>(t + eb) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
 #pragma unroll
-                                    for (int k = 0; k < 8; k++) acc[j][k] = 0.f;
-                                }
-                            }
-                            next_r += __popc(fl);
+                            for (int k = 0; k < 8; k++) acc[j][k] = 0.f;
                         }
                     }
+                    next_r += __popc(fl);
                 }
             }
         }
@@ -273,7 +284,6 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_kernel(const FusedItem *
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     if (xl + g >= npx) break;
-                    const uint32_t xw = cpx0 + xl + g;
                     const uint32_t info = hinfo_s[xl + g];
                     const float4 w0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl + g) * S);
                     const float4 w1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl + g) * S + 4);
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_kernel(const FusedItem *
                                 uint32_t u[4] = {0, 0, 0, 0};
 #pragma unroll
                                 for (int k = 0; k < C; k++) { u[k] = round_u8(hacc[j][k]); hacc[j][k] = 0.f; }
-                                emit_px<C>(it, it.dst_x + o, cy, u);
+                                emit_px<C>(it, h_cx0 + o, h_cy, u);
                             }
                         }
                         h_next += __popc(fl);
