@@ -132,6 +132,18 @@ def cpu_baseline(n_images, threads, steps=1):
     return n_images * MPIX_PER_IMAGE / dt, dt
 
 
+def reduce_timing(ms_total_local, steps, images_per_rank, world, dist, device):
+    """Max over ranks of the device time, and the whole-job aggregate it implies (weak scaling:
+    every rank processed images_per_rank per step).  Returns (ms_per_step, Mpix/s)."""
+    import torch
+
+    t = torch.tensor([ms_total_local], dtype=torch.float64, device=device)
+    if dist is not None and world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / steps
+    return ms_per_step, world * images_per_rank * MPIX_PER_IMAGE / (ms_per_step * 1e-3)
+
+
 def run_reference(args, rank):
     """Reference arm: the reference's CPU implementation of the path (the oracle port: the
     image crate cannot be built here) on all host threads, bounded sample per step."""
@@ -243,12 +255,7 @@ def main():
         ktimes.setdefault(name, []).append(ms)
     total_ms = ev[0].elapsed_time(ev[-1])
     gpu_launches = dev.stats()["kernel_launches"] - launches0
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = world * n * MPIX_PER_IMAGE / (ms_per_step * 1e-3)
+    ms_per_step, value = reduce_timing(total_ms, args.steps, n, world, dist, device)
 
     # parity spot check at full size: a few images of the batch against the oracle
     parity = None

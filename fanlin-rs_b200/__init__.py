@@ -8,7 +8,7 @@ bench.py.  There is no CPU implementation in here: without the built library
 and a CUDA device every compute call raises.
 """
 from .device import (  # noqa: F401
-    Device, DeviceBatch, FanlinError, Job, Plan, lib, lib_path, plan_job, FILTER_LANCZOS3, FILTER_NEAREST,
+    Device, DeviceBatch, FanlinError, Job, Plan, lib, lib_path, plan_job, shard_range, FILTER_LANCZOS3, FILTER_NEAREST,
     GRAYSCALE, INVERSE, HAS_DIMS, CROP, TO_RGBA8,
 )
 from .query import Query  # noqa: F401

@@ -522,6 +522,15 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
 
 }  // namespace
 
+extern "C" void fanlin_shard_range(uint32_t n_jobs, uint32_t n_shards, uint32_t shard, uint32_t *lo, uint32_t *hi) {
+    if (n_shards == 0) n_shards = 1;
+    const uint32_t q = n_jobs / n_shards, r = n_jobs % n_shards;  // the first r shards take one more
+    const uint32_t a = shard < n_shards ? shard * q + std::min(shard, r) : n_jobs;
+    const uint32_t b = shard < n_shards ? a + q + (shard < r ? 1 : 0) : n_jobs;
+    if (lo) *lo = a;
+    if (hi) *hi = b;
+}
+
 extern "C" int fanlin_run(fanlin_ctx *ctx, const fanlin_job *jobs, uint32_t n_jobs, fanlin_plan *plans) {
     if (!ctx || (!jobs && n_jobs)) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
     if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
@@ -535,9 +544,9 @@ extern "C" int fanlin_run(fanlin_ctx *ctx, const fanlin_job *jobs, uint32_t n_jo
     std::vector<std::thread> th;
     std::vector<int> rcs(nd, FANLIN_OK);
     std::vector<std::string> errs(nd);
-    const uint32_t per = (n_jobs + nd - 1) / nd;
     for (int d = 0; d < nd; d++) {
-        const uint32_t lo = std::min<uint32_t>(n_jobs, d * per), hi = std::min<uint32_t>(n_jobs, lo + per);
+        uint32_t lo, hi;
+        fanlin_shard_range(n_jobs, uint32_t(nd), uint32_t(d), &lo, &hi);
         if (lo == hi) continue;
         th.emplace_back([&, d, lo, hi] {
             rcs[d] = run_on_device(ctx, d, jobs + lo, hi - lo, plans ? plans + lo : nullptr);

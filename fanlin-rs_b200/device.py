@@ -105,6 +105,8 @@ def lib():
         L.fanlin_host_free.argtypes = [vp, vp]
         L.fanlin_host_free.restype = None
         L.fanlin_get_stats.argtypes = [vp, P(Stats)]
+        L.fanlin_shard_range.argtypes = [u32, u32, u32, P(u32), P(u32)]
+        L.fanlin_shard_range.restype = None
         L.fanlin_last_error.restype = C.c_char_p
         L.fanlin_query_parse.argtypes = [C.c_char_p, P(QueryStruct)]
         L.fanlin_query_dimensions.argtypes = [P(QueryStruct), P(u32), P(u32)]
@@ -124,6 +126,13 @@ def lib():
 def check(rc: int):
     if rc != 0:
         raise FanlinError(rc, (lib().fanlin_last_error() or b"").decode())
+
+
+def shard_range(n_jobs: int, n_shards: int, shard: int):
+    """[lo, hi) of the images shard `shard` owns (fanlin_shard_range)."""
+    lo, hi = C.c_uint32(), C.c_uint32()
+    lib().fanlin_shard_range(n_jobs, n_shards, shard, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
 
 
 def plan_job(job: Job) -> Plan:

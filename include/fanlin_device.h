@@ -143,6 +143,11 @@ FANLIN_API void fanlin_host_free(fanlin_ctx *ctx, void *p);
 
 FANLIN_API int fanlin_get_stats(const fanlin_ctx *ctx, fanlin_stats *out);
 
+/* How fanlin_run (and bench.py across ranks) shards n_jobs independent images over
+ * n_shards devices: contiguous blocks by image index, no collective.
+ * Pure host. */
+FANLIN_API void fanlin_shard_range(uint32_t n_jobs, uint32_t n_shards, uint32_t shard, uint32_t *lo, uint32_t *hi);
+
 /* Thread-local message of the last failure on this thread. */
 FANLIN_API const char *fanlin_last_error(void);
 
