@@ -25,8 +25,10 @@ using GeomKey = std::tuple<const AxisTable *, const AxisTable *, uint32_t, uint3
 // Scatter view of outputs [o0, o0+n) of `t` over sources [s0, s0+n_s): weights
 // [n_s][8] (slot = (o - slot_base) % 8) and live/flush masks.  Returns false when
 // more than 8 outputs are live at one source index.
-bool scatter(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t slot_base, uint32_t s0, uint32_t n_s, float scale,
-             float *w, uint32_t *info) {
+}  // namespace
+
+bool fused_scatter(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t slot_base, uint32_t s0, uint32_t n_s, float scale,
+                   float *w, uint32_t *info) {
     for (uint32_t o = o0; o < o0 + n; o++) {
         const TapEntry &e = t.entries[o];
         const uint32_t slot = (o - slot_base) % FUSED_SLOTS;
@@ -41,8 +43,6 @@ bool scatter(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t slot_base, ui
     }
     return true;
 }
-
-}  // namespace
 
 struct FusedCache {
     std::map<GeomKey, GeomTab> geoms;
@@ -77,7 +77,7 @@ static const GeomTab &geom_of(const StagePlan &s, FusedCache *cache, FusedTables
         g.hinfo_off = uint32_t(tabs->info.size());
         tabs->w.resize(tabs->w.size() + size_t(g.n_px) * FUSED_SLOTS, 0.0f);
         tabs->info.resize(tabs->info.size() + g.n_px, 0u);
-        bool ok = scatter(*s.htab, s.ox0, s.n_cols, s.ox0, g.px0, g.n_px, hscale, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
+        bool ok = fused_scatter(*s.htab, s.ox0, s.n_cols, s.ox0, g.px0, g.n_px, hscale, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
         // vertical: per band, weights for the band and masks per warp sub-band
         const uint32_t max_band = fused_max_band(s.c, s.c_mem);
         const uint32_t n_bands = (s.n_rows + max_band - 1) / max_band;
@@ -92,7 +92,7 @@ static const GeomTab &geom_of(const StagePlan &s, FusedCache *cache, FusedTables
             for (uint32_t o = o_first; o <= o_last; o++) y1 = std::max(y1, s.vtab->entries[o].left + s.vtab->entries[o].count);
             bt.n_y = y1 - bt.y0;
             std::vector<uint32_t> band_info(bt.n_y, 0u);
-            ok = scatter(*s.vtab, o_first, bt.rows, o_first, bt.y0, bt.n_y, 0.f, nullptr, band_info.data());  // <= 8 live?
+            ok = fused_scatter(*s.vtab, o_first, bt.rows, o_first, bt.y0, bt.n_y, 0.f, nullptr, band_info.data());  // <= 8 live?
             if (!ok) break;
             const uint32_t rq = bt.rows / FUSED_WARPS, rrem = bt.rows % FUSED_WARPS;  // balanced split
             uint32_t max_n = 0;
@@ -124,7 +124,7 @@ static const GeomTab &geom_of(const StagePlan &s, FusedCache *cache, FusedTables
                 blk[2] = wr[w].ra;
                 blk[3] = uint32_t(woff);
                 if (n)
-                    ok = scatter(*s.vtab, o_first + wr[w].ra, wr[w].rb - wr[w].ra, o_first, wr[w].ya, n, vscale,
+                    ok = fused_scatter(*s.vtab, o_first + wr[w].ra, wr[w].rb - wr[w].ra, o_first, wr[w].ya, n, vscale,
                                  &tabs->w[woff], blk + 4);
             }
             g.bands.push_back(bt);

@@ -57,6 +57,12 @@ struct FusedTables {
     std::vector<uint32_t> info;
 };
 
+// Scatter view of outputs [o0, o0+n) of `t` over sources [s0, s0+n_s): weights [n_s][8]
+// (slot = (o - slot_base) % 8, times `scale`; w may be null) and live | flush << 8 masks.
+// False when more than 8 outputs are live at one source index.
+bool fused_scatter(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t slot_base, uint32_t s0, uint32_t n_s, float scale,
+                   float *w, uint32_t *info);
+
 // True when stage `s` of a job can take the fused path (downscale-ish taps that fit
 // 8 live outputs per source index, 4-byte aligned rows).
 bool fused_eligible(const StagePlan &s, const fanlin_job &job);

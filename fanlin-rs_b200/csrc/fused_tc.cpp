@@ -1,0 +1,171 @@
+// Host side of the tensor-core fused resample: bands, 32-row output groups, the
+// s8 digit tiles of the vertical weights and the horizontal scatter table.
+#include "fused_tc.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <tuple>
+
+namespace fanlin {
+
+namespace {
+
+struct TcBand {
+    uint32_t r0, rows, grp_off, n_groups, kg_max;
+};
+struct TcGeom {
+    bool ok = false;
+    uint32_t px0 = 0, n_px = 0, hw_off = 0, hinfo_off = 0;
+    float scale = 1.f;
+    std::vector<TcBand> bands;
+};
+using TcKey = std::tuple<const AxisTable *, const AxisTable *, uint32_t, uint32_t, uint32_t>;
+
+uint32_t r_pad_for(uint32_t rows) {
+    uint32_t r = (rows + 3) & ~3u;
+    while (r % 8 != 4) r += 4;
+    return r;
+}
+
+}  // namespace
+
+uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 128u : c == 2 ? 64u : c == 3 ? 40u : 32u; }
+
+size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
+    const size_t tmp = size_t(TC_M) * r_pad_for(band_rows) * 4;
+    const size_t a = 2 * size_t(kg_max) * TC_M, b = 2 * size_t(TC_N) * kg_max;
+    const size_t ht = (size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15);
+    return tmp + a + b + ht + 128;
+}
+
+uint32_t fused_tc_max_band(uint32_t c) {
+    const size_t limit = 232448 - 1024;
+    const size_t fixed = fused_tc_smem_bytes(c, 0, TC_KG_MAX);
+    const uint32_t rows = uint32_t((limit - fixed) / (TC_M * 4));
+    return std::min(192u, rows / TC_GROUP_ROWS * TC_GROUP_ROWS);
+}
+
+struct FusedTcCache {
+    std::map<TcKey, TcGeom> geoms;
+};
+FusedTcCache *fused_tc_cache_new() { return new FusedTcCache(); }
+void fused_tc_cache_free(FusedTcCache *c) { delete c; }
+
+bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
+    if (!s.present || !s.separable || !s.vtab || !s.htab) return false;
+    if (s.n_rows == 0 || s.n_cols == 0) return false;
+    if (s.v_kind != KIND_LANCZOS3) return false;  // Nearest is a gather (bit-exact on the CUDA-core path); blur has its own kernel
+    if (s.color_op != COLOR_NONE || s.c_mem != s.c) return false;
+    const uint32_t pitch = s.src_is_input ? (job.src_pitch ? job.src_pitch : job.src_w * job.src_channels) : s.in_w * s.c_mem;
+    if (pitch % 4 != 0) return false;
+    if ((uint64_t(s.in_w) * s.c) % 4 != 0) return false;
+    if (s.src_is_input && (reinterpret_cast<uintptr_t>(job.src) & 3)) return false;
+    // a 32-row output group must fit 256 source rows, and the horizontal pass 8 live outputs
+    const double ratio = double(s.in_h) / double(std::max(1u, s.v_out));
+    if ((TC_GROUP_ROWS - 1) * ratio + s.vtab->max_taps > TC_KG_MAX) return false;
+    if (s.htab->max_taps > 8 * std::max(1u, s.in_w / std::max(1u, s.h_out)) + 8) return false;
+    return true;
+}
+
+static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
+    const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c);
+    auto it = cache->geoms.find(key);
+    if (it != cache->geoms.end()) return it->second;
+    TcGeom g;
+    // horizontal: scatter table with true-scale weights (the tile holds true-scale f32)
+    g.px0 = s.sx0 / 4 * 4;
+    g.n_px = s.sx0 + s.n_sx - g.px0;
+    g.hw_off = uint32_t(tabs->w.size());
+    g.hinfo_off = uint32_t(tabs->info.size());
+    tabs->w.resize(tabs->w.size() + size_t(g.n_px) * FUSED_SLOTS, 0.0f);
+    tabs->info.resize(tabs->info.size() + g.n_px, 0u);
+    bool ok = fused_scatter(*s.htab, s.ox0, s.n_cols, s.ox0, g.px0, g.n_px, 1.0f, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
+    // vertical: q = round(w * 2^sh) split into three signed base-128 digits
+    float maxw = 0.f;
+    for (float w : s.vtab->weights) maxw = std::max(maxw, std::fabs(w));
+    int sh = 30;
+    while (sh > 0 && std::ldexp(double(maxw), sh) > 2080000.0) sh--;
+    g.scale = std::ldexp(1.0f, -sh);
+    const uint32_t max_band = fused_tc_max_band(s.c);
+    const uint32_t n_bands = (s.n_rows + max_band - 1) / max_band;
+    uint32_t band_rows = (s.n_rows + n_bands - 1) / n_bands;
+    band_rows = std::min(max_band, (band_rows + TC_GROUP_ROWS - 1) / TC_GROUP_ROWS * TC_GROUP_ROWS);
+    for (uint32_t b0 = 0; b0 < s.n_rows && ok; b0 += band_rows) {
+        TcBand bt{};
+        bt.r0 = b0;
+        bt.rows = std::min(band_rows, s.n_rows - b0);
+        bt.n_groups = (bt.rows + TC_GROUP_ROWS - 1) / TC_GROUP_ROWS;
+        bt.grp_off = uint32_t(tabs->info.size());
+        tabs->info.resize(tabs->info.size() + size_t(bt.n_groups) * 4, 0u);
+        for (uint32_t gi = 0; gi < bt.n_groups && ok; gi++) {
+            const uint32_t ra = gi * TC_GROUP_ROWS, rb = std::min(bt.rows, ra + TC_GROUP_ROWS);
+            const uint32_t o0 = s.oy0 + bt.r0 + ra;
+            const uint32_t k0 = s.vtab->entries[o0].left;
+            uint32_t k1 = 0;
+            for (uint32_t r = ra; r < rb; r++) {
+                const TapEntry &e = s.vtab->entries[s.oy0 + bt.r0 + r];
+                k1 = std::max(k1, e.left + e.count);
+            }
+            const uint32_t kg = (k1 - k0 + 31) / 32 * 32;
+            if (kg > TC_KG_MAX) { ok = false; break; }
+            bt.kg_max = std::max(bt.kg_max, kg);
+            const size_t b_off = (tct->b.size() + 127) & ~size_t(127);
+            tct->b.resize(b_off + size_t(TC_N) * kg, 0);
+            int8_t *tile = reinterpret_cast<int8_t *>(&tct->b[b_off]);
+            for (uint32_t r = ra; r < rb; r++) {
+                const TapEntry &e = s.vtab->entries[s.oy0 + bt.r0 + r];
+                for (uint32_t t = 0; t < e.count; t++) {
+                    const long q = std::lround(std::ldexp(double(s.vtab->weights[e.woff + t]), sh));
+                    const long lo = ((q + 64) & 127) - 64;
+                    const long q1 = (q - lo) / 128;
+                    const long mid = ((q1 + 64) & 127) - 64;
+                    const long hi = (q1 - mid) / 128;
+                    if (hi < -128 || hi > 127) { ok = false; break; }
+                    const uint32_t k = e.left + t - k0, j = r - ra;
+                    const long dig[3] = {hi, mid, lo};
+                    for (uint32_t d = 0; d < 3; d++) {
+                        const uint32_t n = d * TC_GROUP_ROWS + j;  // B row: digit-major
+                        tile[(size_t(n / 8) * (kg / 16) + k / 16) * 128 + (n % 8) * 16 + k % 16] = int8_t(dig[d]);
+                    }
+                }
+            }
+            uint32_t *gw = &tabs->info[bt.grp_off + size_t(gi) * 4];
+            gw[0] = k0; gw[1] = kg; gw[2] = uint32_t(b_off); gw[3] = rb - ra;
+        }
+        g.bands.push_back(bt);
+    }
+    g.ok = ok;
+    return cache->geoms.emplace(key, std::move(g)).first->second;
+}
+
+bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
+    return geom_of(s, cache, tabs, tct).ok;
+}
+
+int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
+                   FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct, std::vector<FusedTcItem> *items) {
+    (void)job;
+    const TcGeom &g = geom_of(s, cache, tabs, tct);
+    if (!g.ok) return FANLIN_EINVAL;
+    const uint32_t chunk_px = fused_tc_chunk_px(s.c);
+    for (size_t b = 0; b < g.bands.size(); b++) {
+        const TcBand &bt = g.bands[b];
+        FusedTcItem f{};
+        f.src = src; f.dst = dst; f.src_pitch = src_pitch; f.src_h = s.in_h;
+        f.c = s.c;
+        f.px0 = g.px0; f.n_px = g.n_px; f.chunk_px = chunk_px; f.n_chunks = (g.n_px + chunk_px - 1) / chunk_px;
+        f.band_r0 = bt.r0; f.band_rows = bt.rows; f.r_pad = r_pad_for(bt.rows);
+        f.grp_off = bt.grp_off; f.n_groups = bt.n_groups; f.kg_max = bt.kg_max;
+        f.scale = g.scale;
+        f.hw_off = g.hw_off; f.hinfo_off = g.hinfo_off;
+        f.n_cols = s.n_cols;
+        f.dst_pitch = s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
+        f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;
+        f.first_band = b == 0; f.last_band = b + 1 == g.bands.size();
+        items->push_back(f);
+    }
+    return FANLIN_OK;
+}
+
+}  // namespace fanlin

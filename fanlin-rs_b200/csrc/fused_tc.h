@@ -1,0 +1,61 @@
+// Fused separable resample, tensor-core vertical stage (sm_100a tcgen05 kind::i8).
+//
+// Same decomposition as fused.h (one CTA per image band, sweep of column chunks,
+// f32 tile in shared memory, scatter horizontal stage on the CUDA cores), but the
+// vertical pass -- 6 FMA per source byte at Lanczos3, which no CUDA-core schedule
+// gets under the HBM time on B200 -- runs as a banded integer
+// contraction on the 5th-generation tensor cores:
+//
+//   D[128 columns x 96] (s32, TMEM) += A[128 columns x 32 rows] (u8) * B[32 rows x 96] (s8)
+//
+// A is the source tile exactly as it lies in the image (rows = K, bytes of a row =
+// M, "MN-major"), staged by cp.async into the no-swizzle core-matrix layout; no byte
+// is converted or shuffled by a thread.  B holds, for a group of 32 output rows, the
+// filter weights as three signed base-128 digits of round(w * 2^s) (columns 0-31 hi,
+// 32-63 mid, 64-95 lo); the epilogue recombines the three s32 sums exactly.  Integer
+// arithmetic is exact; the only deviation from the f32 recipe is the 2^-s weight
+// quantisation (s >= 21), below the rounding noise of the f32 accumulation it replaces.
+#pragma once
+#include <vector>
+
+#include "fused.h"
+
+namespace fanlin {
+
+constexpr uint32_t TC_M = 128;          // source bytes (elements) per chunk row = UMMA M
+constexpr uint32_t TC_GROUP_ROWS = 32;  // output rows per MMA group (N = 3 * 32)
+constexpr uint32_t TC_N = 3 * TC_GROUP_ROWS;
+constexpr uint32_t TC_KG_MAX = 256;     // source rows per group, multiple of 32
+
+struct FusedTcItem {
+    const uint8_t *src;
+    uint8_t *dst;
+    uint32_t src_pitch, src_h;
+    uint32_t c;
+    uint32_t px0, n_px, chunk_px, n_chunks;
+    uint32_t band_r0, band_rows, r_pad;   // r_pad: floats per tile column, == 4 (mod 8)
+    uint32_t grp_off, n_groups, kg_max;   // grp_off: u32 offset of {k0, kg, b_off, rows} x n_groups
+    float scale;                          // 2^-s
+    uint32_t hw_off, hinfo_off;           // horizontal scatter table (unscaled weights)
+    uint32_t n_cols;
+    uint32_t dst_pitch, c_out, canvas_w, canvas_h, dst_x, dst_y, epi, fill;
+    uint32_t first_band, last_band;
+};
+
+struct FusedTcTables {
+    std::vector<uint8_t> b;  // weight digit tiles, core-matrix layout, 128-byte aligned per tile
+};
+
+bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job);
+struct FusedTcCache;
+FusedTcCache *fused_tc_cache_new();
+void fused_tc_cache_free(FusedTcCache *);
+bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs);
+int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
+                   FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs, std::vector<FusedTcItem> *items);
+
+uint32_t fused_tc_chunk_px(uint32_t c);
+size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max);
+uint32_t fused_tc_max_band(uint32_t c);
+
+}  // namespace fanlin

@@ -45,6 +45,10 @@ int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const floa
 struct FusedItem;
 int launch_fused(const FusedItem *d_items, uint32_t n_items, uint32_t variant, uint32_t max_band_rows,
                  const float *d_w, const uint32_t *d_info, LaunchCtx &lc);
+// Fused resample with the vertical pass on the tensor cores (kernels_fused_tc.cu).
+struct FusedTcItem;
+int launch_fused_tc(const FusedTcItem *d_items, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
+                    const float *d_w, const uint32_t *d_info, LaunchCtx &lc);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 

@@ -11,8 +11,8 @@
 // operand (a denormal, value b * 2^-149), and the vertical weights carry 2^100,
 // the horizontal ones 2^49, so the products land back on the true scale.  Power
 // of two scalings are exact, so this changes no rounding.
-#include "device_common.cuh"
 #include "fused.h"
+#include "fused_device.cuh"
 #include "kernels.h"
 
 namespace fanlin {
@@ -32,20 +32,6 @@ struct Raw {
     static constexpr int NW = (CMEM == C) ? 1 : (CMEM == 3 ? 3 : 2);
     uint32_t w[NW];
 };
-
-// cp.async (LDGSTS) of one 4-byte word: global -> this lane's slot of the warp's
-// staging ring.  Completion is tracked per commit group (FIFO), which, unlike
-// register-destination loads sharing six scoreboard slots, lets P rows really be
-// in flight per warp.
-__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g, bool on) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}\n" ::"r"(saddr),
-        "l"(g), "r"(int(on))
-        : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // Issues the copies of the words behind elements [e, e+4) of `row` (e multiple of 4).
 template <int C, int CMEM>
@@ -87,24 +73,6 @@ __device__ __forceinline__ void decode4(const Raw<C, CMEM> &r, float f[4]) {
         f[1] = __uint_as_float(w0 >> 24);
         f[2] = __uint_as_float(luma_u8(w1 & 0xff, (w1 >> 8) & 0xff, (w1 >> 16) & 0xff));
         f[3] = __uint_as_float(w1 >> 24);
-    }
-}
-
-// Epilogue for one produced pixel (already rounded channel values).
-template <int C>
-__device__ __forceinline__ void emit_px(const FusedItem &it, uint32_t cx, uint32_t cy, const uint32_t v[4]) {
-    uint8_t *q = it.dst + size_t(cy) * it.dst_pitch + size_t(cx) * it.c_out;
-    if (it.epi == EPI_PLAIN) {
-        if constexpr (C == 4) {
-            store_rgba(q, v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24);
-        } else {
-#pragma unroll
-            for (int k = 0; k < C; k++) q[k] = uint8_t(v[k]);
-        }
-    } else {
-        uint32_t px = to_rgba_packed(v, C);
-        if (it.epi == EPI_BLEND_FILL) px = blend_rgba(it.fill, px);
-        store_rgba(q, px);
     }
 }
 
@@ -301,7 +269,7 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_kernel(const FusedItem *
                                 uint32_t u[4] = {0, 0, 0, 0};
 #pragma unroll
                                 for (int k = 0; k < C; k++) { u[k] = round_u8(hacc[j][k]); hacc[j][k] = 0.f; }
-                                emit_px<C>(it, h_cx0 + o, h_cy, u);
+                                emit_px<C, FusedItem>(it, h_cx0 + o, h_cy, u);
                             }
                         }
                         h_next += __popc(fl);

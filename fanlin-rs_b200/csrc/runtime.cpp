@@ -4,6 +4,7 @@
 #include "runtime.h"
 
 #include "fused.h"
+#include "fused_tc.h"
 
 #include <algorithm>
 #include <cstring>
@@ -257,7 +258,10 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     const bool exact = ctx->cfg.exact != 0;
     std::unique_ptr<FusedCache, void (*)(FusedCache *)> fcache(fused_cache_new(), fused_cache_free);
     FusedTables ftabs;
-    std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A takes the fused resample kernel
+    std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
+    std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(), fused_tc_cache_free);
+    FusedTcTables tctabs;
+    const bool use_tc = ctx->cfg.vertical_path == 0;
 
     // 1. plans + table arena
     std::map<const AxisTable *, uint32_t> tab_base;
@@ -280,7 +284,8 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
         const JobPlan &p = b->plans[i];
-        fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
+        if (!exact && use_tc && fused_tc_eligible(p.a, jobs[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) fused_a[i] = 2;
+        else fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         add_table(p.b.vtab); add_table(p.b.htab);
     }
@@ -315,16 +320,35 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     // 3. descriptors per chunk and stage kind
     std::vector<StageDesc> descs;
     std::vector<FusedItem> fitems;
-    struct HostStep { int kind; size_t first; LaunchGeom g; uint32_t variant, n_items, max_band; };
+    std::vector<FusedTcItem> tcitems;
+    struct HostStep { int kind; size_t first; LaunchGeom g; uint32_t variant, n_items, max_band; size_t smem; };
     std::vector<HostStep> hsteps;
     uint32_t begin = 0;
     for (uint32_t end : chunk_end) {
         // stage A through the fused kernel, one launch per (channels, colour op) variant
         std::map<uint32_t, std::vector<uint32_t>> by_variant;
-        for (uint32_t i = begin; i < end; i++)
-            if (fused_a[i]) by_variant[fused_variant(b->plans[i].a)].push_back(i);
+        std::map<uint32_t, std::vector<uint32_t>> tc_by_c;
+        for (uint32_t i = begin; i < end; i++) {
+            if (fused_a[i] == 1) by_variant[fused_variant(b->plans[i].a)].push_back(i);
+            if (fused_a[i] == 2) tc_by_c[b->plans[i].a.c].push_back(i);
+        }
+        for (auto &kv : tc_by_c) {
+            HostStep hs{3, tcitems.size(), LaunchGeom{}, kv.first, 0, 0, 0};
+            for (uint32_t i : kv.second) {
+                const JobPlan &p = b->plans[i];
+                uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
+                const uint32_t pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
+                const int rc = fused_tc_build(p.a, jobs[i], jobs[i].src, pitch, p.b.present ? inter : jobs[i].dst, tcache.get(), &ftabs,
+                                              &tctabs, &tcitems);
+                if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core tables"); return rc; }
+            }
+            hs.n_items = uint32_t(tcitems.size() - hs.first);
+            for (size_t k = hs.first; k < tcitems.size(); k++)
+                hs.smem = std::max(hs.smem, fused_tc_smem_bytes(kv.first, tcitems[k].band_rows, tcitems[k].kg_max));
+            if (hs.n_items) hsteps.push_back(hs);
+        }
         for (auto &kv : by_variant) {
-            HostStep hs{2, fitems.size(), LaunchGeom{}, kv.first, 0, 0};
+            HostStep hs{2, fitems.size(), LaunchGeom{}, kv.first, 0, 0, 0};
             for (uint32_t i : kv.second) {
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
@@ -337,7 +361,7 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
             if (hs.n_items) hsteps.push_back(hs);
         }
         for (int pass = 0; pass < 3; pass++) {  // 0: A separable (generic), 1: A compose, 2: B separable
-            HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}, 0, 0, 0};
+            HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
             for (uint32_t i = begin; i < end; i++) {
                 const JobPlan &p = b->plans[i];
                 const StagePlan &s = pass == 2 ? p.b : p.a;
@@ -363,8 +387,12 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     const size_t off_fi = off_w + align_up(weights.size() * sizeof(float), 256);
     const size_t off_fw = off_fi + align_up(fitems.size() * sizeof(FusedItem), 256);
     const size_t off_fn = off_fw + align_up(ftabs.w.size() * sizeof(float), 256);
-    const size_t meta_bytes = off_fn + align_up(ftabs.info.size() * sizeof(uint32_t), 256) + 256;
+    const size_t off_ti = off_fn + align_up(ftabs.info.size() * sizeof(uint32_t), 256);
+    const size_t off_tb = off_ti + align_up(tcitems.size() * sizeof(FusedTcItem), 256);
+    const size_t meta_bytes = off_tb + align_up(tctabs.b.size(), 256) + 256;
     std::vector<uint8_t> meta(meta_bytes, 0);
+    if (!tcitems.empty()) std::memcpy(meta.data() + off_ti, tcitems.data(), tcitems.size() * sizeof(FusedTcItem));
+    if (!tctabs.b.empty()) std::memcpy(meta.data() + off_tb, tctabs.b.data(), tctabs.b.size());
     if (!fitems.empty()) std::memcpy(meta.data() + off_fi, fitems.data(), fitems.size() * sizeof(FusedItem));
     if (!ftabs.w.empty()) std::memcpy(meta.data() + off_fw, ftabs.w.data(), ftabs.w.size() * sizeof(float));
     if (!ftabs.info.empty()) std::memcpy(meta.data() + off_fn, ftabs.info.data(), ftabs.info.size() * sizeof(uint32_t));
@@ -379,7 +407,19 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     b->d_w = reinterpret_cast<const float *>(mbase + off_w);
     b->d_fw = reinterpret_cast<const float *>(mbase + off_fw);
     b->d_finfo = reinterpret_cast<const uint32_t *>(mbase + off_fn);
+    b->d_tb = mbase + off_tb;
     for (const HostStep &hs : hsteps) {
+        if (hs.kind == 3) {
+            fanlin_batch::Step st{};
+            st.kind = 3;
+            st.tc_items = reinterpret_cast<const FusedTcItem *>(mbase + off_ti) + hs.first;
+            st.n_items = hs.n_items;
+            st.variant = hs.variant;
+            st.smem = hs.smem;
+            b->steps.push_back(st);
+            b->launches_per_run += 1;
+            continue;
+        }
         if (hs.kind == 2) {
             fanlin_batch::Step st{};
             st.kind = 2;
@@ -419,7 +459,11 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
         lc.used = b->ev_used;
     }
     for (const fanlin_batch::Step &s : b->steps) {
-        if (s.kind == 2) {
+        if (s.kind == 3) {
+            const int k = launch_fused_tc(s.tc_items, s.n_items, s.variant, s.smem, b->d_tb, b->d_fw, b->d_finfo, lc);
+            if (k < 0) { set_error("fanlin: internal: no tensor-core kernel variant"); return FANLIN_EINVAL; }
+            n += k;
+        } else if (s.kind == 2) {
             const int k = launch_fused(s.items, s.n_items, s.variant, s.max_band, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no fused kernel variant"); return FANLIN_EINVAL; }
             n += k;

@@ -64,7 +64,9 @@ struct fanlin_batch {
     uint32_t n_jobs = 0;
     std::vector<fanlin::JobPlan> plans;
     struct Step {
-        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample
+        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores)
+        const fanlin::FusedTcItem *tc_items;
+        size_t smem;
         const fanlin::StageDesc *descs;
         fanlin::LaunchGeom geom;
         const fanlin::FusedItem *items;
@@ -77,6 +79,7 @@ struct fanlin_batch {
     const float *d_w = nullptr;
     const float *d_fw = nullptr;        // fused scatter tables
     const uint32_t *d_finfo = nullptr;
+    const uint8_t *d_tb = nullptr;      // tensor-core weight digit tiles
     int launches_per_run = 0;
     bool timing = false;
     std::vector<cudaEvent_t> events;

@@ -49,6 +49,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("exact", C.c_uint32),
         ("device_scratch_bytes", C.c_uint64), ("pinned_bytes", C.c_uint64),
         ("batch_window_us", C.c_uint32), ("max_batch_jobs", C.c_uint32),
+        ("vertical_path", C.c_uint32), ("reserved1", C.c_uint32),
     ]
 
 
@@ -177,8 +178,9 @@ class Device:
     """fanlin_ctx: created once at start-up, shared by all request threads."""
 
     def __init__(self, device_ids=None, *, exact=False, device_scratch_bytes=0, pinned_bytes=0,
-                 batch_window_us=0, max_batch_jobs=0):
-        cfg = Config(C.sizeof(Config), int(exact), device_scratch_bytes, pinned_bytes, batch_window_us, max_batch_jobs)
+                 batch_window_us=0, max_batch_jobs=0, tensor_cores=True):
+        cfg = Config(C.sizeof(Config), int(exact), device_scratch_bytes, pinned_bytes, batch_window_us, max_batch_jobs,
+                     0 if tensor_cores else 1, 0)
         h = C.c_void_p()
         if device_ids:
             arr = (C.c_int * len(device_ids))(*device_ids)
