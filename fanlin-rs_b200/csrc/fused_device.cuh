@@ -17,6 +17,12 @@ __device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g, bool on
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(g) : "memory");
 }
+__device__ __forceinline__ void cp_async16_if(uint32_t saddr, const void *g, bool on) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n" ::"r"(saddr),
+        "l"(g), "r"(int(on))
+        : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }

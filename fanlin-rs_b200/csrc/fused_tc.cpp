@@ -30,7 +30,8 @@ uint32_t r_pad_for(uint32_t rows) {
 
 }  // namespace
 
-uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 128u : c == 2 ? 64u : c == 3 ? 40u : 32u; }
+// chunk bytes + the <= 15 bytes of alignment padding in front of them fit the 128-byte tile row
+uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 112u : c == 2 ? 60u : c == 3 ? 38u : 32u; }
 
 size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
     const size_t tmp = size_t(TC_M) * r_pad_for(band_rows) * 4;
@@ -58,9 +59,8 @@ bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
     if (s.v_kind != KIND_LANCZOS3) return false;  // Nearest is a gather (bit-exact on the CUDA-core path); blur has its own kernel
     if (s.color_op != COLOR_NONE || s.c_mem != s.c) return false;
     const uint32_t pitch = s.src_is_input ? (job.src_pitch ? job.src_pitch : job.src_w * job.src_channels) : s.in_w * s.c_mem;
-    if (pitch % 4 != 0) return false;
-    if ((uint64_t(s.in_w) * s.c) % 4 != 0) return false;
-    if (s.src_is_input && (reinterpret_cast<uintptr_t>(job.src) & 3)) return false;
+    if (pitch % 16 != 0) return false;  // rows are staged with 16-byte cp.async
+    if (s.src_is_input && (reinterpret_cast<uintptr_t>(job.src) & 15)) return false;
     // a 32-row output group must fit 256 source rows, and the horizontal pass 8 live outputs
     const double ratio = double(s.in_h) / double(std::max(1u, s.v_out));
     if ((TC_GROUP_ROWS - 1) * ratio + s.vtab->max_taps > TC_KG_MAX) return false;

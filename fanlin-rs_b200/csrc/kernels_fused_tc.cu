@@ -111,17 +111,19 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     const uint32_t *hinfo = tinfo + it.hinfo_off;
     const uint32_t h_cx0 = it.dst_x, h_cy = it.dst_y + it.band_r0 + tid;
 
-    // cp.async of group g of the current chunk into buffer `buf`: the source rows (each lane
-    // 4 bytes; a warp covers 4 rows x 32 B, full sectors) and the weight-digit tile.
-    const uint32_t ld_kr = lane & 3, ld_w8 = lane >> 2;
-    auto issue_load = [&](uint32_t g, uint32_t buf, const uint8_t *src_col, uint32_t nbytes) {
+    // cp.async of group g of the current chunk into buffer `buf`: the source rows as 16-byte
+    // pieces (a quarter warp writes the 8 rows of one core matrix: 128 contiguous bytes of shared
+    // memory, and reads full 32-byte sectors), and the weight-digit tile.  `src_al` is the
+    // 16-byte aligned start of the chunk in row 0; the tile's first `sh` columns are padding.
+    const uint32_t ld_kr = lane & 7, ld_seg = lane >> 3;
+    auto issue_load = [&](uint32_t g, uint32_t buf, const uint8_t *src_al, uint32_t avail) {
         const uint32_t k0 = grp[4 * g], kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
-        const uint32_t a_dst = sA_u + buf * kg_max * TC_M;
-        for (uint32_t u = warp; u < kg; u += NT / 32) {  // unit = (4 rows, 32-byte segment)
-            const uint32_t kk = (u >> 2) * 4 + ld_kr, wi = (u & 3) * 8 + ld_w8;
-            const uint32_t y = min(k0 + kk, it.src_h - 1);  // rows past the image carry zero weights
-            cp_async4(a_dst + ((kk >> 3) * 8 + (wi >> 2)) * 128 + (kk & 7) * 16 + (wi & 3) * 4,
-                      src_col + size_t(y) * pitch + wi * 4, wi * 4 < nbytes);
+        const uint32_t a_dst = sA_u + buf * kg_max * TC_M + ld_kr * 16;
+        const uint32_t y_max = it.src_h - 1;
+        for (uint32_t u = warp; u < kg / 4; u += NT / 32) {  // unit = (block of 8 rows, half of the 8 segments)
+            const uint32_t rb = u >> 1, seg = (u & 1) * 4 + ld_seg;
+            const uint32_t y = min(k0 + rb * 8 + ld_kr, y_max);  // rows past the image carry zero weights
+            cp_async16_if(a_dst + (rb * 8 + seg) * 128, src_al + size_t(y) * pitch + seg * 16, seg * 16 < avail);
         }
         const uint32_t b_dst = sB_u + buf * TC_N * kg_max;
         const uint8_t *bsrc = tb + b_off;
@@ -133,8 +135,9 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
         const uint32_t cpx0 = chunk * chunk_px;
         const uint32_t npx = min(chunk_px, n_px - cpx0);
-        const uint32_t nbytes = (npx * C + 3) & ~3u;
-        const uint8_t *src_col = it.src + size_t(it.px0 + cpx0) * C;
+        const uint32_t byte0 = (it.px0 + cpx0) * C, al0 = byte0 & ~15u, sh = byte0 - al0;
+        const uint8_t *src_col = it.src + al0;
+        const uint32_t nbytes = pitch - al0;  // bytes of the row available from the aligned start
         // horizontal table slice of this chunk + the first two groups
         {
             const uint32_t sa_w = smem_u32(hw_s), sa_i = smem_u32(hinfo_s);
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
             for (uint32_t xl = 0; xl < npx; xl++) {
                 float v[C];
 #pragma unroll
-                for (int k = 0; k < C; k++) v[k] = tcol[size_t(xl * C + k) * r_pad];
+                for (int k = 0; k < C; k++) v[k] = tcol[size_t(sh + xl * C + k) * r_pad];
                 const uint32_t info = hinfo_s[xl];
                 const float4 w0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
                 const float4 w1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
