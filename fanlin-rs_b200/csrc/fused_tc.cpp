@@ -36,7 +36,7 @@ uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 112u : c == 2 ? 60u : c
 size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
     const size_t tmp = size_t(TC_M) * r_pad_for(band_rows) * 4;
     const size_t a = 2 * size_t(kg_max) * TC_M, b = 2 * size_t(TC_N) * kg_max;
-    const size_t ht = (size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15);
+    const size_t ht = 2 * ((size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15));  // two copies of the chunk's horizontal table slice
     return tmp + a + b + ht + 128;
 }
 

@@ -4,17 +4,22 @@
 // Per CTA (8 warps, 1 CTA / SM): one band of <= 192 output rows of one image, swept
 // left to right in chunks of 128 source bytes per row.  Per chunk, per group of 32
 // output rows:
-//   * all threads cp.async the group's source rows (<= 256 x 128 B, straight from the
-//     image, placed in the no-swizzle core-matrix layout) and its s8 weight-digit tile
-//     into one of two shared-memory buffers -- the next group's copies are in flight
-//     while this group is computed;
-//   * one thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3 digits
-//     x 32 output rows, K = 32 source rows each) and commits to an mbarrier;
-//   * all 8 warps read their quarter of TMEM (tcgen05.ld 32x32b), recombine the three
-//     s32 digit sums into the f32 value of the crate's vertical pass and store it to the
-//     tile tmp[element][row];
-// then the horizontal stage runs on the CUDA cores exactly as in kernels_fused.cu (one
-// thread per output row, scatter into <= 8 live output pixels, epilogue).
+//   * ONE thread fetches the group's source rows with a single TMA tensor copy
+//     (cp.async.bulk.tensor.3d; tensor map dims {16 B, rows, 16-byte segments}) -- the box
+//     lands as [segment][row][16 B], a no-swizzle core-matrix layout the tensor core reads
+//     directly; rows past the image are zero-filled -- and the s8 weight-digit tile with
+//     one cp.async.bulk.  Two shared-memory buffers: the copies of group g+2 are issued the
+//     moment the MMAs of group g retire, so a group and a half of loads are always in flight;
+//   * the same thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3 digits
+//     x 32 output rows, K = 32 source rows) for group g+1 and commits to an mbarrier;
+//   * meanwhile all 8 warps read group g's accumulators from TMEM (tcgen05.ld 32x32b),
+//     recombine the three s32 digit sums into the f32 value of the crate's vertical pass and
+//     store it to the tile tmp[element][row];
+// then the horizontal stage runs on the CUDA cores as in kernels_fused.cu (one thread per
+// output row, scatter into <= 8 live output pixels, epilogue), while the first two groups of
+// the next chunk are already being fetched.
+#include <cuda.h>
+
 #include "fused_device.cuh"
 #include "fused_tc.h"
 #include "kernels.h"
@@ -60,12 +65,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
 
 template <int C>
 __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcItem *__restrict__ items,
+                                                                  const CUtensorMap *__restrict__ tmaps,
                                                                   const uint8_t *__restrict__ tb,
                                                                   const float *__restrict__ tw,
                                                                   const uint32_t *__restrict__ tinfo) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ FusedTcItem it_s;
-    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t mbar[2];  // MMAs of the group in accumulator buffer b have retired
+    __shared__ __align__(8) uint64_t full[2];  // the copies into shared-memory buffer b have landed
     __shared__ uint32_t tmem_base_s;
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -73,6 +80,9 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
         it_s = items[blockIdx.x];
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
@@ -88,13 +98,14 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     fill_bars(it, warp, lane, NT / 32);
 
     // ---- shared-memory carve-up
-    const uint32_t r_pad = it.r_pad, kg_max = it.kg_max, pitch = it.src_pitch;
+    const uint32_t r_pad = it.r_pad, kg_max = it.kg_max;
     float *tmp = reinterpret_cast<float *>(smem);                      // [128][r_pad]
-    uint8_t *sA = smem + size_t(TC_M) * r_pad * 4;                     // 2 x [kg_max rows][128 B], core-matrix layout
+    uint8_t *sA = smem + size_t(TC_M) * r_pad * 4;                     // 2 x [8 segments][kg_max rows][16 B]
     uint8_t *sB = sA + 2 * size_t(kg_max) * TC_M;                      // 2 x [96][kg_max], core-matrix layout
-    float *hw_s = reinterpret_cast<float *>(sB + 2 * size_t(TC_N) * kg_max);  // [chunk_px][8], then info words
+    float *hw_s0 = reinterpret_cast<float *>(sB + 2 * size_t(TC_N) * kg_max);  // 2 x ([chunk_px][8] weights + [chunk_px] info)
     const uint32_t chunk_px = it.chunk_px, n_px = it.n_px, n_chunks = it.n_chunks, n_groups = it.n_groups;
-    const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
+    const uint32_t htab_words = (chunk_px * (S + 1) + 3) & ~3u;  // each copy stays 16-byte aligned
+    const CUtensorMap *tmap = tmaps + blockIdx.x;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
     const uint32_t *grp = tinfo + it.grp_off;
     const float scale = it.scale, scale_hi = it.scale * 16384.0f;
@@ -111,77 +122,93 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     const uint32_t *hinfo = tinfo + it.hinfo_off;
     const uint32_t h_cx0 = it.dst_x, h_cy = it.dst_y + it.band_r0 + tid;
 
-    // cp.async of group g of the current chunk into buffer `buf`: the source rows as 16-byte
-    // pieces (a quarter warp writes the 8 rows of one core matrix: 128 contiguous bytes of shared
-    // memory, and reads full 32-byte sectors), and the weight-digit tile.  `src_al` is the
-    // 16-byte aligned start of the chunk in row 0; the tile's first `sh` columns are padding.
-    const uint32_t ld_kr = lane & 7, ld_seg = lane >> 3;
-    auto issue_load = [&](uint32_t g, uint32_t buf, const uint8_t *src_al, uint32_t avail) {
+    // Thread 0 only: fetch group g of the chunk whose 16-byte aligned first column is seg0 into
+    // shared-memory buffer `buf` (one TMA tensor copy + one bulk copy, completion on full[buf]).
+    auto issue_load = [&](uint32_t g, uint32_t buf, uint32_t seg0) {
         const uint32_t k0 = grp[4 * g], kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
-        const uint32_t a_dst = sA_u + buf * kg_max * TC_M + ld_kr * 16;
-        const uint32_t y_max = it.src_h - 1;
-        for (uint32_t u = warp; u < kg / 4; u += NT / 32) {  // unit = (block of 8 rows, half of the 8 segments)
-            const uint32_t rb = u >> 1, seg = (u & 1) * 4 + ld_seg;
-            const uint32_t y = min(k0 + rb * 8 + ld_kr, y_max);  // rows past the image carry zero weights
-            cp_async16_if(a_dst + (rb * 8 + seg) * 128, src_al + size_t(y) * pitch + seg * 16, seg * 16 < avail);
+        const uint32_t bar = smem_u32(&full[buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M + kg * TC_N) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                         sA_u + buf * kg_max * TC_M),
+                     "l"(tmap), "r"(bar), "r"(0), "r"(k0), "r"(seg0)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB_u + buf * TC_N * kg_max),
+                     "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
+                     : "memory");
+    };
+    // Thread 0 only: the MMAs of group g (operands in shared-memory buffer buf, accumulators in
+    // TMEM buffer buf), committed to mbar[buf].
+    auto issue_mma = [&](uint32_t g, uint32_t buf) {
+        const uint32_t kg = grp[4 * g + 1];
+        const uint32_t a0 = sA_u + buf * kg_max * TC_M, b0 = sB_u + buf * TC_N * kg_max;
+        const uint32_t d_tmem = tmem_base + buf * 128;
+        for (uint32_t ks = 0; ks < kg / 32; ks++) {
+            const uint64_t da = umma_desc(a0 + ks * 32 * 16, 128, kg_max * 16);      // K step: 32 rows x 16 B
+            const uint64_t db = umma_desc(b0 + ks * 2 * 128, 128, (kg / 16) * 128);
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(UMMA_IDESC),
+                "r"(uint32_t(ks > 0))
+                : "memory");
         }
-        const uint32_t b_dst = sB_u + buf * TC_N * kg_max;
-        const uint8_t *bsrc = tb + b_off;
-        for (uint32_t i = tid; i < kg * (TC_N / 16); i += NT) cp_async16(b_dst + i * 16, bsrc + size_t(i) * 16);
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[buf])) : "memory");
     };
 
-    uint32_t uses[2] = {0, 0};  // completed MMA batches per accumulator buffer (mbarrier phase)
+    uint32_t uses[2] = {0, 0};       // retired MMA batches per buffer (phase of mbar[])
+    uint32_t full_uses[2] = {0, 0};  // thread 0: landed loads per buffer (phase of full[])
+    auto chunk_seg0 = [&](uint32_t chunk) { return ((it.px0 + chunk * chunk_px) * C) >> 4; };
+    auto stage_htab = [&](uint32_t chunk) {  // the chunk's slice of the horizontal table -> its shared-memory copy
+        const uint32_t cpx0 = chunk * chunk_px, npx = min(chunk_px, n_px - cpx0);
+        float *dstw = hw_s0 + (chunk & 1) * htab_words;
+        const uint32_t sa_w = smem_u32(dstw), sa_i = smem_u32(dstw + size_t(chunk_px) * S);
+        const uint32_t *gw = reinterpret_cast<const uint32_t *>(hw + size_t(cpx0) * S);
+        for (uint32_t k = tid; k < npx * S; k += NT) cp_async4(sa_w + 4 * k, gw + k, true);
+        for (uint32_t k = tid; k < npx; k += NT) cp_async4(sa_i + 4 * k, hinfo + cpx0 + k, true);
+        cp_async_commit();
+    };
 
+    // Groups are numbered flat across chunks (gg = chunk * n_groups + g): buffer = gg & 1, and
+    // the load / MMA cursors of thread 0 simply run 2 and 1 groups ahead of the epilogue.
+    const uint32_t total = n_chunks * n_groups;
+    uint32_t ld_chunk = 0, ld_g = 0, ld_gg = 0;  // thread 0: next group to fetch
+    auto load_next = [&]() {
+        if (ld_gg < total) {
+            issue_load(ld_g, ld_gg & 1, chunk_seg0(ld_chunk));
+            ld_gg++;
+            if (++ld_g == n_groups) { ld_g = 0; ld_chunk++; }
+        }
+    };
+    stage_htab(0);
+    if (tid == 0) {
+        load_next();
+        load_next();
+        mbar_wait(smem_u32(&full[0]), 0);
+        full_uses[0]++;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        issue_mma(0, 0);
+    }
+
+    uint32_t gg = 0;
     for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
         const uint32_t cpx0 = chunk * chunk_px;
         const uint32_t npx = min(chunk_px, n_px - cpx0);
-        const uint32_t byte0 = (it.px0 + cpx0) * C, al0 = byte0 & ~15u, sh = byte0 - al0;
-        const uint8_t *src_col = it.src + al0;
-        const uint32_t nbytes = pitch - al0;  // bytes of the row available from the aligned start
-        // horizontal table slice of this chunk + the first two groups
-        {
-            const uint32_t sa_w = smem_u32(hw_s), sa_i = smem_u32(hinfo_s);
-            const uint32_t *gw = reinterpret_cast<const uint32_t *>(hw + size_t(cpx0) * S);
-            for (uint32_t k = tid; k < npx * S; k += NT) cp_async4(sa_w + 4 * k, gw + k, true);
-            for (uint32_t k = tid; k < npx; k += NT) cp_async4(sa_i + 4 * k, hinfo + cpx0 + k, true);
-        }
-        issue_load(0, 0, src_col, nbytes);
-        cp_async_commit();
-        if (n_groups > 1) issue_load(1, 1, src_col, nbytes);
-        cp_async_commit();
-
+        const uint32_t sh = ((it.px0 + cpx0) * C) & 15u;  // padding columns in front of the chunk
         // ================= vertical stage: tensor cores =================
-        for (uint32_t g = 0; g < n_groups; g++) {
-            const uint32_t buf = g & 1;
-            cp_async_wait<1>();  // this thread's copies of group g have landed
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // -> visible to the tensor core (async proxy)
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t kg = grp[4 * g + 1];
-            if (tid == 0) {
-                const uint32_t a0 = sA_u + buf * kg_max * TC_M, b0 = sB_u + buf * TC_N * kg_max;
-                const uint32_t d_tmem = tmem_base + buf * 128;
-                for (uint32_t ks = 0; ks < kg / 32; ks++) {
-                    const uint64_t da = umma_desc(a0 + ks * 4 * (TC_M / 16) * 128, (TC_M / 16) * 128, 128);
-                    const uint64_t db = umma_desc(b0 + ks * 2 * 128, 128, (kg / 16) * 128);
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(UMMA_IDESC),
-                        "r"(uint32_t(ks > 0))
-                        : "memory");
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[buf]))
-                             : "memory");
-            }
-            mbar_wait(smem_u32(&mbar[buf]), uses[buf] & 1);
+        for (uint32_t g = 0; g < n_groups; g++, gg++) {
+            const uint32_t buf = gg & 1;
+            mbar_wait(smem_u32(&mbar[buf]), uses[buf] & 1);  // the MMAs of group gg have retired
             uses[buf]++;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // the MMAs of group g are done: its shared-memory buffer is free for group g + 2
-            if (g + 2 < n_groups) issue_load(g + 2, buf, src_col, nbytes);
-            cp_async_commit();
-            // ---- epilogue: TMEM -> f32 tile.  Warp w reads lanes [32 (w & 3), +32) (= chunk
-            // bytes m) and the half (w >> 2) of the group's 32 output rows.
+            if (tid == 0) load_next();  // shared-memory buffer `buf` is free: fetch group gg + 2
+            __syncthreads();  // every warp is done with the epilogue of group gg - 1: TMEM buffer buf ^ 1 is free
+            if (tid == 0 && gg + 1 < total) {
+                mbar_wait(smem_u32(&full[buf ^ 1]), full_uses[buf ^ 1] & 1);
+                full_uses[buf ^ 1]++;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_mma(g + 1 < n_groups ? g + 1 : 0, buf ^ 1);  // runs on the tensor core while the warps drain group gg
+            }
+            // ---- epilogue: TMEM -> f32 tile.  Warp w reads lanes [32 (w & 3), +32) (= tile
+            // columns m) and the half (w >> 2) of the group's 32 output rows.
             {
                 const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane;
                 const uint32_t taddr = tmem_base + buf * 128 + (((warp & 3) * 32u) << 16) + half * 16;
@@ -206,15 +233,20 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
-        cp_async_wait<0>();
+        if (chunk + 1 < n_chunks) stage_htab(chunk + 1);  // lands during this chunk's horizontal stage
+        else cp_async_commit();
+        cp_async_wait<1>();  // this chunk's table slice (committed one chunk ago) has landed
         __syncthreads();
         // ================= horizontal stage: CUDA cores =================
         if (h_active) {
-            const float *tcol = tmp + tid;
+            const float *tcol = tmp + tid + size_t(sh) * r_pad;
+            const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
+            const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
+#pragma unroll 2
             for (uint32_t xl = 0; xl < npx; xl++) {
                 float v[C];
 #pragma unroll
-                for (int k = 0; k < C; k++) v[k] = tcol[size_t(sh + xl * C + k) * r_pad];
+                for (int k = 0; k < C; k++) v[k] = tcol[size_t(xl * C + k) * r_pad];
                 const uint32_t info = hinfo_s[xl];
                 const float4 w0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
                 const float4 w1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
@@ -247,27 +279,51 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
 }
 
 template <int C>
-void launch_tc_variant(const FusedTcItem *d_items, uint32_t n_items, size_t smem, const uint8_t *d_b, const float *d_w,
-                       const uint32_t *d_info, LaunchCtx &lc) {
+void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
+                       const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
     auto kern = fused_resample_tc_kernel<C>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     lc.begin("fused_resample_tc_kernel");
-    kern<<<n_items, NT, smem, lc.st>>>(d_items, d_b, d_w, d_info);
+    kern<<<n_items, NT, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info);
     lc.end();
 }
 
 }  // namespace
 
-int launch_fused_tc(const FusedTcItem *d_items, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
+int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
     if (n_items == 0) return 0;
     switch (c) {
-    case 1: launch_tc_variant<1>(d_items, n_items, smem, d_b, d_w, d_info, lc); return 1;
-    case 2: launch_tc_variant<2>(d_items, n_items, smem, d_b, d_w, d_info, lc); return 1;
-    case 3: launch_tc_variant<3>(d_items, n_items, smem, d_b, d_w, d_info, lc); return 1;
-    case 4: launch_tc_variant<4>(d_items, n_items, smem, d_b, d_w, d_info, lc); return 1;
+    case 1: launch_tc_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
+    case 2: launch_tc_variant<2>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
+    case 3: launch_tc_variant<3>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
+    case 4: launch_tc_variant<4>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
     }
     return -1;
+}
+
+}  // namespace fanlin
+
+// ---- host: tensor maps ---------------------------------------------------------------------
+#include <cudaTypedefs.h>
+
+namespace fanlin {
+
+bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t rows, uint32_t box_rows) {
+    static PFN_cuTensorMapEncodeTiled enc = nullptr;
+    if (!enc) {
+        cudaDriverEntryPointQueryResult qr;
+        void *fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return false;
+        enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }
+    const cuuint64_t gdim[3] = {16, rows, pitch / 16};
+    const cuuint64_t gstr[2] = {pitch, 16};
+    const cuuint32_t box[3] = {16, box_rows, TC_M / 16};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(static_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace fanlin

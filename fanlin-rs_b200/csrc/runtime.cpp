@@ -389,10 +389,17 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     const size_t off_fn = off_fw + align_up(ftabs.w.size() * sizeof(float), 256);
     const size_t off_ti = off_fn + align_up(ftabs.info.size() * sizeof(uint32_t), 256);
     const size_t off_tb = off_ti + align_up(tcitems.size() * sizeof(FusedTcItem), 256);
-    const size_t meta_bytes = off_tb + align_up(tctabs.b.size(), 256) + 256;
+    const size_t off_tm = off_tb + align_up(tctabs.b.size(), 256);
+    const size_t meta_bytes = off_tm + tcitems.size() * 128 + 256;
     std::vector<uint8_t> meta(meta_bytes, 0);
     if (!tcitems.empty()) std::memcpy(meta.data() + off_ti, tcitems.data(), tcitems.size() * sizeof(FusedTcItem));
     if (!tctabs.b.empty()) std::memcpy(meta.data() + off_tb, tctabs.b.data(), tctabs.b.size());
+    for (size_t k = 0; k < tcitems.size(); k++) {  // one TMA tensor map per (image, band): box rows = the band's kg_max
+        if (!encode_row_tile_map(meta.data() + off_tm + k * 128, tcitems[k].src, tcitems[k].src_pitch, tcitems[k].src_h, tcitems[k].kg_max)) {
+            set_error("fanlin: cuTensorMapEncodeTiled failed");
+            return FANLIN_ECUDA;
+        }
+    }
     if (!fitems.empty()) std::memcpy(meta.data() + off_fi, fitems.data(), fitems.size() * sizeof(FusedItem));
     if (!ftabs.w.empty()) std::memcpy(meta.data() + off_fw, ftabs.w.data(), ftabs.w.size() * sizeof(float));
     if (!ftabs.info.empty()) std::memcpy(meta.data() + off_fn, ftabs.info.data(), ftabs.info.size() * sizeof(uint32_t));
@@ -413,6 +420,7 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
             fanlin_batch::Step st{};
             st.kind = 3;
             st.tc_items = reinterpret_cast<const FusedTcItem *>(mbase + off_ti) + hs.first;
+            st.tmaps = mbase + off_tm + hs.first * 128;
             st.n_items = hs.n_items;
             st.variant = hs.variant;
             st.smem = hs.smem;
@@ -460,7 +468,7 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
     }
     for (const fanlin_batch::Step &s : b->steps) {
         if (s.kind == 3) {
-            const int k = launch_fused_tc(s.tc_items, s.n_items, s.variant, s.smem, b->d_tb, b->d_fw, b->d_finfo, lc);
+            const int k = launch_fused_tc(s.tc_items, s.tmaps, s.n_items, s.variant, s.smem, b->d_tb, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no tensor-core kernel variant"); return FANLIN_EINVAL; }
             n += k;
         } else if (s.kind == 2) {

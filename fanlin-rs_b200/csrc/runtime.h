@@ -66,6 +66,7 @@ struct fanlin_batch {
     struct Step {
         int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores)
         const fanlin::FusedTcItem *tc_items;
+        const void *tmaps;  // CUtensorMap per tc item
         size_t smem;
         const fanlin::StageDesc *descs;
         fanlin::LaunchGeom geom;
