@@ -37,7 +37,7 @@ size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
     const size_t tmp = size_t(TC_M) * r_pad_for(band_rows) * 4;
     const size_t a = 2 * size_t(kg_max) * TC_M, b = 2 * size_t(TC_N) * kg_max;
     const size_t ht = 2 * ((size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15));  // two copies of the chunk's horizontal table slice
-    return tmp + a + b + ht + 128;
+    return tmp + a + b + ht + 1024 + 128;  // + slack to align the tile buffers to 1024 bytes
 }
 
 uint32_t fused_tc_max_band(uint32_t c) {

@@ -50,7 +50,7 @@ struct FusedTcItem;
 int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc);
 // Host: encodes the TMA tensor map (128 bytes at `out`) through which that kernel fetches rows of
-// one image: dims {16 B, rows, 16-byte segments}, box {16, box_rows, 8}.  Returns false on failure.
+// one image: dims {row bytes, rows}, box {128 B, box_rows}, 128-byte swizzle.  Returns false on failure.
 bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t rows, uint32_t box_rows);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);

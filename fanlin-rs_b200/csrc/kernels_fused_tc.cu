@@ -5,10 +5,11 @@
 // left to right in chunks of 128 source bytes per row.  Per chunk, per group of 32
 // output rows:
 //   * ONE thread fetches the group's source rows with a single TMA tensor copy
-//     (cp.async.bulk.tensor.3d; tensor map dims {16 B, rows, 16-byte segments}) -- the box
-//     lands as [segment][row][16 B], a no-swizzle core-matrix layout the tensor core reads
-//     directly; rows past the image are zero-filled -- and the s8 weight-digit tile with
-//     one cp.async.bulk.  Two shared-memory buffers: the copies of group g+2 are issued the
+//     (cp.async.bulk.tensor.2d; tensor map {row bytes, rows}, box {128 B, kg rows}, 128-byte
+//     swizzle) -- the box lands as [row][128 B] with the hardware swizzle, which is the
+//     MN-major SWIZZLE_128B operand layout the tensor core reads directly (measured:
+//     profiles/microbench/umma_i8_tma128.cu); rows / columns past the image are zero-filled
+//     -- and the s8 weight-digit tile with one cp.async.bulk.  Two shared-memory buffers: the copies of group g+2 are issued the
 //     moment the MMAs of group g retire, so a group and a half of loads are always in flight;
 //   * the same thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3 digits
 //     x 32 output rows, K = 32 source rows) for group g+1 and commits to an mbarrier;
@@ -35,8 +36,8 @@ constexpr uint32_t TMEM_COLS = 256;  // two accumulator buffers of 96 columns at
 // Shared-memory matrix descriptor, no swizzle.  Measured on B200
 // (profiles/microbench/umma_i8.cu): LBO = byte stride between core matrices along K,
 // SBO = along M/N, for both the MN-major A tile and the K-major B tile.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = uint64_t((saddr & 0x3FFFFu) >> 4);
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 0) {
+    uint64_t d = uint64_t((saddr & 0x3FFFFu) >> 4) | (uint64_t(layout) << 61);  // layout 0 = no swizzle, 2 = 128-byte swizzle
     d |= uint64_t((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= uint64_t((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= uint64_t(1) << 46;  // descriptor version of sm_100
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
                                                                   const uint8_t *__restrict__ tb,
                                                                   const float *__restrict__ tw,
                                                                   const uint32_t *__restrict__ tinfo) {
-    extern __shared__ __align__(128) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
     __shared__ FusedTcItem it_s;
     __shared__ __align__(8) uint64_t mbar[2];  // MMAs of the group in accumulator buffer b have retired
     __shared__ __align__(8) uint64_t full[2];  // the copies into shared-memory buffer b have landed
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     // ---- shared-memory carve-up
     const uint32_t r_pad = it.r_pad, kg_max = it.kg_max;
     float *tmp = reinterpret_cast<float *>(smem);                      // [128][r_pad]
-    uint8_t *sA = smem + size_t(TC_M) * r_pad * 4;                     // 2 x [8 segments][kg_max rows][16 B]
+    uint8_t *sA = smem + size_t(TC_M) * r_pad * 4;                     // 2 x [kg_max rows][128 B], 128-byte swizzle (1024-aligned)
     uint8_t *sB = sA + 2 * size_t(kg_max) * TC_M;                      // 2 x [96][kg_max], core-matrix layout
     float *hw_s0 = reinterpret_cast<float *>(sB + 2 * size_t(TC_N) * kg_max);  // 2 x ([chunk_px][8] weights + [chunk_px] info)
     const uint32_t chunk_px = it.chunk_px, n_px = it.n_px, n_chunks = it.n_chunks, n_groups = it.n_groups;
@@ -128,9 +130,9 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
         const uint32_t k0 = grp[4 * g], kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
         const uint32_t bar = smem_u32(&full[buf]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M + kg * TC_N) : "memory");
-        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                          sA_u + buf * kg_max * TC_M),
-                     "l"(tmap), "r"(bar), "r"(0), "r"(k0), "r"(seg0)
+                     "l"(tmap), "r"(bar), "r"(seg0 * 16), "r"(k0)
                      : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB_u + buf * TC_N * kg_max),
                      "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
@@ -143,7 +145,7 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
         const uint32_t a0 = sA_u + buf * kg_max * TC_M, b0 = sB_u + buf * TC_N * kg_max;
         const uint32_t d_tmem = tmem_base + buf * 128;
         for (uint32_t ks = 0; ks < kg / 32; ks++) {
-            const uint64_t da = umma_desc(a0 + ks * 32 * 16, 128, kg_max * 16);      // K step: 32 rows x 16 B
+            const uint64_t da = umma_desc(a0 + ks * 32 * 128, 16, 1024, 2);  // K step: 32 rows x 128 B; SBO = 8-row atom stride
             const uint64_t db = umma_desc(b0 + ks * 2 * 128, 128, (kg / 16) * 128);
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -317,12 +319,12 @@ bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t r
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) return false;
         enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
     }
-    const cuuint64_t gdim[3] = {16, rows, pitch / 16};
-    const cuuint64_t gstr[2] = {pitch, 16};
-    const cuuint32_t box[3] = {16, box_rows, TC_M / 16};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    return enc(static_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), gdim, gstr, box, estr,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    const cuuint64_t gdim[2] = {pitch, rows};
+    const cuuint64_t gstr[1] = {pitch};
+    const cuuint32_t box[2] = {TC_M, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(static_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), gdim, gstr, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
