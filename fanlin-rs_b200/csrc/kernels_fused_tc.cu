@@ -1,24 +1,25 @@
 // Fused separable Lanczos3 resample with the vertical pass on the sm_100a tensor
 // cores (tcgen05.mma kind::i8, accumulators in TMEM).  See fused_tc.h.
 //
-// Per CTA (8 warps, 1 CTA / SM): one band of <= 192 output rows of one image, swept
-// left to right in chunks of 128 source bytes per row.  Per chunk, per group of 32
-// output rows:
-//   * ONE thread fetches the group's source rows with a single TMA tensor copy
+// Per CTA (1 CTA / SM): 8 consumer warps + 1 producer warp; one band of <= 192 output rows
+// of one image, swept left to right in chunks of 128 source bytes per row.  Per chunk, per
+// group of 32 output rows:
+//   * the producer thread fetches the group's source rows with a single TMA tensor copy
 //     (cp.async.bulk.tensor.2d; tensor map {row bytes, rows}, box {128 B, kg rows}, 128-byte
 //     swizzle) -- the box lands as [row][128 B] with the hardware swizzle, which is the
 //     MN-major SWIZZLE_128B operand layout the tensor core reads directly (measured:
 //     profiles/microbench/umma_i8_tma128.cu); rows / columns past the image are zero-filled
-//     -- and the s8 weight-digit tile with one cp.async.bulk.  Two shared-memory buffers: the copies of group g+2 are issued the
-//     moment the MMAs of group g retire, so a group and a half of loads are always in flight;
-//   * the same thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3 digits
-//     x 32 output rows, K = 32 source rows) for group g+1 and commits to an mbarrier;
-//   * meanwhile all 8 warps read group g's accumulators from TMEM (tcgen05.ld 32x32b),
-//     recombine the three s32 digit sums into the f32 value of the crate's vertical pass and
-//     store it to the tile tmp[element][row];
-// then the horizontal stage runs on the CUDA cores as in kernels_fused.cu (one thread per
-// output row, scatter into <= 8 live output pixels, epilogue), while the first two groups of
-// the next chunk are already being fetched.
+//     -- and the s8 weight-digit tile with one cp.async.bulk (two shared-memory slots);
+//   * the producer thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3
+//     digits x 32 output rows, K = 32 source rows) into one of FIVE accumulator regions of
+//     TMEM and commits to an mbarrier.  It runs ahead of the consumers as far as TMEM
+//     allows: while they execute the horizontal stage of chunk c, the tensor core already
+//     computes (almost all of) the vertical pass of chunk c + 1 -- TMEM is the double buffer;
+//   * the consumers drain a region (tcgen05.ld 32x32b), recombine the three s32 digit sums
+//     into the f32 value of the crate's vertical pass, store it to the tile
+//     tmp[element][row] and hand the region back;
+// then the consumers run the horizontal stage on the CUDA cores as in kernels_fused.cu (one
+// thread per output row, scatter into <= 8 live output pixels, epilogue).
 #include <cuda.h>
 
 #include "fused_device.cuh"
@@ -29,9 +30,11 @@ namespace fanlin {
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 256;           // consumer threads (8 warps)
+constexpr int NT_ALL = NT + 32;   // + the producer warp
+constexpr uint32_t NR = 5;        // TMEM accumulator regions of 96 columns
 constexpr int S = FUSED_SLOTS;
-constexpr uint32_t TMEM_COLS = 256;  // two accumulator buffers of 96 columns at 0 and 128
+constexpr uint32_t TMEM_COLS = 512;  // NR regions of 96 columns
 
 // Shared-memory matrix descriptor, no swizzle.  Measured on B200
 // (profiles/microbench/umma_i8.cu): LBO = byte stride between core matrices along K,
@@ -65,7 +68,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
 }
 
 template <int C>
-__global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcItem *__restrict__ items,
+__global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const FusedTcItem *__restrict__ items,
                                                                   const CUtensorMap *__restrict__ tmaps,
                                                                   const uint8_t *__restrict__ tb,
                                                                   const float *__restrict__ tw,
@@ -73,15 +76,18 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
     __shared__ FusedTcItem it_s;
-    __shared__ __align__(8) uint64_t mbar[2];  // MMAs of the group in accumulator buffer b have retired
+    __shared__ __align__(8) uint64_t mbar[NR];       // the MMAs into TMEM region r have retired
+    __shared__ __align__(8) uint64_t tmem_free[NR];  // all 8 consumer warps have drained region r
     __shared__ __align__(8) uint64_t full[2];  // the copies into shared-memory buffer b have landed
     __shared__ uint32_t tmem_base_s;
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     if (tid == 0) {
         it_s = items[blockIdx.x];
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        for (uint32_t r = 0; r < NR; r++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&tmem_free[r])));
+        }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -97,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     const FusedTcItem &it = it_s;
     const uint32_t tmem_base = tmem_base_s;
 
-    fill_bars(it, warp, lane, NT / 32);
+    if (warp < NT / 32) fill_bars(it, warp, lane, NT / 32);
 
     // ---- shared-memory carve-up
     const uint32_t r_pad = it.r_pad, kg_max = it.kg_max;
@@ -140,10 +146,10 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
     };
     // Thread 0 only: the MMAs of group g (operands in shared-memory buffer buf, accumulators in
     // TMEM buffer buf), committed to mbar[buf].
-    auto issue_mma = [&](uint32_t g, uint32_t buf) {
+    auto issue_mma = [&](uint32_t g, uint32_t buf, uint32_t region) {
         const uint32_t kg = grp[4 * g + 1];
         const uint32_t a0 = sA_u + buf * kg_max * TC_M, b0 = sB_u + buf * TC_N * kg_max;
-        const uint32_t d_tmem = tmem_base + buf * 128;
+        const uint32_t d_tmem = tmem_base + region * TC_N;
         for (uint32_t ks = 0; ks < kg / 32; ks++) {
             const uint64_t da = umma_desc(a0 + ks * 32 * 128, 16, 1024, 2);  // K step: 32 rows x 128 B; SBO = 8-row atom stride
             const uint64_t db = umma_desc(b0 + ks * 2 * 128, 128, (kg / 16) * 128);
@@ -153,12 +159,37 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
                 "r"(uint32_t(ks > 0))
                 : "memory");
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[buf])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[region])) : "memory");
     };
 
-    uint32_t uses[2] = {0, 0};       // retired MMA batches per buffer (phase of mbar[])
-    uint32_t full_uses[2] = {0, 0};  // thread 0: landed loads per buffer (phase of full[])
     auto chunk_seg0 = [&](uint32_t chunk) { return ((it.px0 + chunk * chunk_px) * C) >> 4; };
+    // Groups are numbered flat across chunks (gg = chunk * n_groups + g): shared-memory slot
+    // gg & 1, TMEM region gg % NR.
+    const uint32_t total = n_chunks * n_groups;
+
+    if (warp == NT / 32) {
+        // ================= producer warp: TMA loads + MMA issue (one thread) =================
+        if (lane == 0) {
+            uint32_t ld_chunk = 0, ld_g = 0;
+            for (uint32_t gg = 0; gg <= total; gg++) {
+                if (gg < total) {
+                    if (gg >= 2) {  // slot gg & 1 was read by the MMAs of group gg - 2
+                        mbar_wait(smem_u32(&mbar[(gg - 2) % NR]), ((gg - 2) / NR) & 1);
+                    }
+                    issue_load(ld_g, gg & 1, chunk_seg0(ld_chunk));
+                    if (++ld_g == n_groups) { ld_g = 0; ld_chunk++; }
+                }
+                if (gg >= 1) {  // MMAs of group gg - 1 (its loads were issued one iteration ago)
+                    const uint32_t pg = gg - 1, region = pg % NR, use = pg / NR;
+                    mbar_wait(smem_u32(&full[pg & 1]), (pg >> 1) & 1);
+                    if (use > 0) mbar_wait(smem_u32(&tmem_free[region]), (use - 1) & 1);  // consumers drained its previous contents
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    issue_mma(pg % n_groups, pg & 1, region);
+                }
+            }
+        }
+    } else {
+    // ================= consumer warps =================
     auto stage_htab = [&](uint32_t chunk) {  // the chunk's slice of the horizontal table -> its shared-memory copy
         const uint32_t cpx0 = chunk * chunk_px, npx = min(chunk_px, n_px - cpx0);
         float *dstw = hw_s0 + (chunk & 1) * htab_words;
@@ -168,57 +199,30 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
         for (uint32_t k = tid; k < npx; k += NT) cp_async4(sa_i + 4 * k, hinfo + cpx0 + k, true);
         cp_async_commit();
     };
-
-    // Groups are numbered flat across chunks (gg = chunk * n_groups + g): buffer = gg & 1, and
-    // the load / MMA cursors of thread 0 simply run 2 and 1 groups ahead of the epilogue.
-    const uint32_t total = n_chunks * n_groups;
-    uint32_t ld_chunk = 0, ld_g = 0, ld_gg = 0;  // thread 0: next group to fetch
-    auto load_next = [&]() {
-        if (ld_gg < total) {
-            issue_load(ld_g, ld_gg & 1, chunk_seg0(ld_chunk));
-            ld_gg++;
-            if (++ld_g == n_groups) { ld_g = 0; ld_chunk++; }
-        }
-    };
     stage_htab(0);
-    if (tid == 0) {
-        load_next();
-        load_next();
-        mbar_wait(smem_u32(&full[0]), 0);
-        full_uses[0]++;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        issue_mma(0, 0);
-    }
 
     uint32_t gg = 0;
     for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
         const uint32_t cpx0 = chunk * chunk_px;
         const uint32_t npx = min(chunk_px, n_px - cpx0);
         const uint32_t sh = ((it.px0 + cpx0) * C) & 15u;  // padding columns in front of the chunk
-        // ================= vertical stage: tensor cores =================
+        // ================= vertical stage: drain the tensor-core results =================
         for (uint32_t g = 0; g < n_groups; g++, gg++) {
-            const uint32_t buf = gg & 1;
-            mbar_wait(smem_u32(&mbar[buf]), uses[buf] & 1);  // the MMAs of group gg have retired
-            uses[buf]++;
+            const uint32_t region = gg % NR;
+            mbar_wait(smem_u32(&mbar[region]), (gg / NR) & 1);  // the MMAs of group gg have retired
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (tid == 0) load_next();  // shared-memory buffer `buf` is free: fetch group gg + 2
-            __syncthreads();  // every warp is done with the epilogue of group gg - 1: TMEM buffer buf ^ 1 is free
-            if (tid == 0 && gg + 1 < total) {
-                mbar_wait(smem_u32(&full[buf ^ 1]), full_uses[buf ^ 1] & 1);
-                full_uses[buf ^ 1]++;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_mma(g + 1 < n_groups ? g + 1 : 0, buf ^ 1);  // runs on the tensor core while the warps drain group gg
-            }
-            // ---- epilogue: TMEM -> f32 tile.  Warp w reads lanes [32 (w & 3), +32) (= tile
-            // columns m) and the half (w >> 2) of the group's 32 output rows.
+            // TMEM -> f32 tile.  Warp w reads lanes [32 (w & 3), +32) (= tile columns m) and the
+            // half (w >> 2) of the group's 32 output rows.
             {
                 const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane;
-                const uint32_t taddr = tmem_base + buf * 128 + (((warp & 3) * 32u) << 16) + half * 16;
+                const uint32_t taddr = tmem_base + region * TC_N + (((warp & 3) * 32u) << 16) + half * 16;
                 uint32_t hi[16], mid[16], lo[16];
                 tmem_ld16(taddr, hi);
                 tmem_ld16(taddr + 32, mid);
                 tmem_ld16(taddr + 64, lo);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[region])) : "memory");
                 const uint32_t r0 = g * TC_GROUP_ROWS + half * 16;
                 float *t = tmp + size_t(m) * r_pad + r0;
 #pragma unroll
@@ -233,12 +237,11 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
                     if (r0 + 4 * q < r_pad) *reinterpret_cast<float4 *>(t + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
         if (chunk + 1 < n_chunks) stage_htab(chunk + 1);  // lands during this chunk's horizontal stage
         else cp_async_commit();
         cp_async_wait<1>();  // this chunk's table slice (committed one chunk ago) has landed
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // consumers only: the tile is complete
         // ================= horizontal stage: CUDA cores =================
         if (h_active) {
             const float *tcol = tmp + tid + size_t(sh) * r_pad;
@@ -273,8 +276,9 @@ __global__ void __launch_bounds__(NT, 1) fused_resample_tc_kernel(const FusedTcI
                 }
             }
         }
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the tile may be overwritten
     }
+    }  // consumer warps
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
@@ -286,7 +290,7 @@ void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t
     auto kern = fused_resample_tc_kernel<C>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     lc.begin("fused_resample_tc_kernel");
-    kern<<<n_items, NT, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info);
+    kern<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info);
     lc.end();
 }
 
