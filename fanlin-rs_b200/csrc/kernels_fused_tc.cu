@@ -59,6 +59,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ void ffma2(float2 &acc, float2 a, float w) {
+    const float2 b = make_float2(w, w);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;"
+        : "+l"(reinterpret_cast<unsigned long long &>(acc))
+        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -120,11 +127,17 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
 
     // ---- horizontal-stage role of this thread: one output row of the band
     const bool h_active = tid < it.band_rows;
-    float hacc[S][C];
+    // accumulators of the <= 8 live output pixels: channel pairs as f32x2 (one FFMA2 issue slot
+    // per pair; the stage is issue-bound, not FMA-pipe-bound), the odd channel as a scalar
+    constexpr int CP = C / 2, CO = C & 1;
+    float2 hacc2[S][CP > 0 ? CP : 1];
+    float hacc1[S];
 #pragma unroll
-    for (int j = 0; j < S; j++)
+    for (int j = 0; j < S; j++) {
 #pragma unroll
-        for (int k = 0; k < C; k++) hacc[j][k] = 0.f;
+        for (int k = 0; k < (CP > 0 ? CP : 1); k++) hacc2[j][k] = make_float2(0.f, 0.f);
+        hacc1[j] = 0.f;
+    }
     uint32_t h_next = 0;
     const float *hw = tw + it.hw_off;
     const uint32_t *hinfo = tinfo + it.hinfo_off;
@@ -247,19 +260,15 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             const float *tcol = tmp + tid + size_t(sh) * r_pad;
             const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
             const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
-#pragma unroll 2
-            for (uint32_t xl = 0; xl < npx; xl++) {
-                float v[C];
-#pragma unroll
-                for (int k = 0; k < C; k++) v[k] = tcol[size_t(xl * C + k) * r_pad];
-                const uint32_t info = hinfo_s[xl];
-                const float4 w0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
-                const float4 w1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
+            // one pixel: scatter its C values into the live slots, then flush completed outputs
+            auto step = [&](const float (&v)[C], const float4 &w0, const float4 &w1, uint32_t info) {
                 const float w[S] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int j = 0; j < S; j++)
+                for (int j = 0; j < S; j++) {
 #pragma unroll
-                    for (int k = 0; k < C; k++) hacc[j][k] = fmaf(v[k], w[j], hacc[j][k]);
+                    for (int k = 0; k < CP; k++) ffma2(hacc2[j][k], make_float2(v[2 * k], v[2 * k + 1]), w[j]);
+                    if (CO) hacc1[j] = fmaf(v[C - 1], w[j], hacc1[j]);
+                }
                 const uint32_t fl = (info >> 8) & 0xffu;
                 if (fl) {
 #pragma unroll
@@ -268,12 +277,33 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                             const uint32_t o = h_next + ((uint32_t(j) - h_next) & (S - 1));
                             uint32_t u[4] = {0, 0, 0, 0};
 #pragma unroll
-                            for (int k = 0; k < C; k++) { u[k] = round_u8(hacc[j][k]); hacc[j][k] = 0.f; }
+                            for (int k = 0; k < CP; k++) {
+                                u[2 * k] = round_u8(hacc2[j][k].x);
+                                u[2 * k + 1] = round_u8(hacc2[j][k].y);
+                                hacc2[j][k] = make_float2(0.f, 0.f);
+                            }
+                            if (CO) { u[C - 1] = round_u8(hacc1[j]); hacc1[j] = 0.f; }
                             emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy, u);
                         }
                     }
                     h_next += __popc(fl);
                 }
+            };
+            // two pixels per iteration: all shared-memory reads of both are issued before the FMAs
+            for (uint32_t xl = 0; xl < npx; xl += 2) {
+                const bool two = xl + 1 < npx;
+                float va[C], vb[C];
+#pragma unroll
+                for (int k = 0; k < C; k++) va[k] = tcol[size_t(xl * C + k) * r_pad];
+#pragma unroll
+                for (int k = 0; k < C; k++) vb[k] = tcol[size_t((xl + 1) * C + k) * r_pad];  // within the tile even past npx
+                const uint32_t ia = hinfo_s[xl], ib = hinfo_s[xl + 1];
+                const float4 wa0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
+                const float4 wa1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
+                const float4 wb0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl + 1) * S);
+                const float4 wb1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl + 1) * S + 4);
+                step(va, wa0, wa1, ia);
+                if (two) step(vb, wb0, wb1, ib);
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the tile may be overwritten
