@@ -157,3 +157,48 @@ def test_full_size_c2_properties(fanlin, dev):
     want = O.process(imgs[0], w=300, h=200)
     h = hist(gots[0], want)
     assert h[">=2"] == 0, h
+
+
+# ---- the three resample paths against each other and the oracle ----------------------------
+
+@pytest.fixture(scope="module")
+def dev_cuda_cores(fanlin):
+    d = fanlin.Device([0], tensor_cores=False)
+    yield d
+    d.close()
+
+
+PATH_CASES = [
+    # (seed, h, w, c, query): shapes chosen to hit 1 / 2 / 3 / 4 channels, several bands (> 192 output rows),
+    # odd numbers of 32-row groups, crop windows that start off the 16-byte grid, and upscales (generic path)
+    (11, 1080, 1920, 3, "w=300&h=200"),
+    (12, 540, 960, 4, "w=404&h=250&crop=true"),
+    (13, 600, 800, 1, "w=333&h=250"),
+    (14, 600, 800, 2, "w=320&h=240&rgb=9,8,7"),
+    (15, 1500, 1000, 3, "w=500&h=750"),          # 750 output rows: 4 bands
+    (16, 900, 1200, 3, "w=401&h=301&crop=true"),  # 301 rows: bands of 160 + 141 (5 groups each)
+    (17, 700, 1100, 4, "w=97&h=89&crop=true"),    # ratio 7.9: kg near the 256-row limit
+    (18, 480, 640, 3, "w=640&h=300"),             # horizontal ratio 1 (aspect fit by height)
+    (19, 300, 400, 3, "w=800&h=600"),             # upscale: more than 8 live outputs -> generic kernels
+    (20, 1080, 1920, 3, "w=300&h=200&inverse=true"),
+    (21, 1080, 1920, 3, "w=300&h=200&grayscale=true"),
+    (22, 540, 960, 4, "w=300&h=200&grayscale=true"),
+]
+
+
+@pytest.mark.parametrize("seed,h,w,c,qs", PATH_CASES, ids=[f"{p[1]}x{p[2]}x{p[3]}-{p[4]}" for p in PATH_CASES])
+def test_resample_paths_agree(fanlin, dev, dev_cuda_cores, dev_exact, seed, h, w, c, qs):
+    img = synth_image(seed, h, w, c)
+    q = fanlin.Query(qs)
+    kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+    kw["w"], kw["h"] = q.dimensions()
+    want = O.process(img, **kw)
+    exact = fanlin.process_image(dev_exact, img, q)
+    assert np.array_equal(exact, want), hist(exact, want)
+    for name, d in (("tensor-core", dev), ("cuda-core", dev_cuda_cores)):
+        got = fanlin.process_image(d, img, q)
+        assert got.shape == want.shape
+        hh = hist(got, want)
+        print(name, qs, "mismatch histogram", hh)
+        assert hh[">=2"] == 0, (name, hh)
+        assert hh[1] <= 0.002 * want.size, (name, hh)  # off-by-one only where the f32 sum sits on a rounding boundary
