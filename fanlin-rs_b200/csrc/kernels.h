@@ -52,6 +52,10 @@ int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_
 // Host: encodes the TMA tensor map (128 bytes at `out`) through which that kernel fetches rows of
 // one image: dims {row bytes, rows}, box {128 B, box_rows}, 128-byte swizzle.  Returns false on failure.
 bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t rows, uint32_t box_rows);
+// Fast Gaussian blur (kernels_blur.cu): items share channel count, radius and padded tap count.
+struct BlurItem;
+int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
+                uint32_t taps_pad, const float *d_w, LaunchCtx &lc);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 

@@ -1,0 +1,179 @@
+// Separable Gaussian blur (image-0.25.6 imageops::blur as called by reference
+// src/handler.rs:250-255): vertical pass u8 -> f32, horizontal pass f32 -> u8,
+// 2*floor(2 sigma)+1 taps (41..81), windows truncated at the borders and renormalised.
+//
+// Both passes stage a tile with its halo in shared memory as f32 and slide a register window
+// along the filtered axis: per 8 taps a thread loads 8 new values and issues 64 FMAs for its 8
+// outputs (weights broadcast from shared memory), so the kernels run near the FP32 issue rate
+// instead of one shared-memory load per FMA.  The crate's border handling -- weights divided by
+// the sum of the taps that fall inside the image -- is applied as one per-row / per-column
+// factor after accumulating with the interior weights and zeros outside the image; that is the
+// same value up to f32 rounding (the parity tests bound the result to 1 LSB).
+#include "blur.h"
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace fanlin {
+
+namespace {
+
+constexpr int VT = 128;    // vertical kernel: threads = element columns per block
+constexpr int V_ROWS = 64; // output rows per block
+constexpr int HT = 256;    // horizontal kernel threads
+constexpr int H_PX = 32;   // output pixels per block row
+
+// ---- vertical pass: src u8 [h][pitch] -> tmp f32 [h][w*c] ------------------------------------
+__global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__ items, const float *__restrict__ tw) {
+    extern __shared__ __align__(16) float sm[];  // u[taps_pad], then tile [(V_ROWS + 2R)][VT]
+    const BlurItem it = items[blockIdx.z];
+    const uint32_t n_e = it.w * it.c;
+    const uint32_t e0 = blockIdx.x * VT, y0 = blockIdx.y * V_ROWS;
+    if (e0 >= n_e || y0 >= it.h) return;
+    const uint32_t R = it.radius, taps_pad = it.taps_pad;
+    float *u_s = sm;
+    float *tile = sm + taps_pad;
+    const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    for (uint32_t k = t; k < taps_pad; k += VT) u_s[k] = tw[it.u_off + k];
+    // stage rows [y0 - R, y0 + V_ROWS + R + 7): one warp per row, 4 bytes per lane
+    const uint32_t n_rows_tile = V_ROWS + 2 * R + 8;  // + 8: the window reads ahead inside the last (zero-weight) taps
+    for (uint32_t r = warp; r < n_rows_tile; r += VT / 32) {
+        const int y = int(y0 + r) - int(R);
+        float f[4] = {0.f, 0.f, 0.f, 0.f};
+        if (y >= 0 && y < int(it.h)) {
+            const uint8_t *row = it.src + size_t(y) * it.src_pitch;
+            const uint32_t e = e0 + 4 * lane;
+            if (it.aligned4 && e + 3 < n_e) {
+                const uint32_t wv = __ldg(reinterpret_cast<const uint32_t *>(row + e));
+                f[0] = float(wv & 0xff); f[1] = float((wv >> 8) & 0xff); f[2] = float((wv >> 16) & 0xff); f[3] = float(wv >> 24);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (e + q < n_e) f[q] = float(row[e + q]);
+            }
+        }
+        *reinterpret_cast<float4 *>(tile + size_t(r) * VT + 4 * lane) = make_float4(f[0], f[1], f[2], f[3]);
+    }
+    __syncthreads();
+    const uint32_t e = e0 + t;
+    const float *col = tile + t;
+    for (uint32_t p = 0; p < V_ROWS / 8; p++) {
+        const uint32_t j0 = y0 + 8 * p;
+        if (j0 >= it.h) break;
+        float acc[8], x[16];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { acc[i] = 0.f; x[i] = col[size_t(8 * p + i) * VT]; }
+        for (uint32_t k0 = 0; k0 < taps_pad; k0 += 8) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(u_s + k0), w1 = *reinterpret_cast<const float4 *>(u_s + k0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[8 + i] = col[size_t(8 * p + k0 + 8 + i) * VT];
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++)
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = x[8 + i];
+        }
+        if (e < n_e) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++)
+                if (j0 + jj < it.h) it.tmp[size_t(j0 + jj) * n_e + e] = acc[jj] * tw[it.corrv_off + j0 + jj];
+        }
+    }
+}
+
+// ---- horizontal pass: tmp f32 [h][w*c] -> dst u8 [h][w*c] --------------------------------------
+__global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__ items, const float *__restrict__ tw) {
+    extern __shared__ __align__(16) float sm[];  // u[taps_pad], tile [rb][pitch], then the u8 output tile
+    const BlurItem it = items[blockIdx.z];
+    const uint32_t C = it.c;
+    const uint32_t rb = HT / C;  // rows per block
+    const uint32_t x0 = blockIdx.x * H_PX, y0 = blockIdx.y * rb;
+    if (x0 >= it.w || y0 >= it.h) return;
+    const uint32_t R = it.radius, taps_pad = it.taps_pad;
+    const uint32_t n_px_tile = H_PX + 2 * R + 8;
+    uint32_t pitch = n_px_tile * C;             // floats per tile row, == C (mod 32): conflict-free for lanes = (row, channel)
+    pitch += (C + 32 - (pitch & 31)) & 31;
+    float *u_s = sm;
+    float *tile = sm + taps_pad;
+    uint8_t *out_s = reinterpret_cast<uint8_t *>(tile + size_t(rb) * pitch);  // [rb][H_PX * C]
+    const uint32_t t = threadIdx.x;
+    for (uint32_t k = t; k < taps_pad; k += HT) u_s[k] = tw[it.u_off + k];
+    const uint32_t n_e = it.w * C;
+    // stage: tile row r <- tmp[y0 + r][(x0 - R) * C ...), zeros outside the image
+    const uint32_t row_elems = n_px_tile * C;
+    for (uint32_t r = t >> 5; r < rb; r += HT / 32) {  // one warp per row: coalesced, no index division
+        const uint32_t y = y0 + r;
+        const float *src = it.tmp + size_t(y) * n_e;
+        const int ge0 = int(x0 * C) - int(R * C);
+#pragma unroll 4
+        for (uint32_t i = t & 31; i < row_elems; i += 32) {
+            const int ge = ge0 + int(i);
+            tile[size_t(r) * pitch + i] = (y < it.h && ge >= 0 && ge < int(n_e)) ? __ldg(src + ge) : 0.f;
+        }
+    }
+    __syncthreads();
+    const uint32_t rows_here = min(rb, it.h - y0);
+    if (t < rb * C) {
+        const uint32_t r = t / C, ch = t - r * C;
+        const float *rowp = tile + size_t(r) * pitch + ch;
+        for (uint32_t p = 0; p < H_PX / 8; p++) {
+            float acc[8], x[16];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { acc[i] = 0.f; x[i] = rowp[size_t(8 * p + i) * C]; }
+            for (uint32_t k0 = 0; k0 < taps_pad; k0 += 8) {
+                const float4 w0 = *reinterpret_cast<const float4 *>(u_s + k0), w1 = *reinterpret_cast<const float4 *>(u_s + k0 + 4);
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[8 + i] = rowp[size_t(8 * p + k0 + 8 + i) * C];
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++)
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = x[8 + i];
+            }
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const uint32_t x = x0 + 8 * p + jj;
+                const float cf = x < it.w ? tw[it.corrh_off + x] : 0.f;
+                out_s[size_t(r) * (H_PX * C) + (8 * p + jj) * C + ch] = uint8_t(round_u8(acc[jj] * cf));
+            }
+        }
+    }
+    __syncthreads();
+    // coalesced store of the u8 tile
+    const uint32_t px_here = min(uint32_t(H_PX), it.w - x0), bytes_row = px_here * C;
+    for (uint32_t r = t >> 5; r < rows_here; r += HT / 32) {  // one warp per row
+        uint8_t *d = it.dst + size_t(y0 + r) * n_e + size_t(x0) * C;
+        for (uint32_t i = t & 31; i < bytes_row; i += 32) d[i] = out_s[size_t(r) * (H_PX * C) + i];
+    }
+}
+
+}  // namespace
+
+size_t blur_v_smem(uint32_t radius, uint32_t taps_pad) { return (size_t(taps_pad) + size_t(V_ROWS + 2 * radius + 8) * VT) * 4; }
+size_t blur_h_smem(uint32_t radius, uint32_t taps_pad, uint32_t c) {
+    const uint32_t rb = HT / c;
+    uint32_t pitch = (H_PX + 2 * radius + 8) * c;
+    pitch += (c + 32 - (pitch & 31)) & 31;
+    return (size_t(taps_pad) + size_t(rb) * pitch) * 4 + size_t(rb) * H_PX * c + 16;
+}
+
+int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
+                uint32_t taps_pad, const float *d_w, LaunchCtx &lc) {
+    if (n_items == 0) return 0;
+    const size_t sv = blur_v_smem(radius, taps_pad), sh = blur_h_smem(radius, taps_pad, c);
+    cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv));
+    cudaFuncSetAttribute(blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sh));
+    const uint32_t rb = HT / c;
+    lc.begin("blur_v_kernel");
+    blur_v_kernel<<<dim3((max_w * c + VT - 1) / VT, (max_h + V_ROWS - 1) / V_ROWS, n_items), VT, sv, lc.st>>>(d_items, d_w);
+    lc.end();
+    lc.begin("blur_h_kernel");
+    blur_h_kernel<<<dim3((max_w + H_PX - 1) / H_PX, (max_h + rb - 1) / rb, n_items), HT, sh, lc.st>>>(d_items, d_w);
+    lc.end();
+    return 2;
+}
+
+}  // namespace fanlin

@@ -4,6 +4,7 @@
 #include "runtime.h"
 
 #include "fused.h"
+#include "blur.h"
 #include "fused_tc.h"
 
 #include <algorithm>
@@ -262,6 +263,9 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(), fused_tc_cache_free);
     FusedTcTables tctabs;
     const bool use_tc = ctx->cfg.vertical_path == 0;
+    std::vector<uint8_t> fast_b(n_jobs, 0);  // stage B takes the fast blur kernels
+    BlurTables btabs;
+    std::vector<BlurItem> bitems;
 
     // 1. plans + table arena
     std::map<const AxisTable *, uint32_t> tab_base;
@@ -287,7 +291,8 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
         if (!exact && use_tc && fused_tc_eligible(p.a, jobs[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) fused_a[i] = 2;
         else fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
-        add_table(p.b.vtab); add_table(p.b.htab);
+        fast_b[i] = !exact && blur_eligible(p.b);
+        if (!fast_b[i]) { add_table(p.b.vtab); add_table(p.b.htab); }
     }
 
     // 2. scratch layout, chunked so one chunk fits the scratch budget
@@ -301,7 +306,7 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
             if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_w) * p.a.canvas_h * p.a.c_out, 256);
             size_t ta = 0, tb = 0;
             if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
-            if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;
+            if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of either blur path
             js[i].tmp = align_up(std::max(ta, tb), 256);
             const size_t need = js[i].inter + js[i].tmp;
             if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
@@ -368,6 +373,7 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
                 if (!s.present) continue;
                 if (pass == 0 && (!s.separable || fused_a[i])) continue;
                 if (pass == 1 && s.separable) continue;
+                if (pass == 2 && fast_b[i]) continue;
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 float *tmp = js[i].tmp ? reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off) : nullptr;
                 StageDesc d;
@@ -377,6 +383,33 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
                 descs.push_back(d);
             }
             if (hs.g.n_jobs) hsteps.push_back(hs);
+        }
+        // stage B through the fast blur kernels, one launch pair per (channels, sigma)
+        std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> blur_groups;
+        for (uint32_t i = begin; i < end; i++)
+            if (fast_b[i]) {
+                uint32_t sb;
+                std::memcpy(&sb, &b->plans[i].b.sigma, 4);
+                blur_groups[{b->plans[i].b.c, sb}].push_back(i);
+            }
+        for (auto &kv : blur_groups) {
+            HostStep hs{4, bitems.size(), LaunchGeom{}, 0, 0, 0, 0};
+            for (uint32_t i : kv.second) {
+                const JobPlan &p = b->plans[i];
+                BlurItem bi{};
+                blur_build(p.b, &btabs, &ftabs.w, &bi);
+                uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
+                bi.src = p.b.src_is_input ? jobs[i].src : inter;
+                bi.src_pitch = p.b.src_is_input ? (jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels) : p.b.in_w * p.b.c;
+                bi.dst = jobs[i].dst;
+                bi.tmp = reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off);
+                bi.aligned4 = (bi.src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(bi.src) & 3) == 0);
+                hs.g.max_canvas_w = std::max(hs.g.max_canvas_w, bi.w);
+                hs.g.max_canvas_h = std::max(hs.g.max_canvas_h, bi.h);
+                hs.variant = bi.c; hs.n_items++; hs.max_band = bi.radius; hs.smem = bi.taps_pad;
+                bitems.push_back(bi);
+            }
+            hsteps.push_back(hs);
         }
         begin = end;
     }
@@ -390,10 +423,12 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     const size_t off_ti = off_fn + align_up(ftabs.info.size() * sizeof(uint32_t), 256);
     const size_t off_tb = off_ti + align_up(tcitems.size() * sizeof(FusedTcItem), 256);
     const size_t off_tm = off_tb + align_up(tctabs.b.size(), 256);
-    const size_t meta_bytes = off_tm + tcitems.size() * 128 + 256;
+    const size_t off_bi = off_tm + align_up(tcitems.size() * 128, 256);
+    const size_t meta_bytes = off_bi + align_up(bitems.size() * sizeof(BlurItem), 256) + 256;
     std::vector<uint8_t> meta(meta_bytes, 0);
     if (!tcitems.empty()) std::memcpy(meta.data() + off_ti, tcitems.data(), tcitems.size() * sizeof(FusedTcItem));
     if (!tctabs.b.empty()) std::memcpy(meta.data() + off_tb, tctabs.b.data(), tctabs.b.size());
+    if (!bitems.empty()) std::memcpy(meta.data() + off_bi, bitems.data(), bitems.size() * sizeof(BlurItem));
     for (size_t k = 0; k < tcitems.size(); k++) {  // one TMA tensor map per (image, band): box rows = the band's kg_max
         if (!encode_row_tile_map(meta.data() + off_tm + k * 128, tcitems[k].src, tcitems[k].src_pitch, tcitems[k].src_h, tcitems[k].kg_max)) {
             set_error("fanlin: cuTensorMapEncodeTiled failed");
@@ -416,6 +451,19 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     b->d_finfo = reinterpret_cast<const uint32_t *>(mbase + off_fn);
     b->d_tb = mbase + off_tb;
     for (const HostStep &hs : hsteps) {
+        if (hs.kind == 4) {
+            for (uint32_t o = 0; o < hs.n_items; o += 65535) {  // grid.z carries the job index
+                fanlin_batch::Step st{};
+                st.kind = 4;
+                st.blur_items = reinterpret_cast<const BlurItem *>(mbase + off_bi) + hs.first + o;
+                st.n_items = std::min<uint32_t>(65535, hs.n_items - o);
+                st.max_w = hs.g.max_canvas_w; st.max_h = hs.g.max_canvas_h;
+                st.c = hs.variant; st.radius = hs.max_band; st.taps_pad = uint32_t(hs.smem);
+                b->steps.push_back(st);
+                b->launches_per_run += 2;
+            }
+            continue;
+        }
         if (hs.kind == 3) {
             fanlin_batch::Step st{};
             st.kind = 3;
@@ -467,7 +515,9 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
         lc.used = b->ev_used;
     }
     for (const fanlin_batch::Step &s : b->steps) {
-        if (s.kind == 3) {
+        if (s.kind == 4) {
+            n += launch_blur(s.blur_items, s.n_items, s.max_w, s.max_h, s.c, s.radius, s.taps_pad, b->d_fw, lc);
+        } else if (s.kind == 3) {
             const int k = launch_fused_tc(s.tc_items, s.tmaps, s.n_items, s.variant, s.smem, b->d_tb, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no tensor-core kernel variant"); return FANLIN_EINVAL; }
             n += k;

@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Times every BASELINE.json config shape (device-resident, reduced batch) through the C ABI and
+checks a sample against the oracle.  Not the driver's bench (that is bench.py, config C2); this
+records where the other configs stand.  Usage: python tools/bench_configs.py [--batch N]"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CONFIGS = [
+    ("C1 lenna-shaped 512x512 RGB fit+fill", 512, 512, 3, "w=300&h=200&rgb=32,32,32", False, 1024),
+    ("C2 1080p RGB fit+fill", 1080, 1920, 3, "w=300&h=200", False, 592),
+    ("C3 4K RGBA crop (no blur)", 2160, 3840, 4, "w=1618&h=1000&crop=true", False, 148),
+    ("C3 4K RGBA crop + blur=10", 2160, 3840, 4, "w=1618&h=1000&crop=true&blur=10", False, 32),
+    ("C4 GIF frames literal (grayscale only)", 270, 480, 4, "w=200&grayscale=true&inverse=true", True, 200),
+    ("C4' GIF frames w=200&h=113 nearest", 270, 480, 4, "w=200&h=113&grayscale=true&inverse=true", True, 200),
+    ("C5 12MP RGB crop+gray (no blur)", 3000, 4000, 3, "w=1618&h=1000&crop=true&grayscale=true", False, 148),
+    ("C5 12MP RGB fit+fill+gray (no blur)", 3000, 4000, 3, "w=1618&h=1000&grayscale=true", False, 148),
+    ("C5 12MP RGB crop+gray+blur=10", 3000, 4000, 3, "w=1618&h=1000&crop=true&grayscale=true&blur=10", False, 32),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes")
+    ap.add_argument("--steps", type=int, default=3)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import __graft_entry__ as G
+    from oracle import oracle as O
+    from synth import synth_image
+
+    pkg = G.load_package()
+    dev = pkg.Device([0])
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    device = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(device)
+    out = []
+    for name, h, w, c, qs, gif, batch in CONFIGS:
+        n = max(1, int(batch * args.scale))
+        base = [torch.from_numpy(synth_image(900 + i, h, w, c)).to(device) for i in range(4)]
+        src = torch.stack([base[i % 4] for i in range(n)]).contiguous()
+        q = pkg.Query(qs)
+        proto = pkg.Job()
+        pkg.lib().fanlin_job_from_query(C.byref(q._q), int(gif), C.byref(proto))
+        proto.src_w, proto.src_h, proto.src_channels = w, h, c
+        plan = pkg.plan_job(proto)
+        dst = torch.zeros((n, plan.out_h, plan.out_w, plan.out_channels), dtype=torch.uint8, device=device)
+        jobs = (pkg.Job * n)()
+        for i in range(n):
+            C.memmove(C.byref(jobs, i * C.sizeof(pkg.Job)), C.byref(proto), C.sizeof(pkg.Job))
+            jobs[i].src = src.data_ptr() + i * h * w * c
+            jobs[i].dst = dst.data_ptr() + i * plan.out_bytes
+            jobs[i].dst_capacity = plan.out_bytes
+        b = dev.prepare(jobs, 0)
+        b.set_timing(True)
+        b.launch(stream.cuda_stream)
+        torch.cuda.synchronize()
+        b.kernel_times()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            b.launch(stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        kt = {}
+        for k, v in b.kernel_times():
+            kt.setdefault(k, []).append(v)
+        kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=0.0 if gif else q.blur(), rgb=q.fill_color(), gif=gif)
+        if q.dimensions():
+            kw["w"], kw["h"] = q.dimensions()
+        want = O.process(base[1].cpu().numpy(), **kw)
+        got = dst[1].cpu().numpy()
+        d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+        alg = plan.algorithmic_bytes * n
+        rec = dict(config=name, query=qs, batch=n, ms=ms, us_per_image=ms * 1e3 / n, out_mpix_s=n * plan.out_w * plan.out_h / 1e6 / (ms * 1e-3),
+                   hbm_frac=alg / (ms * 1e-3) / 1e9 / peak, kernels_ms={k: sum(v) / len(v) for k, v in kt.items()},
+                   parity=dict(diff1=int((d == 1).sum()), diff_ge2=int((d >= 2).sum()), n=int(d.size)))
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+        b.free()
+        del src, dst
+        torch.cuda.empty_cache()
+    dev.close()
+
+
+if __name__ == "__main__":
+    main()
