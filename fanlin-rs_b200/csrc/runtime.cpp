@@ -237,14 +237,32 @@ void geom_add(LaunchGeom *g, const StageDesc &d) {
 extern "C" void fanlin_batch_free(fanlin_batch *b) {
     if (!b) return;
     if (b->dev) cudaSetDevice(b->dev->ordinal);
-    if (b->d_meta) cudaFree(b->d_meta);
-    if (b->d_scratch) cudaFree(b->d_scratch);
+    if (b->d_meta) cudaFreeAsync(b->d_meta, b->alloc_stream);
+    if (b->d_scratch) cudaFreeAsync(b->d_scratch, b->alloc_stream);
+    if (b->h_meta && b->ctx) b->ctx->pinned.free(b->h_meta);
     for (cudaEvent_t e : b->events) cudaEventDestroy(e);
     delete b;
 }
 
+static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job *jobs, uint32_t n_jobs, fanlin_plan *plans_out,
+                             fanlin_batch **out, cudaStream_t up_stream);
+
 extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fanlin_job *jobs, uint32_t n_jobs,
                                     fanlin_plan *plans_out, fanlin_batch **out) {
+    if (!ctx || !out || (!jobs && n_jobs)) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
+    if (device_index < 0 || device_index >= int(ctx->devs.size())) { set_error("fanlin: bad device index"); return FANLIN_EINVAL; }
+    DeviceState *dev = ctx->devs[device_index].get();
+    const int rc = prepare_on_stream(ctx, device_index, jobs, n_jobs, plans_out, out, dev->stream);
+    if (rc != FANLIN_OK) return rc;
+    // the caller may launch on any stream: make the uploaded descriptors visible first
+    if (cudaStreamSynchronize(dev->stream) != cudaSuccess) { set_error("fanlin: CUDA error while uploading batch descriptors"); return FANLIN_ECUDA; }
+    return FANLIN_OK;
+}
+
+// Plans the jobs, builds tables and descriptors and enqueues their upload on `up_stream`
+// (launches on that stream are ordered after it; no host synchronisation).
+static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job *jobs, uint32_t n_jobs, fanlin_plan *plans_out,
+                             fanlin_batch **out, cudaStream_t up_stream) {
     if (!ctx || !out || (!jobs && n_jobs)) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
     *out = nullptr;
     if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
@@ -320,7 +338,8 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
         }
         chunk_end.push_back(n_jobs);
     }
-    if (scratch_bytes) CUDA_TRY(cudaMalloc(&b->d_scratch, scratch_bytes));
+    b->alloc_stream = up_stream;
+    if (scratch_bytes) CUDA_TRY(cudaMallocAsync(&b->d_scratch, scratch_bytes, up_stream));  // stream-ordered pool: no device sync
 
     // 3. descriptors per chunk and stage kind
     std::vector<StageDesc> descs;
@@ -425,7 +444,13 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     const size_t off_tm = off_tb + align_up(tctabs.b.size(), 256);
     const size_t off_bi = off_tm + align_up(tcitems.size() * 128, 256);
     const size_t meta_bytes = off_bi + align_up(bitems.size() * sizeof(BlurItem), 256) + 256;
-    std::vector<uint8_t> meta(meta_bytes, 0);
+    b->h_meta = ctx->pinned.alloc(meta_bytes);  // pinned, kept until the batch is freed: the upload is asynchronous
+    if (!b->h_meta) { set_error("fanlin: pinned allocation failed"); return FANLIN_ENOMEM; }
+    struct MetaView {
+        uint8_t *p;
+        uint8_t *data() { return p; }
+    } meta{static_cast<uint8_t *>(b->h_meta)};
+    std::memset(meta.data(), 0, meta_bytes);
     if (!tcitems.empty()) std::memcpy(meta.data() + off_ti, tcitems.data(), tcitems.size() * sizeof(FusedTcItem));
     if (!tctabs.b.empty()) std::memcpy(meta.data() + off_tb, tctabs.b.data(), tctabs.b.size());
     if (!bitems.empty()) std::memcpy(meta.data() + off_bi, bitems.data(), bitems.size() * sizeof(BlurItem));
@@ -441,9 +466,8 @@ extern "C" int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
     if (!descs.empty()) std::memcpy(meta.data(), descs.data(), descs.size() * sizeof(StageDesc));
     if (!entries.empty()) std::memcpy(meta.data() + off_tab, entries.data(), entries.size() * sizeof(TapEntry));
     if (!weights.empty()) std::memcpy(meta.data() + off_w, weights.data(), weights.size() * sizeof(float));
-    CUDA_TRY(cudaMalloc(&b->d_meta, meta_bytes));
-    CUDA_TRY(cudaMemcpyAsync(b->d_meta, meta.data(), meta_bytes, cudaMemcpyHostToDevice, dev->stream));
-    CUDA_TRY(cudaStreamSynchronize(dev->stream));
+    CUDA_TRY(cudaMallocAsync(&b->d_meta, meta_bytes, up_stream));
+    CUDA_TRY(cudaMemcpyAsync(b->d_meta, meta.data(), meta_bytes, cudaMemcpyHostToDevice, up_stream));
     const uint8_t *mbase = static_cast<const uint8_t *>(b->d_meta);
     b->d_tab = reinterpret_cast<const TapEntry *>(mbase + off_tab);
     b->d_w = reinterpret_cast<const float *>(mbase + off_w);
@@ -562,62 +586,105 @@ extern "C" int fanlin_batch_kernel_times(fanlin_batch *b, const char **names, fl
 
 namespace {
 
-// Runs jobs[first, last) (host pointers) on one device: stage in, launch, stage out.
+// One sub-batch in flight on one stream: device staging buffers and the prepared batch.
+struct Flight {
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    fanlin_batch *batch = nullptr;
+    cudaStream_t st = nullptr;
+    void release() {
+        if (batch) fanlin_batch_free(batch);
+        if (d_in) cudaFreeAsync(d_in, st);
+        if (d_out) cudaFreeAsync(d_out, st);
+        batch = nullptr;
+        d_in = d_out = nullptr;
+    }
+};
+
+// Runs jobs (host pointers) on one device.  The batch is cut into sub-batches that alternate
+// between two streams, so the H2D copies of one overlap the kernels and D2H copies of the other.
 int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32_t n, fanlin_plan *plans) {
     DeviceState *dev = ctx->devs[dev_index].get();
     std::lock_guard<std::mutex> lk(dev->mu);
     CUDA_TRY(cudaSetDevice(dev->ordinal));
-    std::vector<fanlin_job> djobs(jobs, jobs + n);
     std::vector<fanlin_plan> pl(n);
-    size_t in_bytes = 0, out_bytes = 0;
-    std::vector<size_t> in_off(n), out_off(n);
     for (uint32_t i = 0; i < n; i++) {
         const int rc = fanlin_plan_job(&jobs[i], &pl[i]);
         if (rc != FANLIN_OK) return rc;
         if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
         if (jobs[i].dst_capacity < pl[i].out_bytes) { set_error("fanlin: dst_capacity smaller than the planned output"); return FANLIN_ECAPACITY; }
-        in_off[i] = in_bytes;
-        in_bytes += align_up(size_t(jobs[i].src_w) * jobs[i].src_channels * jobs[i].src_h, 256);
-        out_off[i] = out_bytes;
-        out_bytes += align_up(pl[i].out_bytes, 256);
     }
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_in), in_bytes + 256, dev->stream));
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_out), out_bytes + 256, dev->stream));
+    const uint32_t per = std::max<uint32_t>(64, (n + 15) / 16);  // <= 16 sub-batches, each at least 64 jobs
+    const size_t max_bytes = size_t(2) << 30;
+    Flight fl[2];
+    fl[0].st = dev->copy_in;
+    fl[1].st = dev->copy_out;
     int rc = FANLIN_OK;
-    fanlin_batch *batch = nullptr;
-    do {
-        for (uint32_t i = 0; i < n && rc == FANLIN_OK; i++) {
-            const size_t row = size_t(jobs[i].src_w) * jobs[i].src_channels;
-            const size_t pitch = jobs[i].src_pitch ? jobs[i].src_pitch : row;
-            cudaError_t e = cudaMemcpy2DAsync(d_in + in_off[i], row, jobs[i].src, pitch, row, jobs[i].src_h,
-                                              cudaMemcpyHostToDevice, dev->stream);
+    uint32_t begin = 0, k = 0;
+    std::vector<fanlin_job> djobs;
+    std::vector<size_t> in_off, out_off;
+    while (begin < n && rc == FANLIN_OK) {
+        Flight &f = fl[k & 1];
+        if (f.batch || f.d_in) {  // the sub-batch that used this slot two rounds ago must have drained
+            if (cudaStreamSynchronize(f.st) != cudaSuccess) { set_error("fanlin: CUDA error in a sub-batch"); rc = FANLIN_ECUDA; break; }
+            f.release();
+        }
+        uint32_t end = begin;
+        size_t in_bytes = 0, out_bytes = 0;
+        in_off.clear();
+        out_off.clear();
+        while (end < n && end - begin < per) {
+            const size_t ib = align_up(size_t(jobs[end].src_w) * jobs[end].src_channels * jobs[end].src_h, 256);
+            if (end > begin && in_bytes + ib > max_bytes) break;
+            in_off.push_back(in_bytes);
+            out_off.push_back(out_bytes);
+            in_bytes += ib;
+            out_bytes += align_up(pl[end].out_bytes, 256);
+            end++;
+        }
+        const uint32_t m = end - begin;
+        if (cudaMallocAsync(reinterpret_cast<void **>(&f.d_in), in_bytes + 256, f.st) != cudaSuccess ||
+            cudaMallocAsync(reinterpret_cast<void **>(&f.d_out), out_bytes + 256, f.st) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("fanlin: device allocation failed");
+            rc = FANLIN_ENOMEM;
+            break;
+        }
+        djobs.assign(jobs + begin, jobs + end);
+        for (uint32_t i = 0; i < m && rc == FANLIN_OK; i++) {
+            const fanlin_job &j = jobs[begin + i];
+            const size_t row = size_t(j.src_w) * j.src_channels;
+            const size_t pitch = j.src_pitch ? j.src_pitch : row;
+            const cudaError_t e = pitch == row
+                                      ? cudaMemcpyAsync(f.d_in + in_off[i], j.src, row * j.src_h, cudaMemcpyHostToDevice, f.st)
+                                      : cudaMemcpy2DAsync(f.d_in + in_off[i], row, j.src, pitch, row, j.src_h, cudaMemcpyHostToDevice, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; }
-            djobs[i].src = d_in + in_off[i];
+            djobs[i].src = f.d_in + in_off[i];
             djobs[i].src_pitch = 0;
-            djobs[i].dst = d_out + out_off[i];
-            djobs[i].dst_capacity = pl[i].out_bytes;
-            ctx->h2d_bytes += row * jobs[i].src_h;
+            djobs[i].dst = f.d_out + out_off[i];
+            djobs[i].dst_capacity = pl[begin + i].out_bytes;
+            ctx->h2d_bytes += row * j.src_h;
         }
         if (rc != FANLIN_OK) break;
-        rc = fanlin_batch_prepare(ctx, dev_index, djobs.data(), n, nullptr, &batch);
+        rc = prepare_on_stream(ctx, dev_index, djobs.data(), m, nullptr, &f.batch, f.st);
         if (rc != FANLIN_OK) break;
-        rc = fanlin_batch_launch(batch, dev->stream);
+        rc = fanlin_batch_launch(f.batch, f.st);
         if (rc != FANLIN_OK) break;
-        for (uint32_t i = 0; i < n; i++) {
-            cudaError_t e = cudaMemcpyAsync(jobs[i].dst, d_out + out_off[i], pl[i].out_bytes, cudaMemcpyDeviceToHost, dev->stream);
+        for (uint32_t i = 0; i < m; i++) {
+            const cudaError_t e = cudaMemcpyAsync(jobs[begin + i].dst, f.d_out + out_off[i], pl[begin + i].out_bytes, cudaMemcpyDeviceToHost, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: D2H failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; break; }
-            ctx->d2h_bytes += pl[i].out_bytes;
+            ctx->d2h_bytes += pl[begin + i].out_bytes;
         }
-    } while (false);
-    cudaError_t se = cudaStreamSynchronize(dev->stream);
-    if (rc == FANLIN_OK && se != cudaSuccess) {
-        set_error(std::string("fanlin: CUDA error: ") + cudaGetErrorString(se));
-        rc = FANLIN_ECUDA;
+        begin = end;
+        k++;
     }
-    if (batch) fanlin_batch_free(batch);
-    cudaFreeAsync(d_in, dev->stream);
-    cudaFreeAsync(d_out, dev->stream);
+    for (Flight &f : fl) {
+        const cudaError_t se = cudaStreamSynchronize(f.st);
+        if (rc == FANLIN_OK && se != cudaSuccess) {
+            set_error(std::string("fanlin: CUDA error: ") + cudaGetErrorString(se));
+            rc = FANLIN_ECUDA;
+        }
+        f.release();
+    }
     if (rc == FANLIN_OK && plans) std::copy(pl.begin(), pl.end(), plans);
     return rc;
 }

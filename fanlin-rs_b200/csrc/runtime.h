@@ -77,6 +77,8 @@ struct fanlin_batch {
     };
     std::vector<Step> steps;
     void *d_meta = nullptr;     // descriptors + tables
+    cudaStream_t alloc_stream = nullptr;  // stream the device blocks were allocated on (stream-ordered pool)
+    void *h_meta = nullptr;     // their pinned host copy (the upload is asynchronous)
     void *d_scratch = nullptr;  // intermediates (reused across chunks)
     const fanlin::TapEntry *d_tab = nullptr;
     const float *d_w = nullptr;

@@ -129,6 +129,7 @@ FANLIN_API int fanlin_batch_prepare(fanlin_ctx *ctx, int device_index, const fan
 FANLIN_API int fanlin_batch_launch(fanlin_batch *batch, void *cuda_stream);
 /* Kernels one launch enqueues, and the name-independent index of the dominant one. */
 FANLIN_API int fanlin_batch_launch_count(const fanlin_batch *batch);
+/* The caller must have synchronised every stream it launched the batch on. */
 FANLIN_API void fanlin_batch_free(fanlin_batch *batch);
 /* Per-kernel device times of a batch (benchmarks): when enabled, fanlin_batch_launch
  * brackets every kernel with CUDA events on the launching stream;
