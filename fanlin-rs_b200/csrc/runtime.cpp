@@ -8,6 +8,7 @@
 #include "fused_tc.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <string>
 
@@ -106,6 +107,8 @@ extern "C" int fanlin_plan_job(const fanlin_job *job, fanlin_plan *plan) {
     return rc;
 }
 
+static void batcher_main(fanlin_ctx *ctx, int dev_index);
+
 extern "C" int fanlin_init(const int *device_ids, int n_devices, const fanlin_config *cfg, fanlin_ctx **out) {
     if (!out) { set_error("fanlin: null out pointer"); return FANLIN_EINVAL; }
     *out = nullptr;
@@ -145,7 +148,9 @@ extern "C" int fanlin_init(const int *device_ids, int n_devices, const fanlin_co
         }
         ctx->devs.push_back(std::move(d));
     }
-    *out = ctx.release();
+    fanlin_ctx *raw = ctx.release();
+    for (size_t i = 0; i < raw->devs.size(); i++) raw->devs[i]->worker = std::thread(batcher_main, raw, int(i));
+    *out = raw;
     return FANLIN_OK;
 }
 
@@ -700,15 +705,83 @@ extern "C" void fanlin_shard_range(uint32_t n_jobs, uint32_t n_shards, uint32_t 
     if (hi) *hi = b;
 }
 
+// Request batcher: one collector thread per device.  Small fanlin_run calls (a request = one
+// image, src/main.rs:179 calls process_image from up to max_clients tokio workers at once) queue
+// here; the collector waits batch_window_us after the first arrival, merges what came in into one
+// ragged batch, runs it, and wakes the callers.  A failing merged batch is re-run request by
+// request so that one bad image fails alone.
+constexpr uint32_t BATCHER_DIRECT_JOBS = 32;  // calls this large are batches already
+
+static void batcher_main(fanlin_ctx *ctx, int dev_index) {
+    DeviceState *dev = ctx->devs[dev_index].get();
+    for (;;) {
+        std::vector<Request *> take;
+        {
+            std::unique_lock<std::mutex> lk(dev->qmu);
+            dev->qcv.wait(lk, [&] { return dev->stop || !dev->queue.empty(); });
+            if (dev->stop && dev->queue.empty()) return;
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(ctx->cfg.batch_window_us);
+            uint32_t jobs = 0;
+            for (;;) {
+                while (!dev->queue.empty() && jobs < ctx->cfg.max_batch_jobs) {
+                    jobs += dev->queue.front()->n;
+                    take.push_back(dev->queue.front());
+                    dev->queue.pop_front();
+                }
+                if (jobs >= ctx->cfg.max_batch_jobs || dev->stop) break;
+                if (dev->qcv.wait_until(lk, deadline) == std::cv_status::timeout && dev->queue.empty()) break;
+            }
+        }
+        std::vector<fanlin_job> merged;
+        std::vector<fanlin_plan> plans;
+        for (Request *r : take) merged.insert(merged.end(), r->jobs, r->jobs + r->n);
+        plans.resize(merged.size());
+        int rc = run_on_device(ctx, dev_index, merged.data(), uint32_t(merged.size()), plans.data());
+        size_t off = 0;
+        for (Request *r : take) {
+            int rrc = rc;
+            std::string err;
+            if (rc != FANLIN_OK && take.size() > 1) {  // isolate the failure
+                rrc = run_on_device(ctx, dev_index, r->jobs, r->n, r->plans);
+                if (rrc != FANLIN_OK) err = get_error();
+            } else if (rc != FANLIN_OK) {
+                err = get_error();
+            } else if (r->plans) {
+                std::copy(plans.begin() + off, plans.begin() + off + r->n, r->plans);
+            }
+            off += r->n;
+            std::lock_guard<std::mutex> lk(r->m);
+            r->rc = rrc;
+            r->err = err;
+            r->done = true;
+            r->cv.notify_one();
+        }
+    }
+}
+
 extern "C" int fanlin_run(fanlin_ctx *ctx, const fanlin_job *jobs, uint32_t n_jobs, fanlin_plan *plans) {
     if (!ctx || (!jobs && n_jobs)) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
     if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
     if (n_jobs == 0) return FANLIN_OK;
     const int nd = int(ctx->devs.size());
-    if (nd == 1 || n_jobs == 1) {
-        const int dev = nd == 1 ? 0 : int(ctx->rr++ % uint32_t(nd));
-        return run_on_device(ctx, dev, jobs, n_jobs, plans);
+    if (n_jobs < BATCHER_DIRECT_JOBS) {  // a request or a short GIF: through the batcher of one device
+        DeviceState *dev = ctx->devs[ctx->rr++ % uint32_t(nd)].get();
+        Request r;
+        r.jobs = jobs;
+        r.n = n_jobs;
+        r.plans = plans;
+        {
+            std::lock_guard<std::mutex> lk(dev->qmu);
+            if (dev->stop) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
+            dev->queue.push_back(&r);
+        }
+        dev->qcv.notify_all();
+        std::unique_lock<std::mutex> lk(r.m);
+        r.cv.wait(lk, [&] { return r.done; });
+        if (r.rc != FANLIN_OK) set_error(r.err);
+        return r.rc;
     }
+    if (nd == 1) return run_on_device(ctx, 0, jobs, n_jobs, plans);
     // shard by image index: contiguous blocks, one host thread per device, no collective
     std::vector<std::thread> th;
     std::vector<int> rcs(nd, FANLIN_OK);

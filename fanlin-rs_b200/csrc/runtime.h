@@ -8,6 +8,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -32,7 +33,17 @@ class PinnedPool {
     size_t cached_ = 0, limit_ = size_t(2) << 30;
 };
 
-struct Request;
+// One blocked fanlin_run call waiting in a device's batcher queue.
+struct Request {
+    const fanlin_job *jobs = nullptr;
+    uint32_t n = 0;
+    fanlin_plan *plans = nullptr;
+    int rc = 0;
+    std::string err;
+    bool done = false;
+    std::mutex m;
+    std::condition_variable cv;
+};
 
 struct DeviceState {
     int ordinal = 0;

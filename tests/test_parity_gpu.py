@@ -202,3 +202,57 @@ def test_resample_paths_agree(fanlin, dev, dev_cuda_cores, dev_exact, seed, h, w
         print(name, qs, "mismatch histogram", hh)
         assert hh[">=2"] == 0, (name, hh)
         assert hh[1] <= 0.002 * want.size, (name, hh)  # off-by-one only where the f32 sum sits on a rounding boundary
+
+
+# ---- request batcher ------------------------------------------------------------------------
+
+def test_concurrent_requests_are_merged_and_isolated(fanlin):
+    """Many threads call fanlin_run with one image each (what the tokio workers do at
+    src/main.rs:179): the batcher merges them into ragged batches; a bad request fails alone."""
+    import threading
+
+    d = fanlin.Device([0], batch_window_us=20000)
+    try:
+        imgs = [synth_image(300 + i, 90 + 3 * i, 120 + 5 * i, 3) for i in range(24)]
+        q = fanlin.Query("w=64&h=48&rgb=5,6,7")
+        outs, errs = [None] * 25, [None] * 25
+
+        def work(i):
+            try:
+                if i == 24:  # destination too small -> FANLIN_ECAPACITY for this caller only
+                    j = fanlin.make_job(imgs[0], q)
+                    o = np.zeros(16, np.uint8)
+                    j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
+                    d.run([j])
+                else:
+                    outs[i] = fanlin.process_image(d, imgs[i], q)
+            except fanlin.FanlinError as e:
+                errs[i] = e
+
+        def run_threads(ids):
+            th = [threading.Thread(target=work, args=(i,)) for i in ids]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+
+        # phase 1: 24 good one-image calls -> a handful of merged batches
+        before = d.stats()
+        run_threads(range(24))
+        after = d.stats()
+        for i in range(24):
+            assert errs[i] is None, errs[i]
+            want = O.process(imgs[i], w=64, h=48, rgb=(5, 6, 7))
+            assert outs[i].shape == want.shape and hist(outs[i], want)[">=2"] == 0
+        assert after["jobs"] - before["jobs"] == 24
+        print("batches for 24 concurrent requests:", after["batches"] - before["batches"])
+        assert after["batches"] - before["batches"] <= 6
+        # phase 2: a bad request among good ones fails alone (the merged batch is re-run per request)
+        outs[:] = [None] * 25
+        run_threads(range(20, 25))
+        assert errs[24] is not None and errs[24].status == 3
+        for i in range(20, 24):
+            assert errs[i] is None and outs[i] is not None
+            assert hist(outs[i], O.process(imgs[i], w=64, h=48, rgb=(5, 6, 7)))[">=2"] == 0
+    finally:
+        d.close()
