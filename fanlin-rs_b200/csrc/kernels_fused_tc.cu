@@ -126,18 +126,16 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const float scale = it.scale, scale_hi = it.scale * 16384.0f;
 
     // ---- horizontal-stage role of this thread: one output row of the band
-    const bool h_active = tid < it.band_rows;
-    // accumulators of the <= 8 live output pixels: channel pairs as f32x2 (one FFMA2 issue slot
-    // per pair; the stage is issue-bound, not FMA-pipe-bound), the odd channel as a scalar
-    constexpr int CP = C / 2, CO = C & 1;
-    float2 hacc2[S][CP > 0 ? CP : 1];
-    float hacc1[S];
+    // Each horizontal thread owns TWO output rows (r and r + h_half): the pair shares the table
+    // loads, and every channel value of the two rows goes through one f32x2 FMA.
+    const uint32_t h_half = (it.band_rows + 1) / 2;
+    const bool h_active = tid < h_half;
+    const bool h_second = tid + h_half < it.band_rows;
+    float2 hacc[S][C];  // .x = row tid, .y = row tid + h_half
 #pragma unroll
-    for (int j = 0; j < S; j++) {
+    for (int j = 0; j < S; j++)
 #pragma unroll
-        for (int k = 0; k < (CP > 0 ? CP : 1); k++) hacc2[j][k] = make_float2(0.f, 0.f);
-        hacc1[j] = 0.f;
-    }
+        for (int k = 0; k < C; k++) hacc[j][k] = make_float2(0.f, 0.f);
     uint32_t h_next = 0;
     const float *hw = tw + it.hw_off;
     const uint32_t *hinfo = tinfo + it.hinfo_off;
@@ -260,30 +258,28 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             const float *tcol = tmp + tid + size_t(sh) * r_pad;
             const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
             const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
-            // one pixel: scatter its C values into the live slots, then flush completed outputs
-            auto step = [&](const float (&v)[C], const float4 &w0, const float4 &w1, uint32_t info) {
+            // one pixel: scatter its C values (of both rows) into the live slots, then flush completed outputs
+            auto step = [&](const float2 (&v)[C], const float4 &w0, const float4 &w1, uint32_t info) {
                 const float w[S] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int j = 0; j < S; j++) {
+                for (int j = 0; j < S; j++)
 #pragma unroll
-                    for (int k = 0; k < CP; k++) ffma2(hacc2[j][k], make_float2(v[2 * k], v[2 * k + 1]), w[j]);
-                    if (CO) hacc1[j] = fmaf(v[C - 1], w[j], hacc1[j]);
-                }
+                    for (int k = 0; k < C; k++) ffma2(hacc[j][k], v[k], w[j]);
                 const uint32_t fl = (info >> 8) & 0xffu;
                 if (fl) {
 #pragma unroll
                     for (int j = 0; j < S; j++) {
                         if (fl & (1u << j)) {
                             const uint32_t o = h_next + ((uint32_t(j) - h_next) & (S - 1));
-                            uint32_t u[4] = {0, 0, 0, 0};
+                            uint32_t ua[4] = {0, 0, 0, 0}, ub[4] = {0, 0, 0, 0};
 #pragma unroll
-                            for (int k = 0; k < CP; k++) {
-                                u[2 * k] = round_u8(hacc2[j][k].x);
-                                u[2 * k + 1] = round_u8(hacc2[j][k].y);
-                                hacc2[j][k] = make_float2(0.f, 0.f);
+                            for (int k = 0; k < C; k++) {
+                                ua[k] = round_u8(hacc[j][k].x);
+                                ub[k] = round_u8(hacc[j][k].y);
+                                hacc[j][k] = make_float2(0.f, 0.f);
                             }
-                            if (CO) { u[C - 1] = round_u8(hacc1[j]); hacc1[j] = 0.f; }
-                            emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy, u);
+                            emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy, ua);
+                            if (h_second) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy + h_half, ub);
                         }
                     }
                     h_next += __popc(fl);
@@ -292,11 +288,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             // two pixels per iteration: all shared-memory reads of both are issued before the FMAs
             for (uint32_t xl = 0; xl < npx; xl += 2) {
                 const bool two = xl + 1 < npx;
-                float va[C], vb[C];
+                float2 va[C], vb[C];
 #pragma unroll
-                for (int k = 0; k < C; k++) va[k] = tcol[size_t(xl * C + k) * r_pad];
+                for (int k = 0; k < C; k++) va[k] = make_float2(tcol[size_t(xl * C + k) * r_pad], tcol[size_t(xl * C + k) * r_pad + h_half]);
 #pragma unroll
-                for (int k = 0; k < C; k++) vb[k] = tcol[size_t((xl + 1) * C + k) * r_pad];  // within the tile even past npx
+                for (int k = 0; k < C; k++)  // within shared memory even past npx
+                    vb[k] = make_float2(tcol[size_t((xl + 1) * C + k) * r_pad], tcol[size_t((xl + 1) * C + k) * r_pad + h_half]);
                 const uint32_t ia = hinfo_s[xl], ib = hinfo_s[xl + 1];
                 const float4 wa0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
                 const float4 wa1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
