@@ -12,7 +12,7 @@ namespace fanlin {
 namespace {
 
 struct TcBand {
-    uint32_t r0, rows, grp_off, n_groups, kg_max;
+    uint32_t r0, rows, grp_off, n_groups, kg_max, grp_rows;
 };
 struct TcGeom {
     bool ok = false;
@@ -22,10 +22,13 @@ struct TcGeom {
 };
 using TcKey = std::tuple<const AxisTable *, const AxisTable *, uint32_t, uint32_t, uint32_t>;
 
-uint32_t r_pad_for(uint32_t rows) {
-    uint32_t r = (rows + 3) & ~3u;
-    while (r % 8 != 4) r += 4;
-    return r;
+// Floats per tile column.  Odd, so the drain's lanes (= consecutive tile columns) hit distinct
+// banks; and congruent to ~32/c (mod 32), so the horizontal stage's lanes (= (row, channel)
+// pairs, channel fastest) do too: bank = channel * r_pad + row.
+uint32_t r_pad_for(uint32_t rows, uint32_t c) {
+    const uint32_t want = c == 1 ? 1u : c == 2 ? 17u : c == 3 ? 11u : 9u;
+    if (c == 1) return rows | 1u;
+    return rows + ((want + 32u - (rows & 31u)) & 31u);
 }
 
 }  // namespace
@@ -34,7 +37,7 @@ uint32_t r_pad_for(uint32_t rows) {
 uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 112u : c == 2 ? 60u : c == 3 ? 38u : 32u; }
 
 size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
-    const size_t tmp = size_t(TC_M) * r_pad_for(band_rows) * 4;
+    const size_t tmp = size_t(TC_M) * r_pad_for(band_rows, c) * 4;
     const size_t a = 2 * size_t(kg_max) * TC_M, b = 2 * size_t(TC_N) * kg_max;
     const size_t ht = 2 * ((size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15));  // two copies of the chunk's horizontal table slice
     return tmp + a + b + ht + 1024 + 128;  // + slack to align the tile buffers to 1024 bytes
@@ -43,8 +46,10 @@ size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
 uint32_t fused_tc_max_band(uint32_t c) {
     const size_t limit = 232448 - 1024;
     const size_t fixed = fused_tc_smem_bytes(c, 0, TC_KG_MAX);
-    const uint32_t rows = uint32_t((limit - fixed) / (TC_M * 4));
-    return std::min(192u, rows / TC_GROUP_ROWS * TC_GROUP_ROWS);
+    const uint32_t rows = uint32_t((limit - fixed) / (TC_M * 4));  // fixed already holds r_pad_for(0) <= 17 columns
+    // the horizontal stage maps (row pair, channel) to the lanes of TC_H_WARPS warps
+    const uint32_t lanes_cap = 2 * TC_H_WARPS * (32 / c);
+    return std::min(std::min(192u, lanes_cap), rows - 32);
 }
 
 struct FusedTcCache {
@@ -63,7 +68,7 @@ bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
     if (s.src_is_input && (reinterpret_cast<uintptr_t>(job.src) & 15)) return false;
     // a 32-row output group must fit 256 source rows, and the horizontal pass 8 live outputs
     const double ratio = double(s.in_h) / double(std::max(1u, s.v_out));
-    if ((TC_GROUP_ROWS - 1) * ratio + s.vtab->max_taps > TC_KG_MAX) return false;
+    if (7 * ratio + s.vtab->max_taps > TC_KG_MAX) return false;
     if (s.htab->max_taps > 8 * std::max(1u, s.in_w / std::max(1u, s.h_out)) + 8) return false;
     return true;
 }
@@ -89,26 +94,44 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
     g.scale = std::ldexp(1.0f, -sh);
     const uint32_t max_band = fused_tc_max_band(s.c);
     const uint32_t n_bands = (s.n_rows + max_band - 1) / max_band;
-    uint32_t band_rows = (s.n_rows + n_bands - 1) / n_bands;
-    band_rows = std::min(max_band, (band_rows + TC_GROUP_ROWS - 1) / TC_GROUP_ROWS * TC_GROUP_ROWS);
+    const uint32_t band_rows = (s.n_rows + n_bands - 1) / n_bands;
+    // source rows spanned by output rows [ra, rb) of the band starting at b0
+    auto span = [&](uint32_t b0, uint32_t ra, uint32_t rb, uint32_t *k0) {
+        *k0 = s.vtab->entries[s.oy0 + b0 + ra].left;
+        uint32_t k1 = 0;
+        for (uint32_t r = ra; r < rb; r++) {
+            const TapEntry &e = s.vtab->entries[s.oy0 + b0 + r];
+            k1 = std::max(k1, e.left + e.count);
+        }
+        return k1 - *k0;
+    };
     for (uint32_t b0 = 0; b0 < s.n_rows && ok; b0 += band_rows) {
         TcBand bt{};
         bt.r0 = b0;
         bt.rows = std::min(band_rows, s.n_rows - b0);
-        bt.n_groups = (bt.rows + TC_GROUP_ROWS - 1) / TC_GROUP_ROWS;
+        // rows per group: every MMA costs the same ~112 clk floor whatever N is, so minimise the
+        // number of 32-row K steps over the band (C2: 29 rows -> 6 x 7 instead of 6 x 8 at 32)
+        uint32_t best_r = 0, best_cost = ~0u;
+        for (uint32_t gr = TC_GROUP_ROWS; gr >= 8; gr--) {
+            uint32_t cost = 0;
+            bool fits = true;
+            for (uint32_t ra = 0; ra < bt.rows && fits; ra += gr) {
+                uint32_t k0;
+                const uint32_t kspan = span(b0, ra, std::min(bt.rows, ra + gr), &k0);
+                fits = kspan <= TC_KG_MAX;
+                cost += (kspan + 31) / 32;
+            }
+            if (fits && cost < best_cost) { best_cost = cost; best_r = gr; }
+        }
+        if (!best_r || (bt.rows + best_r - 1) / best_r > 24) { ok = false; break; }  // the kernel keeps <= 24 group records in shared memory
+        bt.grp_rows = best_r;
+        bt.n_groups = (bt.rows + best_r - 1) / best_r;
         bt.grp_off = uint32_t(tabs->info.size());
         tabs->info.resize(tabs->info.size() + size_t(bt.n_groups) * 4, 0u);
         for (uint32_t gi = 0; gi < bt.n_groups && ok; gi++) {
-            const uint32_t ra = gi * TC_GROUP_ROWS, rb = std::min(bt.rows, ra + TC_GROUP_ROWS);
-            const uint32_t o0 = s.oy0 + bt.r0 + ra;
-            const uint32_t k0 = s.vtab->entries[o0].left;
-            uint32_t k1 = 0;
-            for (uint32_t r = ra; r < rb; r++) {
-                const TapEntry &e = s.vtab->entries[s.oy0 + bt.r0 + r];
-                k1 = std::max(k1, e.left + e.count);
-            }
-            const uint32_t kg = (k1 - k0 + 31) / 32 * 32;
-            if (kg > TC_KG_MAX) { ok = false; break; }
+            const uint32_t ra = gi * best_r, rb = std::min(bt.rows, ra + best_r);
+            uint32_t k0;
+            const uint32_t kg = (span(b0, ra, rb, &k0) + 31) / 32 * 32;
             bt.kg_max = std::max(bt.kg_max, kg);
             const size_t b_off = (tct->b.size() + 127) & ~size_t(127);
             tct->b.resize(b_off + size_t(TC_N) * kg, 0);
@@ -155,8 +178,8 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         f.src = src; f.dst = dst; f.src_pitch = src_pitch; f.src_h = s.in_h;
         f.c = s.c;
         f.px0 = g.px0; f.n_px = g.n_px; f.chunk_px = chunk_px; f.n_chunks = (g.n_px + chunk_px - 1) / chunk_px;
-        f.band_r0 = bt.r0; f.band_rows = bt.rows; f.r_pad = r_pad_for(bt.rows);
-        f.grp_off = bt.grp_off; f.n_groups = bt.n_groups; f.kg_max = bt.kg_max;
+        f.band_r0 = bt.r0; f.band_rows = bt.rows; f.r_pad = r_pad_for(bt.rows, s.c);
+        f.grp_off = bt.grp_off; f.n_groups = bt.n_groups; f.kg_max = bt.kg_max; f.grp_rows = bt.grp_rows;
         f.scale = g.scale;
         f.hw_off = g.hw_off; f.hinfo_off = g.hinfo_off;
         f.n_cols = s.n_cols;

@@ -23,9 +23,10 @@
 namespace fanlin {
 
 constexpr uint32_t TC_M = 128;          // source bytes (elements) per chunk row = UMMA M
-constexpr uint32_t TC_GROUP_ROWS = 32;  // output rows per MMA group (N = 3 * 32)
+constexpr uint32_t TC_GROUP_ROWS = 32;  // most output rows per MMA group (N = 3 * 32); a band may use fewer (grp_rows)
 constexpr uint32_t TC_N = 3 * TC_GROUP_ROWS;
 constexpr uint32_t TC_KG_MAX = 256;     // source rows per group, multiple of 32
+constexpr uint32_t TC_H_WARPS = 10;     // consumer warps; the horizontal stage gives each (row pair, channel) a lane
 
 struct FusedTcItem {
     const uint8_t *src;
@@ -33,7 +34,8 @@ struct FusedTcItem {
     uint32_t src_pitch, src_h;
     uint32_t c;
     uint32_t px0, n_px, chunk_px, n_chunks;
-    uint32_t band_r0, band_rows, r_pad;   // r_pad: floats per tile column, == 4 (mod 8)
+    uint32_t band_r0, band_rows, r_pad;   // r_pad: floats per tile column (see r_pad_for)
+    uint32_t grp_rows;                    // output rows per group (<= 32), chosen to minimise MMAs per row
     uint32_t grp_off, n_groups, kg_max;   // grp_off: u32 offset of {k0, kg, b_off, rows} x n_groups
     float scale;                          // 2^-s
     uint32_t hw_off, hinfo_off;           // horizontal scatter table (unscaled weights)

@@ -1,16 +1,16 @@
 // Fused separable Lanczos3 resample with the vertical pass on the sm_100a tensor
 // cores (tcgen05.mma kind::i8, accumulators in TMEM).  See fused_tc.h.
 //
-// Per CTA (1 CTA / SM): 8 consumer warps + 1 producer warp; one band of <= 192 output rows
+// Per CTA (1 CTA / SM): 10 consumer warps + an MMA-issuing warp + a TMA-issuing warp; one band of <= 192 output rows
 // of one image, swept left to right in chunks of 128 source bytes per row.  Per chunk, per
 // group of 32 output rows:
-//   * the producer thread fetches the group's source rows with a single TMA tensor copy
+//   * the TMA thread fetches the group's source rows with a single TMA tensor copy
 //     (cp.async.bulk.tensor.2d; tensor map {row bytes, rows}, box {128 B, kg rows}, 128-byte
 //     swizzle) -- the box lands as [row][128 B] with the hardware swizzle, which is the
 //     MN-major SWIZZLE_128B operand layout the tensor core reads directly (measured:
 //     profiles/microbench/umma_i8_tma128.cu); rows / columns past the image are zero-filled
 //     -- and the s8 weight-digit tile with one cp.async.bulk (two shared-memory slots);
-//   * the producer thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3
+//   * the MMA thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3
 //     digits x 32 output rows, K = 32 source rows) into one of FIVE accumulator regions of
 //     TMEM and commits to an mbarrier.  It runs ahead of the consumers as far as TMEM
 //     allows: while they execute the horizontal stage of chunk c, the tensor core already
@@ -18,8 +18,10 @@
 //   * the consumers drain a region (tcgen05.ld 32x32b), recombine the three s32 digit sums
 //     into the f32 value of the crate's vertical pass, store it to the tile
 //     tmp[element][row] and hand the region back;
-// then the consumers run the horizontal stage on the CUDA cores as in kernels_fused.cu (one
-// thread per output row, scatter into <= 8 live output pixels, epilogue).
+// then the consumers run the horizontal stage on the CUDA cores: the scatter of
+// kernels_fused.cu (<= 8 live output pixels per row), with one lane per (pair of output rows,
+// channel) so that every consumer warp takes part, f32x2 FMAs over the row pair, and a warp
+// shuffle that gathers a finished pixel's channels for the epilogue.
 #include <cuda.h>
 
 #include "fused_device.cuh"
@@ -30,8 +32,8 @@ namespace fanlin {
 
 namespace {
 
-constexpr int NT = 256;           // consumer threads (8 warps)
-constexpr int NT_ALL = NT + 32;   // + the producer warp
+constexpr int NT = 32 * TC_H_WARPS;  // consumer threads (10 warps: 8 drain TMEM, all run the horizontal stage)
+constexpr int NT_ALL = NT + 64;   // + the MMA-issuing warp and the TMA-issuing warp
 constexpr uint32_t NR = 5;        // TMEM accumulator regions of 96 columns
 constexpr int S = FUSED_SLOTS;
 constexpr uint32_t TMEM_COLS = 512;  // NR regions of 96 columns
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
     __shared__ FusedTcItem it_s;
     __shared__ __align__(8) uint64_t mbar[NR];       // the MMAs into TMEM region r have retired
-    __shared__ __align__(8) uint64_t tmem_free[NR];  // all 8 consumer warps have drained region r
+    __shared__ __align__(8) uint64_t tmem_free[NR];  // the 8 draining warps have emptied region r
     __shared__ __align__(8) uint64_t full[2];  // the copies into shared-memory buffer b have landed
     __shared__ uint32_t tmem_base_s;
     const uint32_t tid = threadIdx.x;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     if (warp < NT / 32) fill_bars(it, warp, lane, NT / 32);
 
     // ---- shared-memory carve-up
-    const uint32_t r_pad = it.r_pad, kg_max = it.kg_max;
+    const uint32_t r_pad = it.r_pad, kg_max = it.kg_max, grp_rows = it.grp_rows;
     float *tmp = reinterpret_cast<float *>(smem);                      // [128][r_pad]
     uint8_t *sA = smem + size_t(TC_M) * r_pad * 4;                     // 2 x [kg_max rows][128 B], 128-byte swizzle (1024-aligned)
     uint8_t *sB = sA + 2 * size_t(kg_max) * TC_M;                      // 2 x [96][kg_max], core-matrix layout
@@ -122,24 +124,32 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const uint32_t htab_words = (chunk_px * (S + 1) + 3) & ~3u;  // each copy stays 16-byte aligned
     const CUtensorMap *tmap = tmaps + blockIdx.x;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    const uint32_t *grp = tinfo + it.grp_off;
+    // group table {k0, kg, b_off, rows} in shared memory: the producer's issue path must not wait on L2
+    __shared__ uint32_t grp[4 * 24];
+    for (uint32_t k = tid; k < 4 * it.n_groups; k += NT_ALL) grp[k] = tinfo[it.grp_off + k];
+    __syncthreads();
     const float scale = it.scale, scale_hi = it.scale * 16384.0f;
 
-    // ---- horizontal-stage role of this thread: one output row of the band
-    // Each horizontal thread owns TWO output rows (r and r + h_half): the pair shares the table
-    // loads, and every channel value of the two rows goes through one f32x2 FMA.
+    // ---- horizontal-stage role of this thread: one channel of TWO output rows (ra and rb = ra +
+    // h_half).  Lanes are (row slot, channel) with the channel fastest, 32 / C slots per warp, so
+    // all consumer warps share the stage; the two rows go through one f32x2 FMA per output slot.
+    constexpr uint32_t RPW = 32 / C;  // row slots per warp (C = 3 leaves lanes 30 and 31 idle)
     const uint32_t h_half = (it.band_rows + 1) / 2;
-    const bool h_active = tid < h_half;
-    const bool h_second = tid + h_half < it.band_rows;
-    float2 hacc[S][C];  // .x = row tid, .y = row tid + h_half
+    const uint32_t h_ch = lane % C, h_slot = warp * RPW + lane / C;
+    const bool h_warp = warp * RPW < h_half;  // warp-uniform: this warp has rows to produce
+    const bool h_lane = lane < RPW * C && h_slot < h_half;
+    const uint32_t h_ra = min(h_slot, h_half - 1), h_rb = min(h_ra + h_half, it.band_rows - 1);  // clamped: idle lanes read valid tile rows
+    // which of the two rows this lane writes out once the channels are gathered: channel 0 -> ra,
+    // channel 1 -> rb (a single-channel lane writes both)
+    const bool h_emit_a = h_lane && h_ch == 0;
+    const bool h_emit_b = h_lane && h_ch == (C > 1 ? 1u : 0u) && h_slot + h_half < it.band_rows;
+    float2 hacc[S];  // .x = row ra, .y = row rb
 #pragma unroll
-    for (int j = 0; j < S; j++)
-#pragma unroll
-        for (int k = 0; k < C; k++) hacc[j][k] = make_float2(0.f, 0.f);
+    for (int j = 0; j < S; j++) hacc[j] = make_float2(0.f, 0.f);
     uint32_t h_next = 0;
     const float *hw = tw + it.hw_off;
     const uint32_t *hinfo = tinfo + it.hinfo_off;
-    const uint32_t h_cx0 = it.dst_x, h_cy = it.dst_y + it.band_r0 + tid;
+    const uint32_t h_cx0 = it.dst_x, h_cy = it.dst_y + it.band_r0 + h_ra;
 
     // Thread 0 only: fetch group g of the chunk whose 16-byte aligned first column is seg0 into
     // shared-memory buffer `buf` (one TMA tensor copy + one bulk copy, completion on full[buf]).
@@ -159,16 +169,19 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     // TMEM buffer buf), committed to mbar[buf].
     auto issue_mma = [&](uint32_t g, uint32_t buf, uint32_t region) {
         const uint32_t kg = grp[4 * g + 1];
-        const uint32_t a0 = sA_u + buf * kg_max * TC_M, b0 = sB_u + buf * TC_N * kg_max;
+        // descriptors advance by a constant per K step: 32 rows x 128 B of A, 2 core matrices of B
+        uint64_t da = umma_desc(sA_u + buf * kg_max * TC_M, 16, 1024, 2);  // SBO = 8-row atom stride
+        uint64_t db = umma_desc(sB_u + buf * TC_N * kg_max, 128, (kg / 16) * 128);
         const uint32_t d_tmem = tmem_base + region * TC_N;
-        for (uint32_t ks = 0; ks < kg / 32; ks++) {
-            const uint64_t da = umma_desc(a0 + ks * 32 * 128, 16, 1024, 2);  // K step: 32 rows x 128 B; SBO = 8-row atom stride
-            const uint64_t db = umma_desc(b0 + ks * 2 * 128, 128, (kg / 16) * 128);
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da), "l"(db), "r"(UMMA_IDESC),
-                "r"(uint32_t(ks > 0))
-                : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "l"(da), "l"(db), "r"(UMMA_IDESC)
+                     : "memory");
+        for (uint32_t ks = 1; ks < kg / 32; ks++) {
+            da += (32 * 128) >> 4;
+            db += (2 * 128) >> 4;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                         "l"(da), "l"(db), "r"(UMMA_IDESC)
+                         : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[region])) : "memory");
     };
@@ -178,25 +191,25 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     // gg & 1, TMEM region gg % NR.
     const uint32_t total = n_chunks * n_groups;
 
-    if (warp == NT / 32) {
-        // ================= producer warp: TMA loads + MMA issue (one thread) =================
+    if (warp == NT / 32 + 1) {
+        // ================= TMA warp: one thread keeps the two shared-memory slots filled =================
         if (lane == 0) {
             uint32_t ld_chunk = 0, ld_g = 0;
-            for (uint32_t gg = 0; gg <= total; gg++) {
-                if (gg < total) {
-                    if (gg >= 2) {  // slot gg & 1 was read by the MMAs of group gg - 2
-                        mbar_wait(smem_u32(&mbar[(gg - 2) % NR]), ((gg - 2) / NR) & 1);
-                    }
-                    issue_load(ld_g, gg & 1, chunk_seg0(ld_chunk));
-                    if (++ld_g == n_groups) { ld_g = 0; ld_chunk++; }
-                }
-                if (gg >= 1) {  // MMAs of group gg - 1 (its loads were issued one iteration ago)
-                    const uint32_t pg = gg - 1, region = pg % NR, use = pg / NR;
-                    mbar_wait(smem_u32(&full[pg & 1]), (pg >> 1) & 1);
-                    if (use > 0) mbar_wait(smem_u32(&tmem_free[region]), (use - 1) & 1);  // consumers drained its previous contents
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue_mma(pg % n_groups, pg & 1, region);
-                }
+            for (uint32_t gg = 0; gg < total; gg++) {
+                if (gg >= 2) mbar_wait(smem_u32(&mbar[(gg - 2) % NR]), ((gg - 2) / NR) & 1);  // slot gg & 1 was read by the MMAs of group gg - 2
+                issue_load(ld_g, gg & 1, chunk_seg0(ld_chunk));
+                if (++ld_g == n_groups) { ld_g = 0; ld_chunk++; }
+            }
+        }
+    } else if (warp == NT / 32) {
+        // ================= MMA warp: one thread issues every tcgen05.mma =================
+        if (lane == 0) {
+            for (uint32_t pg = 0; pg < total; pg++) {
+                const uint32_t region = pg % NR, use = pg / NR;
+                mbar_wait(smem_u32(&full[pg & 1]), (pg >> 1) & 1);                       // operands have landed
+                if (use > 0) mbar_wait(smem_u32(&tmem_free[region]), (use - 1) & 1);    // consumers drained the region's previous contents
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_mma(pg % n_groups, pg & 1, region);
             }
         }
     } else {
@@ -220,11 +233,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         // ================= vertical stage: drain the tensor-core results =================
         for (uint32_t g = 0; g < n_groups; g++, gg++) {
             const uint32_t region = gg % NR;
-            mbar_wait(smem_u32(&mbar[region]), (gg / NR) & 1);  // the MMAs of group gg have retired
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // TMEM -> f32 tile.  Warp w reads lanes [32 (w & 3), +32) (= tile columns m) and the
-            // half (w >> 2) of the group's 32 output rows.
-            {
+            // TMEM -> f32 tile.  Warp w < 8 reads lanes [32 (w & 3), +32) (= tile columns m) and the
+            // half (w >> 2) of the group's 32 output rows; warps 8 and 9 only join the horizontal stage.
+            if (warp < 8) {
+                mbar_wait(smem_u32(&mbar[region]), (gg / NR) & 1);  // the MMAs of group gg have retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane;
                 const uint32_t taddr = tmem_base + region * TC_N + (((warp & 3) * 32u) << 16) + half * 16;
                 uint32_t hi[16], mid[16], lo[16];
@@ -234,18 +247,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[region])) : "memory");
-                const uint32_t r0 = g * TC_GROUP_ROWS + half * 16;
-                float *t = tmp + size_t(m) * r_pad + r0;
+                const uint32_t jn = grp[4 * g + 3];  // output rows in this group
+                float *t = tmp + size_t(m) * r_pad + g * grp_rows;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    float v[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const int j = 4 * q + e;
-                        const int ml = int(mid[j]) * 128 + int(lo[j]);
-                        v[e] = fmaf(float(int(hi[j])), scale_hi, float(ml) * scale);
-                    }
-                    if (r0 + 4 * q < r_pad) *reinterpret_cast<float4 *>(t + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
+                for (int e = 0; e < 16; e++) {
+                    const uint32_t j = half * 16 + e;
+                    const int ml = int(mid[e]) * 128 + int(lo[e]);
+                    const float v = fmaf(float(int(hi[e])), scale_hi, float(ml) * scale);
+                    if (j < jn) t[j] = v;  // lanes = consecutive columns, r_pad odd: conflict-free
                 }
             }
         }
@@ -254,32 +263,35 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         cp_async_wait<1>();  // this chunk's table slice (committed one chunk ago) has landed
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // consumers only: the tile is complete
         // ================= horizontal stage: CUDA cores =================
-        if (h_active) {
-            const float *tcol = tmp + tid + size_t(sh) * r_pad;
+        if (h_warp) {
+            const float *tcol = tmp + size_t(sh + h_ch) * r_pad;
             const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
             const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
-            // one pixel: scatter its C values (of both rows) into the live slots, then flush completed outputs
-            auto step = [&](const float2 (&v)[C], const float4 &w0, const float4 &w1, uint32_t info) {
+            // one pixel: scatter this lane's channel value (of both rows) into the live slots, then flush completed outputs
+            auto step = [&](const float2 v, const float4 &w0, const float4 &w1, uint32_t info) {
                 const float w[S] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int j = 0; j < S; j++)
-#pragma unroll
-                    for (int k = 0; k < C; k++) ffma2(hacc[j][k], v[k], w[j]);
+                for (int j = 0; j < S; j++) ffma2(hacc[j], v, w[j]);
                 const uint32_t fl = (info >> 8) & 0xffu;
-                if (fl) {
+                if (fl) {  // uniform over the CTA
 #pragma unroll
                     for (int j = 0; j < S; j++) {
                         if (fl & (1u << j)) {
                             const uint32_t o = h_next + ((uint32_t(j) - h_next) & (S - 1));
-                            uint32_t ua[4] = {0, 0, 0, 0}, ub[4] = {0, 0, 0, 0};
+                            const uint32_t mine = round_u8(hacc[j].x) | round_u8(hacc[j].y) << 8;
+                            hacc[j] = make_float2(0.f, 0.f);
+                            // gather the pixel's channels from the C lanes of this row slot
+                            uint32_t u[4] = {0, 0, 0, 0};
+                            const uint32_t sel = (C > 1 && h_ch == 1) ? 8u : 0u;
 #pragma unroll
-                            for (int k = 0; k < C; k++) {
-                                ua[k] = round_u8(hacc[j][k].x);
-                                ub[k] = round_u8(hacc[j][k].y);
-                                hacc[j][k] = make_float2(0.f, 0.f);
+                            for (int k = 0; k < C; k++) u[k] = (__shfl_sync(0xffffffffu, mine, int(lane - h_ch) + k) >> sel) & 0xffu;
+                            if constexpr (C == 1) {
+                                if (h_emit_a) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy, u);
+                                u[0] = mine >> 8;
+                                if (h_emit_b) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy + h_half, u);
+                            } else {
+                                if (h_emit_a || h_emit_b) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy + (h_ch ? h_half : 0u), u);
                             }
-                            emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy, ua);
-                            if (h_second) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy + h_half, ub);
                         }
                     }
                     h_next += __popc(fl);
@@ -288,12 +300,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             // two pixels per iteration: all shared-memory reads of both are issued before the FMAs
             for (uint32_t xl = 0; xl < npx; xl += 2) {
                 const bool two = xl + 1 < npx;
-                float2 va[C], vb[C];
-#pragma unroll
-                for (int k = 0; k < C; k++) va[k] = make_float2(tcol[size_t(xl * C + k) * r_pad], tcol[size_t(xl * C + k) * r_pad + h_half]);
-#pragma unroll
-                for (int k = 0; k < C; k++)  // within shared memory even past npx
-                    vb[k] = make_float2(tcol[size_t((xl + 1) * C + k) * r_pad], tcol[size_t((xl + 1) * C + k) * r_pad + h_half]);
+                const float *pa = tcol + size_t(xl * C) * r_pad, *pb = pa + size_t(C) * r_pad;  // within shared memory even past npx
+                const float2 va = make_float2(pa[h_ra], pa[h_rb]);
+                const float2 vb = make_float2(pb[h_ra], pb[h_rb]);
                 const uint32_t ia = hinfo_s[xl], ib = hinfo_s[xl + 1];
                 const float4 wa0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
                 const float4 wa1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
