@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--e2e-pool", type=int, default=1024, help="distinct pinned host images cycled by the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check (kernel ablation runs only)")
     ap.add_argument("--exact", action="store_true", help="bit-exact kernels (crate operation order)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -259,7 +260,7 @@ def main():
 
     # parity spot check at full size: a few images of the batch against the oracle
     parity = None
-    if rank == 0:
+    if rank == 0 and not args.no_parity:
         from oracle import oracle as O
 
         d2 = 0

@@ -29,11 +29,13 @@ __device__ __forceinline__ void load_px(const StageDesc &d, uint32_t x, uint32_t
     }
 }
 
-// clamp(t, 0, 255) then f32::round (half away from zero), as FloatNearest.
+// clamp(t, 0, 255) then f32::round (half away from zero), as FloatNearest.  For t >= 0,
+// round(t) = floor(t + 0.5); adding with round-toward-zero keeps the sum from rounding up to
+// the next integer (t = 0.5 - 2^-25), and the saturating conversion is the clamp (NaN -> 0).
 __device__ __forceinline__ uint32_t round_u8(float t) {
-    t = fminf(fmaxf(t, 0.0f), 255.0f);
-    const float f = floorf(t);
-    return uint32_t(f) + ((t - f) >= 0.5f ? 1u : 0u);
+    uint32_t r;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(__fadd_rz(t, 0.5f)));
+    return r;
 }
 
 // DynamicImage pixel viewed as Rgba<u8> (to_rgba): L->(l,l,l,255) La->(l,l,l,a) Rgb->(r,g,b,255).

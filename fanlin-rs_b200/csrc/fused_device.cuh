@@ -27,7 +27,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// Epilogue for one produced pixel (already rounded channel values).
+// Epilogue for one produced pixel (already rounded channel values) at canvas address q.
+template <int C>
+__device__ __forceinline__ void emit_at(uint8_t *q, uint32_t epi, uint32_t fill, const uint32_t v[4]) {
+    if (epi == EPI_PLAIN) {
+        if constexpr (C == 4) {
+            store_rgba(q, v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24);
+        } else {
+#pragma unroll
+            for (int k = 0; k < C; k++) q[k] = uint8_t(v[k]);
+        }
+    } else {
+        uint32_t px = to_rgba_packed(v, C);
+        if (epi == EPI_BLEND_FILL) px = blend_rgba(fill, px);
+        store_rgba(q, px);
+    }
+}
+
 template <int C, typename ITEM>
 __device__ __forceinline__ void emit_px(const ITEM &it, uint32_t cx, uint32_t cy, const uint32_t v[4]) {
     uint8_t *q = it.dst + size_t(cy) * it.dst_pitch + size_t(cx) * it.c_out;

@@ -16,7 +16,7 @@ struct TcBand {
 };
 struct TcGeom {
     bool ok = false;
-    uint32_t px0 = 0, n_px = 0, hw_off = 0, hinfo_off = 0;
+    uint32_t px0 = 0, n_px = 0, hw_off = 0, hinfo_off = 0, cpre_off = 0, out_stride = 1;
     float scale = 1.f;
     std::vector<TcBand> bands;
 };
@@ -31,25 +31,59 @@ uint32_t r_pad_for(uint32_t rows, uint32_t c) {
     return rows + ((want + 32u - (rows & 31u)) & 31u);
 }
 
+// Horizontal scatter table of the tensor-core kernel, one record per PAIR of source pixels
+// (x0 = px0 + 2p, x0 + 1): w[p][0..8) / w[p][8..16) are the weights of the two pixels for
+// the outputs base(p) + j, j < 8, where base(p) is the first output whose window has not ended
+// before x0; cnt[p] = outputs whose window ends inside the pair.  The kernel keeps the 8
+// accumulators as a shift register: after the pair it writes out and shifts cnt[p] times, so
+// slot j always means "j-th unfinished output" and no slot index is ever computed.
+bool tc_pair_table(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t px0, uint32_t n_px, float *w, uint32_t *cnt) {
+    const uint32_t n_pairs = (n_px + 1) / 2, o_end = o0 + n;
+    uint32_t base = o0;
+    for (uint32_t p = 0; p < n_pairs; p++) {
+        const uint32_t x0 = px0 + 2 * p, x1 = x0 + 1;
+        for (uint32_t o = base; o < o_end && t.entries[o].left <= x1; o++) {
+            const TapEntry &e = t.entries[o];
+            const uint32_t j = o - base;
+            if (j >= FUSED_SLOTS) return false;  // more than 8 unfinished outputs
+            if (x0 >= e.left && x0 < e.left + e.count) w[size_t(p) * 16 + j] = t.weights[e.woff + (x0 - e.left)];
+            if (x1 >= e.left && x1 < e.left + e.count) w[size_t(p) * 16 + 8 + j] = t.weights[e.woff + (x1 - e.left)];
+        }
+        uint32_t c = 0;
+        while (base < o_end && t.entries[base].left + t.entries[base].count <= x0 + 2) { base++; c++; }
+        cnt[p] = c;
+    }
+    return base == o_end;  // every output was finished, in order
+}
+
 }  // namespace
 
 // chunk bytes + the <= 15 bytes of alignment padding in front of them fit the 128-byte tile row
 uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 112u : c == 2 ? 60u : c == 3 ? 38u : 32u; }
 
-size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max) {
+static const size_t TC_SMEM_LIMIT = 232448 - 3072 - 256;  // the kernel also has 3 KB of static shared memory
+
+size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max, uint32_t out_stride, uint32_t n_a) {
     const size_t tmp = size_t(TC_M) * r_pad_for(band_rows, c) * 4;
-    const size_t a = 2 * size_t(kg_max) * TC_M, b = 2 * size_t(TC_N) * kg_max;
+    const size_t a = size_t(n_a) * kg_max * TC_M, b = 2 * size_t(TC_N) * kg_max;       // source slots, two weight-tile slots
     const size_t ht = 2 * ((size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15));  // two copies of the chunk's horizontal table slice
-    return tmp + a + b + ht + 1024 + 128;  // + slack to align the tile buffers to 1024 bytes
+    const size_t out = size_t(band_rows) * out_stride * 4;                            // output pixels finished in the chunk
+    return tmp + a + b + ht + out + 1024 + 128;  // + slack to align the slots to 1024 bytes
 }
 
-uint32_t fused_tc_max_band(uint32_t c) {
-    const size_t limit = 232448 - 1024;
-    const size_t fixed = fused_tc_smem_bytes(c, 0, TC_KG_MAX);
-    const uint32_t rows = uint32_t((limit - fixed) / (TC_M * 4));  // fixed already holds r_pad_for(0) <= 17 columns
+// Source slots take the shared memory the band leaves: the more groups are in flight, the
+// better the loads cover the L2 / HBM latency (2 = ping-pong, measured latency-bound).
+uint32_t fused_tc_source_slots(uint32_t c, uint32_t band_rows, uint32_t kg_max, uint32_t out_stride) {
+    uint32_t n = 4;
+    while (n > 0 && fused_tc_smem_bytes(c, band_rows, kg_max, out_stride, n) > TC_SMEM_LIMIT) n--;
+    return n;
+}
+
+uint32_t fused_tc_max_band(uint32_t c, uint32_t out_stride) {
     // the horizontal stage maps (row pair, channel) to the lanes of TC_H_WARPS warps
-    const uint32_t lanes_cap = 2 * TC_H_WARPS * (32 / c);
-    return std::min(std::min(192u, lanes_cap), rows - 32);
+    uint32_t rows = std::min(192u, 2 * TC_H_WARPS * (32 / c));
+    while (rows > 8 && fused_tc_source_slots(c, rows, TC_KG_MAX, out_stride) < 2) rows--;
+    return rows;
 }
 
 struct FusedTcCache {
@@ -74,25 +108,44 @@ bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
 }
 
 static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
-    const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c);
+    const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c | (s.c_out << 8));
     auto it = cache->geoms.find(key);
     if (it != cache->geoms.end()) return it->second;
     TcGeom g;
-    // horizontal: scatter table with true-scale weights (the tile holds true-scale f32)
+    // horizontal: pair table with true-scale weights (the tile holds true-scale f32)
     g.px0 = s.sx0 / 4 * 4;
     g.n_px = s.sx0 + s.n_sx - g.px0;
+    tabs->w.resize((tabs->w.size() + 3) & ~size_t(3), 0.0f);  // the kernel stages the table with 16-byte copies
     g.hw_off = uint32_t(tabs->w.size());
     g.hinfo_off = uint32_t(tabs->info.size());
-    tabs->w.resize(tabs->w.size() + size_t(g.n_px) * FUSED_SLOTS, 0.0f);
-    tabs->info.resize(tabs->info.size() + g.n_px, 0u);
-    bool ok = fused_scatter(*s.htab, s.ox0, s.n_cols, s.ox0, g.px0, g.n_px, 1.0f, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
+    const uint32_t n_pairs = (g.n_px + 1) / 2;
+    tabs->w.resize(tabs->w.size() + size_t(n_pairs) * 16, 0.0f);
+    tabs->info.resize(tabs->info.size() + n_pairs, 0u);
+    bool ok = tc_pair_table(*s.htab, s.ox0, s.n_cols, g.px0, g.n_px, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
+    // outputs finished before each chunk; the widest chunk sizes the output staging buffer
+    {
+        const uint32_t chunk_pairs = fused_tc_chunk_px(s.c) / 2, n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+        g.cpre_off = uint32_t(tabs->info.size());
+        tabs->info.resize(tabs->info.size() + n_chunks + 1, 0u);
+        uint32_t acc = 0, widest = 0;
+        for (uint32_t ch = 0; ch < n_chunks; ch++) {
+            tabs->info[g.cpre_off + ch] = acc;
+            uint32_t here = 0;
+            for (uint32_t p = ch * chunk_pairs; p < std::min(n_pairs, (ch + 1) * chunk_pairs); p++) here += tabs->info[g.hinfo_off + p];
+            acc += here;
+            widest = std::max(widest, here);
+        }
+        tabs->info[g.cpre_off + n_chunks] = acc;
+        g.out_stride = ((widest * s.c_out + 6) / 4 + 1) | 1u;  // + 3 bytes of alignment phase; odd: rows hit distinct banks
+    }
     // vertical: q = round(w * 2^sh) split into three signed base-128 digits
     float maxw = 0.f;
     for (float w : s.vtab->weights) maxw = std::max(maxw, std::fabs(w));
     int sh = 30;
     while (sh > 0 && std::ldexp(double(maxw), sh) > 2080000.0) sh--;
     g.scale = std::ldexp(1.0f, -sh);
-    const uint32_t max_band = fused_tc_max_band(s.c);
+    const uint32_t max_band = fused_tc_max_band(s.c, g.out_stride);
+    if (max_band < 32) ok = false;  // strong upscales finish too many pixels per chunk to stage: CUDA-core path
     const uint32_t n_bands = (s.n_rows + max_band - 1) / max_band;
     const uint32_t band_rows = (s.n_rows + n_bands - 1) / n_bands;
     // source rows spanned by output rows [ra, rb) of the band starting at b0
@@ -181,7 +234,8 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         f.band_r0 = bt.r0; f.band_rows = bt.rows; f.r_pad = r_pad_for(bt.rows, s.c);
         f.grp_off = bt.grp_off; f.n_groups = bt.n_groups; f.kg_max = bt.kg_max; f.grp_rows = bt.grp_rows;
         f.scale = g.scale;
-        f.hw_off = g.hw_off; f.hinfo_off = g.hinfo_off;
+        f.hw_off = g.hw_off; f.hinfo_off = g.hinfo_off; f.cpre_off = g.cpre_off; f.out_stride = g.out_stride;
+        f.n_a = fused_tc_source_slots(s.c, bt.rows, bt.kg_max, g.out_stride);
         f.n_cols = s.n_cols;
         f.dst_pitch = s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
         f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;

@@ -23,6 +23,7 @@
 // channel) so that every consumer warp takes part, f32x2 FMAs over the row pair, and a warp
 // shuffle that gathers a finished pixel's channels for the epilogue.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "fused_device.cuh"
 #include "fused_tc.h"
@@ -33,7 +34,10 @@ namespace fanlin {
 namespace {
 
 constexpr int NT = 32 * TC_H_WARPS;  // consumer threads (10 warps: 8 drain TMEM, all run the horizontal stage)
-constexpr int NT_ALL = NT + 64;   // + the MMA-issuing warp and the TMA-issuing warp
+constexpr int NT_ALL = NT + 96;   // + the MMA-issuing warp and the two TMA-issuing warps (source slabs, weight tiles)
+constexpr uint32_t NB = 2;        // shared-memory slots for weight-digit tiles
+constexpr uint32_t SLAB = 32 * TC_M;  // one K step of A: 32 source rows x 128 bytes
+constexpr uint32_t NA_MAX = 4;    // most shared-memory slots for a group's source rows
 constexpr uint32_t NR = 5;        // TMEM accumulator regions of 96 columns
 constexpr int S = FUSED_SLOTS;
 constexpr uint32_t TMEM_COLS = 512;  // NR regions of 96 columns
@@ -68,6 +72,8 @@ __device__ __forceinline__ void ffma2(float2 &acc, float2 a, float w) {
         : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
 }
 
+__device__ __forceinline__ void sts8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
@@ -81,13 +87,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                                                                   const CUtensorMap *__restrict__ tmaps,
                                                                   const uint8_t *__restrict__ tb,
                                                                   const float *__restrict__ tw,
-                                                                  const uint32_t *__restrict__ tinfo) {
+                                                                  const uint32_t *__restrict__ tinfo, uint32_t dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
     __shared__ FusedTcItem it_s;
     __shared__ __align__(8) uint64_t mbar[NR];       // the MMAs into TMEM region r have retired
     __shared__ __align__(8) uint64_t tmem_free[NR];  // the 8 draining warps have emptied region r
-    __shared__ __align__(8) uint64_t full[2];  // the copies into shared-memory buffer b have landed
+    __shared__ __align__(8) uint64_t a_full[NA_MAX];         // the group's source rows have landed
+    __shared__ __align__(8) uint64_t b_full[NB];             // the group's weight-digit tile has landed
     __shared__ uint32_t tmem_base_s;
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
@@ -97,8 +104,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[r])));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&tmem_free[r])));
         }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&full[1])));
+        for (uint32_t r = 0; r < NA_MAX; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&a_full[r])));
+        for (uint32_t r = 0; r < NB; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&b_full[r])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -116,12 +123,18 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
 
     // ---- shared-memory carve-up
     const uint32_t r_pad = it.r_pad, kg_max = it.kg_max, grp_rows = it.grp_rows;
-    float *tmp = reinterpret_cast<float *>(smem);                      // [128][r_pad]
-    uint8_t *sA = smem + size_t(TC_M) * r_pad * 4;                     // 2 x [kg_max rows][128 B], 128-byte swizzle (1024-aligned)
-    uint8_t *sB = sA + 2 * size_t(kg_max) * TC_M;                      // 2 x [96][kg_max], core-matrix layout
-    float *hw_s0 = reinterpret_cast<float *>(sB + 2 * size_t(TC_N) * kg_max);  // 2 x ([chunk_px][8] weights + [chunk_px] info)
+    const uint32_t n_a = it.n_a;
+    uint8_t *sA = smem;                                                // n_a x [kg_max rows][128 B], 128-byte swizzle (1024-aligned)
+    uint8_t *sB = sA + size_t(n_a) * kg_max * TC_M;                    // NB x [96][kg_max], core-matrix layout
+    float *tmp = reinterpret_cast<float *>(sB + NB * size_t(TC_N) * kg_max);  // [128][r_pad]
+    float *hw_s0 = tmp + size_t(TC_M) * r_pad;                         // 2 x ([chunk_px / 2][16] weights + [chunk_px / 2] counts)
     const uint32_t chunk_px = it.chunk_px, n_px = it.n_px, n_chunks = it.n_chunks, n_groups = it.n_groups;
     const uint32_t htab_words = (chunk_px * (S + 1) + 3) & ~3u;  // each copy stays 16-byte aligned
+    // pixels finished during a chunk wait here, [band row][out_stride words], and leave as whole
+    // words per row segment after the chunk (scattered 1-byte stores cost one LSU slot per row)
+    uint32_t *out_s = reinterpret_cast<uint32_t *>(hw_s0 + 2 * htab_words);
+    const uint32_t out_stride = it.out_stride;
+    for (uint32_t k = tid; k < it.band_rows * out_stride; k += NT_ALL) out_s[k] = 0xffffffffu;  // alpha of opaque RGBA output stays 255
     const CUtensorMap *tmap = tmaps + blockIdx.x;
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
     // group table {k0, kg, b_off, rows} in shared memory: the producer's issue path must not wait on L2
@@ -139,77 +152,86 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const bool h_warp = warp * RPW < h_half;  // warp-uniform: this warp has rows to produce
     const bool h_lane = lane < RPW * C && h_slot < h_half;
     const uint32_t h_ra = min(h_slot, h_half - 1), h_rb = min(h_ra + h_half, it.band_rows - 1);  // clamped: idle lanes read valid tile rows
-    // which of the two rows this lane writes out once the channels are gathered: channel 0 -> ra,
-    // channel 1 -> rb (a single-channel lane writes both)
-    const bool h_emit_a = h_lane && h_ch == 0;
-    const bool h_emit_b = h_lane && h_ch == (C > 1 ? 1u : 0u) && h_slot + h_half < it.band_rows;
-    float2 hacc[S];  // .x = row ra, .y = row rb
+    float2 hacc[S];  // .x = row ra, .y = row rb; slot j = the j-th unfinished output pixel (shift register)
 #pragma unroll
     for (int j = 0; j < S; j++) hacc[j] = make_float2(0.f, 0.f);
-    uint32_t h_next = 0;
-    const float *hw = tw + it.hw_off;
-    const uint32_t *hinfo = tinfo + it.hinfo_off;
-    const uint32_t h_cx0 = it.dst_x, h_cy = it.dst_y + it.band_r0 + h_ra;
-
-    // Thread 0 only: fetch group g of the chunk whose 16-byte aligned first column is seg0 into
-    // shared-memory buffer `buf` (one TMA tensor copy + one bulk copy, completion on full[buf]).
-    auto issue_load = [&](uint32_t g, uint32_t buf, uint32_t seg0) {
-        const uint32_t k0 = grp[4 * g], kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
-        const uint32_t bar = smem_u32(&full[buf]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M + kg * TC_N) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                         sA_u + buf * kg_max * TC_M),
-                     "l"(tmap), "r"(bar), "r"(seg0 * 16), "r"(k0)
-                     : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB_u + buf * TC_N * kg_max),
-                     "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
-                     : "memory");
-    };
-    // Thread 0 only: the MMAs of group g (operands in shared-memory buffer buf, accumulators in
-    // TMEM buffer buf), committed to mbar[buf].
-    auto issue_mma = [&](uint32_t g, uint32_t buf, uint32_t region) {
-        const uint32_t kg = grp[4 * g + 1];
-        // descriptors advance by a constant per K step: 32 rows x 128 B of A, 2 core matrices of B
-        uint64_t da = umma_desc(sA_u + buf * kg_max * TC_M, 16, 1024, 2);  // SBO = 8-row atom stride
-        uint64_t db = umma_desc(sB_u + buf * TC_N * kg_max, 128, (kg / 16) * 128);
-        const uint32_t d_tmem = tmem_base + region * TC_N;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                     "l"(da), "l"(db), "r"(UMMA_IDESC)
-                     : "memory");
-        for (uint32_t ks = 1; ks < kg / 32; ks++) {
-            da += (32 * 128) >> 4;
-            db += (2 * 128) >> 4;
-            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                         "l"(da), "l"(db), "r"(UMMA_IDESC)
-                         : "memory");
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[region])) : "memory");
-    };
+    const float *hw = tw + it.hw_off;            // [pixel pairs][2][8]
+    const uint32_t *hinfo = tinfo + it.hinfo_off;  // [pixel pairs] outputs finished by the pair
+    // first canvas byte of the band's rows: row r starts at h_row0 + r * dst_pitch
+    const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows;
+    uint8_t *const h_row0 = it.dst + size_t(it.dst_y + it.band_r0) * it.dst_pitch + size_t(it.dst_x) * h_cout;
+    const bool h_has_b = h_lane && h_slot + h_half < it.band_rows;
+    const uint32_t h_pha = uint32_t(reinterpret_cast<uintptr_t>(h_row0 + size_t(h_ra) * it.dst_pitch));  // low bits: alignment phase
+    const uint32_t h_phb = uint32_t(reinterpret_cast<uintptr_t>(h_row0 + size_t(h_rb) * it.dst_pitch));
+    const uint32_t out_u = smem_u32(out_s);
+    const uint32_t *cpre = tinfo + it.cpre_off;
+    const uint32_t h_epi = it.epi, h_fill = it.fill;
 
     auto chunk_seg0 = [&](uint32_t chunk) { return ((it.px0 + chunk * chunk_px) * C) >> 4; };
-    // Groups are numbered flat across chunks (gg = chunk * n_groups + g): shared-memory slot
-    // gg & 1, TMEM region gg % NR.
+    // Groups are numbered flat across chunks (gg = chunk * n_groups + g): source slot gg % n_a,
+    // weight-tile slot gg % NB, TMEM region gg % NR.
     const uint32_t total = n_chunks * n_groups;
 
     if (warp == NT / 32 + 1) {
-        // ================= TMA warp: one thread keeps the two shared-memory slots filled =================
+        // ===== source TMA warp: one tensor copy per group (kg_max rows x 128 B), n_a groups deep =====
         if (lane == 0) {
-            uint32_t ld_chunk = 0, ld_g = 0;
+            uint32_t g = 0, chunk = 0, slot = 0;
             for (uint32_t gg = 0; gg < total; gg++) {
-                if (gg >= 2) mbar_wait(smem_u32(&mbar[(gg - 2) % NR]), ((gg - 2) / NR) & 1);  // slot gg & 1 was read by the MMAs of group gg - 2
-                issue_load(ld_g, gg & 1, chunk_seg0(ld_chunk));
-                if (++ld_g == n_groups) { ld_g = 0; ld_chunk++; }
+                if (gg >= n_a) mbar_wait(smem_u32(&mbar[(gg - n_a) % NR]), ((gg - n_a) / NR) & 1);  // the slot was read by the MMAs of group gg - n_a
+                const uint32_t bar = smem_u32(&a_full[slot]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                                 sA_u + slot * kg_max * TC_M),
+                             "l"(tmap), "r"(bar), "r"(chunk_seg0(chunk) * 16), "r"(grp[4 * g])
+                             : "memory");
+                if (++slot == n_a) slot = 0;
+                if (++g == n_groups) { g = 0; chunk++; }
+            }
+        }
+    } else if (warp == NT / 32 + 2) {
+        // ===== weight TMA warp: one bulk copy per group into slot gg % NB =====
+        if (lane == 0) {
+            uint32_t g = 0;
+            for (uint32_t gg = 0; gg < total; gg++) {
+                if (gg >= NB) mbar_wait(smem_u32(&mbar[(gg - NB) % NR]), ((gg - NB) / NR) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
+                const uint32_t kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
+                const uint32_t bar = smem_u32(&b_full[gg % NB]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 sB_u + (gg % NB) * TC_N * kg_max),
+                             "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
+                             : "memory");
+                if (++g == n_groups) g = 0;
             }
         }
     } else if (warp == NT / 32) {
-        // ================= MMA warp: one thread issues every tcgen05.mma =================
+        // ===== MMA warp: one thread issues every tcgen05.mma =====
         if (lane == 0) {
-            for (uint32_t pg = 0; pg < total; pg++) {
-                const uint32_t region = pg % NR, use = pg / NR;
-                mbar_wait(smem_u32(&full[pg & 1]), (pg >> 1) & 1);                       // operands have landed
-                if (use > 0) mbar_wait(smem_u32(&tmem_free[region]), (use - 1) & 1);    // consumers drained the region's previous contents
+            uint32_t g = 0, slot = 0, suse = 0;
+            for (uint32_t gg = 0; gg < total; gg++) {
+                const uint32_t region = gg % NR, ruse = gg / NR, bslot = gg % NB;
+                const uint32_t kg = grp[4 * g + 1];
+                mbar_wait(smem_u32(&b_full[bslot]), (gg / NB) & 1);                      // the weight tile has landed
+                mbar_wait(smem_u32(&a_full[slot]), suse & 1);                           // the source rows have landed
+                if (ruse > 0) mbar_wait(smem_u32(&tmem_free[region]), (ruse - 1) & 1);  // consumers drained the region's previous contents
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_mma(pg % n_groups, pg & 1, region);
+                // descriptors advance by a constant per K step: 32 rows x 128 B of A, 2 core matrices of B
+                uint64_t da = umma_desc(sA_u + slot * kg_max * TC_M, 16, 1024, 2);  // SBO = 8-row atom stride
+                uint64_t db = umma_desc(sB_u + bslot * TC_N * kg_max, 128, (kg / 16) * 128);
+                const uint32_t d_tmem = tmem_base + region * TC_N;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                             "l"(da), "l"(db), "r"(UMMA_IDESC)
+                             : "memory");
+                for (uint32_t ks = 1; ks < kg / 32; ks++) {
+                    da += SLAB >> 4;
+                    db += (2 * 128) >> 4;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                                 "l"(da), "l"(db), "r"(UMMA_IDESC)
+                                 : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[region])) : "memory");
+                if (++slot == n_a) { slot = 0; suse++; }
+                if (++g == n_groups) g = 0;
             }
         }
     } else {
@@ -219,8 +241,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         float *dstw = hw_s0 + (chunk & 1) * htab_words;
         const uint32_t sa_w = smem_u32(dstw), sa_i = smem_u32(dstw + size_t(chunk_px) * S);
         const uint32_t *gw = reinterpret_cast<const uint32_t *>(hw + size_t(cpx0) * S);
-        for (uint32_t k = tid; k < npx * S; k += NT) cp_async4(sa_w + 4 * k, gw + k, true);
-        for (uint32_t k = tid; k < npx; k += NT) cp_async4(sa_i + 4 * k, hinfo + cpx0 + k, true);
+        const uint32_t npairs = (npx + 1) / 2;  // cpx0 and chunk_px are even
+        for (uint32_t k = tid; k < npairs * 4; k += NT) cp_async16(sa_w + 16 * k, gw + 4 * k);
+        for (uint32_t k = tid; k < npairs; k += NT) cp_async4(sa_i + 4 * k, hinfo + cpx0 / 2 + k, true);
         cp_async_commit();
     };
     stage_htab(0);
@@ -230,6 +253,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         const uint32_t cpx0 = chunk * chunk_px;
         const uint32_t npx = min(chunk_px, n_px - cpx0);
         const uint32_t sh = ((it.px0 + cpx0) * C) & 15u;  // padding columns in front of the chunk
+        const uint32_t o_first = __ldg(cpre + chunk), o_count = __ldg(cpre + chunk + 1) - o_first;  // output pixels finished by this chunk
         // ================= vertical stage: drain the tensor-core results =================
         for (uint32_t g = 0; g < n_groups; g++, gg++) {
             const uint32_t region = gg % NR;
@@ -254,7 +278,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                     const uint32_t j = half * 16 + e;
                     const int ml = int(mid[e]) * 128 + int(lo[e]);
                     const float v = fmaf(float(int(hi[e])), scale_hi, float(ml) * scale);
-                    if (j < jn) t[j] = v;  // lanes = consecutive columns, r_pad odd: conflict-free
+                    if (j < jn && !(dbg & 4)) t[j] = v;  // lanes = consecutive columns, r_pad odd: conflict-free
                 }
             }
         }
@@ -263,56 +287,110 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         cp_async_wait<1>();  // this chunk's table slice (committed one chunk ago) has landed
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // consumers only: the tile is complete
         // ================= horizontal stage: CUDA cores =================
-        if (h_warp) {
-            const float *tcol = tmp + size_t(sh + h_ch) * r_pad;
+        if (h_warp && !(dbg & 1)) {
             const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
             const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
-            // one pixel: scatter this lane's channel value (of both rows) into the live slots, then flush completed outputs
-            auto step = [&](const float2 v, const float4 &w0, const float4 &w1, uint32_t info) {
-                const float w[S] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const uint32_t n_pairs = (npx + 1) / 2;
+            // staging byte addresses of this lane's channel in rows ra / rb: the row segment keeps the
+            // alignment phase of its canvas address so that staged words are canvas words
+            uint32_t sa = out_u + (h_ra * out_stride) * 4 + ((h_pha + o_first * h_cout) & 3u) + h_ch;
+            uint32_t sb = out_u + (h_rb * out_stride) * 4 + ((h_phb + o_first * h_cout) & 3u) + h_ch;
+            // Software pipeline over pixel pairs, two register sets (A, B) in ping-pong: the shared-memory
+            // reads of the next pair are issued before the FMAs of the current one.  (The second pixel
+            // of a last odd pair lies inside the tile and has zero weights.)
+            struct PairRegs {
+                float2 va, vb;
+                float4 w0, w1, w2, w3;
+                uint32_t cnt;
+            };
+            const float *pva = tmp + size_t(sh + h_ch) * r_pad + h_ra, *pvb = tmp + size_t(sh + h_ch) * r_pad + h_rb;
+            const uint32_t cstep = C * r_pad, pstep = 2 * C * r_pad;
+            const float4 *wp = reinterpret_cast<const float4 *>(hw_s);
+            const uint32_t last = n_pairs - 1;
+            auto load = [&](PairRegs &P, uint32_t pi) {
+                pi = min(pi, last);
+                const float *qa = pva + size_t(pi) * pstep, *qb = pvb + size_t(pi) * pstep;
+                P.va = make_float2(qa[0], qb[0]);
+                P.vb = make_float2(qa[cstep], qb[cstep]);
+                P.w0 = wp[4 * pi]; P.w1 = wp[4 * pi + 1]; P.w2 = wp[4 * pi + 2]; P.w3 = wp[4 * pi + 3];
+                P.cnt = hinfo_s[pi];
+            };
+            auto compute = [&](const PairRegs &P) {
+                const float wa[S] = {P.w0.x, P.w0.y, P.w0.z, P.w0.w, P.w1.x, P.w1.y, P.w1.z, P.w1.w};
+                const float wb[S] = {P.w2.x, P.w2.y, P.w2.z, P.w2.w, P.w3.x, P.w3.y, P.w3.z, P.w3.w};
 #pragma unroll
-                for (int j = 0; j < S; j++) ffma2(hacc[j], v, w[j]);
-                const uint32_t fl = (info >> 8) & 0xffu;
-                if (fl) {  // uniform over the CTA
+                for (int j = 0; j < S; j++) ffma2(hacc[j], P.va, wa[j]);
 #pragma unroll
-                    for (int j = 0; j < S; j++) {
-                        if (fl & (1u << j)) {
-                            const uint32_t o = h_next + ((uint32_t(j) - h_next) & (S - 1));
-                            const uint32_t mine = round_u8(hacc[j].x) | round_u8(hacc[j].y) << 8;
-                            hacc[j] = make_float2(0.f, 0.f);
-                            // gather the pixel's channels from the C lanes of this row slot
-                            uint32_t u[4] = {0, 0, 0, 0};
-                            const uint32_t sel = (C > 1 && h_ch == 1) ? 8u : 0u;
+                for (int j = 0; j < S; j++) ffma2(hacc[j], P.vb, wb[j]);
+                for (uint32_t n = 0; n < ((dbg & 2) ? 0u : P.cnt); n++) {  // uniform over the CTA: write out slot 0, shift the rest down
+                    const uint32_t ua = round_u8(hacc[0].x), ub = round_u8(hacc[0].y);
 #pragma unroll
-                            for (int k = 0; k < C; k++) u[k] = (__shfl_sync(0xffffffffu, mine, int(lane - h_ch) + k) >> sel) & 0xffu;
-                            if constexpr (C == 1) {
-                                if (h_emit_a) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy, u);
-                                u[0] = mine >> 8;
-                                if (h_emit_b) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy + h_half, u);
+                    for (int j = 0; j + 1 < S; j++) hacc[j] = hacc[j + 1];
+                    hacc[S - 1] = make_float2(0.f, 0.f);
+                    if constexpr (C == 1 || C == 3) {
+                        // Opaque pixels: the overlay onto the fill colour returns the pixel itself (blend_rgba,
+                        // alpha 255), so every lane stages its own channel byte and nothing is gathered.
+                        if (h_lane) sts8(sa, ua);
+                        if (h_has_b) sts8(sb, ub);
+                        if (C == 1 && h_epi != EPI_PLAIN) {  // L -> (l, l, l, 255)
+                            if (h_lane) { sts8(sa + 1, ua); sts8(sa + 2, ua); }
+                            if (h_has_b) { sts8(sb + 1, ub); sts8(sb + 2, ub); }
+                        }
+                    } else {
+                        // gather the pixel's channels from the C lanes of this row slot; the channel-0 lane
+                        // stages row ra, the channel-1 lane row rb
+                        const uint32_t mine = ua | ub << 8;
+                        uint32_t u[4] = {0, 0, 0, 0};
+                        const uint32_t sel = h_ch == 1 ? 8u : 0u;
+#pragma unroll
+                        for (int k = 0; k < C; k++) u[k] = (__shfl_sync(0xffffffffu, mine, int(lane - h_ch) + k) >> sel) & 0xffu;
+                        if (h_ch == 0 ? h_lane : (h_ch == 1 && h_has_b)) {
+                            const uint32_t s0 = (h_ch == 1 ? sb : sa) - h_ch;
+                            if (h_epi == EPI_PLAIN) {
+#pragma unroll
+                                for (int k = 0; k < C; k++) sts8(s0 + k, u[k]);
                             } else {
-                                if (h_emit_a || h_emit_b) emit_px<C, FusedTcItem>(it, h_cx0 + o, h_cy + (h_ch ? h_half : 0u), u);
+                                uint32_t px = to_rgba_packed(u, C);
+                                if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
+#pragma unroll
+                                for (int k = 0; k < 4; k++) sts8(s0 + k, px >> (8 * k));
                             }
                         }
                     }
-                    h_next += __popc(fl);
+                    sa += h_cout;
+                    sb += h_cout;
                 }
             };
-            // two pixels per iteration: all shared-memory reads of both are issued before the FMAs
-            for (uint32_t xl = 0; xl < npx; xl += 2) {
-                const bool two = xl + 1 < npx;
-                const float *pa = tcol + size_t(xl * C) * r_pad, *pb = pa + size_t(C) * r_pad;  // within shared memory even past npx
-                const float2 va = make_float2(pa[h_ra], pa[h_rb]);
-                const float2 vb = make_float2(pb[h_ra], pb[h_rb]);
-                const uint32_t ia = hinfo_s[xl], ib = hinfo_s[xl + 1];
-                const float4 wa0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S);
-                const float4 wa1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl) * S + 4);
-                const float4 wb0 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl + 1) * S);
-                const float4 wb1 = *reinterpret_cast<const float4 *>(hw_s + size_t(xl + 1) * S + 4);
-                step(va, wa0, wa1, ia);
-                if (two) step(vb, wb0, wb1, ib);
+            PairRegs A, B;
+            load(A, 0);
+            for (uint32_t p = 0; p < n_pairs; p += 2) {
+                load(B, p + 1);
+                compute(A);
+                load(A, p + 2);
+                if (p + 1 < n_pairs) compute(B);
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the tile may be overwritten
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the tile may be overwritten; the staged pixels are complete
+        // ================= write out the pixels finished in this chunk =================
+        if (const uint32_t nb = o_count * h_cout) {
+            for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8) {  // 8 lanes per row segment
+                uint8_t *g0 = h_row0 + size_t(r) * h_pitch + size_t(o_first) * h_cout;
+                const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(g0)) & 3u;
+                const uint32_t nw = (ph + nb + 3) >> 2;
+                for (uint32_t k = tid & 7; k < nw; k += 8) {
+                    const uint32_t wv = out_s[r * out_stride + k];
+                    uint8_t *gw = g0 - ph + 4 * k;
+                    const int lo = int(ph) - int(4 * k), hi = int(ph + nb) - int(4 * k);  // the word's valid bytes: [lo, hi)
+                    if (lo <= 0 && hi >= 4) {
+                        *reinterpret_cast<uint32_t *>(gw) = wv;
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (b >= lo && b < hi) gw[b] = uint8_t(wv >> (8 * b));
+                    }
+                }
+            }
+        }
     }
     }  // consumer warps
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -326,7 +404,7 @@ void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t
     auto kern = fused_resample_tc_kernel<C>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     lc.begin("fused_resample_tc_kernel");
-    kern<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info);
+    kern<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info, getenv("TC_DBG") ? atoi(getenv("TC_DBG")) : 0);
     lc.end();
 }
 

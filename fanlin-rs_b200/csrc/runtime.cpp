@@ -373,7 +373,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             }
             hs.n_items = uint32_t(tcitems.size() - hs.first);
             for (size_t k = hs.first; k < tcitems.size(); k++)
-                hs.smem = std::max(hs.smem, fused_tc_smem_bytes(kv.first, tcitems[k].band_rows, tcitems[k].kg_max));
+                hs.smem = std::max(hs.smem, fused_tc_smem_bytes(kv.first, tcitems[k].band_rows, tcitems[k].kg_max, tcitems[k].out_stride, tcitems[k].n_a));
             if (hs.n_items) hsteps.push_back(hs);
         }
         for (auto &kv : by_variant) {
