@@ -12,4 +12,4 @@ from .device import (  # noqa: F401
     GRAYSCALE, INVERSE, HAS_DIMS, CROP, TO_RGBA8,
 )
 from .query import Query  # noqa: F401
-from .stage import process_image, process_gif_frames, make_job  # noqa: F401
+from .stage import process_image, process_images, process_gif_frames, make_job  # noqa: F401

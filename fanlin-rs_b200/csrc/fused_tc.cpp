@@ -80,8 +80,8 @@ uint32_t fused_tc_source_slots(uint32_t c, uint32_t band_rows, uint32_t kg_max, 
 }
 
 uint32_t fused_tc_max_band(uint32_t c, uint32_t out_stride) {
-    // the horizontal stage maps (row pair, channel) to the lanes of TC_H_WARPS warps
-    uint32_t rows = std::min(192u, 2 * TC_H_WARPS * (32 / c));
+    // the horizontal stage maps (row pair, channel) to the threads of TC_H_WARPS warps
+    uint32_t rows = std::min(192u, 2 * (TC_H_WARPS * 32 / c));
     while (rows > 8 && fused_tc_source_slots(c, rows, TC_KG_MAX, out_stride) < 2) rows--;
     return rows;
 }

@@ -26,7 +26,7 @@ constexpr uint32_t TC_M = 128;          // source bytes (elements) per chunk row
 constexpr uint32_t TC_GROUP_ROWS = 32;  // most output rows per MMA group (N = 3 * 32); a band may use fewer (grp_rows)
 constexpr uint32_t TC_N = 3 * TC_GROUP_ROWS;
 constexpr uint32_t TC_KG_MAX = 256;     // source rows per group, multiple of 32
-constexpr uint32_t TC_H_WARPS = 10;     // consumer warps; the horizontal stage gives each (row pair, channel) a lane
+constexpr uint32_t TC_H_WARPS = 8;      // consumer warps; the horizontal stage gives each (row pair, channel) a thread
 
 struct FusedTcItem {
     const uint8_t *src;

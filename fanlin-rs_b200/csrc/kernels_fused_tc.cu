@@ -1,7 +1,7 @@
 // Fused separable Lanczos3 resample with the vertical pass on the sm_100a tensor
 // cores (tcgen05.mma kind::i8, accumulators in TMEM).  See fused_tc.h.
 //
-// Per CTA (1 CTA / SM): 10 consumer warps + an MMA-issuing warp + a TMA-issuing warp; one band of <= 192 output rows
+// Per CTA (1 CTA / SM): 8 consumer warps + an MMA-issuing warp + two TMA-issuing warps; one band of <= 192 output rows
 // of one image, swept left to right in chunks of 128 source bytes per row.  Per chunk, per
 // group of 32 output rows:
 //   * the TMA thread fetches the group's source rows with a single TMA tensor copy
@@ -33,7 +33,7 @@ namespace fanlin {
 
 namespace {
 
-constexpr int NT = 32 * TC_H_WARPS;  // consumer threads (10 warps: 8 drain TMEM, all run the horizontal stage)
+constexpr int NT = 32 * TC_H_WARPS;  // consumer threads (8 warps: each drains a quarter of TMEM's lanes and runs a share of the horizontal stage)
 constexpr int NT_ALL = NT + 96;   // + the MMA-issuing warp and the two TMA-issuing warps (source slabs, weight tiles)
 constexpr uint32_t NB = 2;        // shared-memory slots for weight-digit tiles
 constexpr uint32_t SLAB = 32 * TC_M;  // one K step of A: 32 source rows x 128 bytes
@@ -73,6 +73,22 @@ __device__ __forceinline__ void ffma2(float2 &acc, float2 a, float w) {
 }
 
 __device__ __forceinline__ void sts8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(saddr), "r"(v) : "memory"); }
+
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
     asm volatile(
@@ -144,13 +160,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const float scale = it.scale, scale_hi = it.scale * 16384.0f;
 
     // ---- horizontal-stage role of this thread: one channel of TWO output rows (ra and rb = ra +
-    // h_half).  Lanes are (row slot, channel) with the channel fastest, 32 / C slots per warp, so
-    // all consumer warps share the stage; the two rows go through one f32x2 FMA per output slot.
-    constexpr uint32_t RPW = 32 / C;  // row slots per warp (C = 3 leaves lanes 30 and 31 idle)
+    // h_half).  The (row slot, channel) pairs are laid over the consumer threads back to back,
+    // channel fastest -- a slot's channels may sit in two warps -- so that 85 slots x 3 channels
+    // fill exactly the 8 warps, two per scheduler; the two rows go through one f32x2 FMA per
+    // output slot.
     const uint32_t h_half = (it.band_rows + 1) / 2;
-    const uint32_t h_ch = lane % C, h_slot = warp * RPW + lane / C;
-    const bool h_warp = warp * RPW < h_half;  // warp-uniform: this warp has rows to produce
-    const bool h_lane = lane < RPW * C && h_slot < h_half;
+    const uint32_t h_ch = tid % C, h_slot = tid / C;
+    const bool h_warp = (warp * 32) / C < h_half;  // warp-uniform: this warp has rows to produce
+    const bool h_lane = h_slot < h_half;
     const uint32_t h_ra = min(h_slot, h_half - 1), h_rb = min(h_ra + h_half, it.band_rows - 1);  // clamped: idle lanes read valid tile rows
     float2 hacc[S];  // .x = row ra, .y = row rb; slot j = the j-th unfinished output pixel (shift register)
 #pragma unroll
@@ -257,9 +274,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         // ================= vertical stage: drain the tensor-core results =================
         for (uint32_t g = 0; g < n_groups; g++, gg++) {
             const uint32_t region = gg % NR;
-            // TMEM -> f32 tile.  Warp w < 8 reads lanes [32 (w & 3), +32) (= tile columns m) and the
-            // half (w >> 2) of the group's 32 output rows; warps 8 and 9 only join the horizontal stage.
-            if (warp < 8) {
+            // TMEM -> f32 tile.  Warp w reads lanes [32 (w & 3), +32) (= tile columns m) and the
+            // half (w >> 2) of the group's 32 output rows.
+            {
                 mbar_wait(smem_u32(&mbar[region]), (gg / NR) & 1);  // the MMAs of group gg have retired
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane;
@@ -272,13 +289,27 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[region])) : "memory");
                 const uint32_t jn = grp[4 * g + 3];  // output rows in this group
-                float *t = tmp + size_t(m) * r_pad + g * grp_rows;
+                float *t = tmp + size_t(m) * r_pad + g * grp_rows + half * 16;
+                const uint32_t nv = jn > half * 16 ? jn - half * 16 : 0;  // rows of this half that exist
+                float2 v2[8];
 #pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    const uint32_t j = half * 16 + e;
-                    const int ml = int(mid[e]) * 128 + int(lo[e]);
-                    const float v = fmaf(float(int(hi[e])), scale_hi, float(ml) * scale);
-                    if (j < jn && !(dbg & 4)) t[j] = v;  // lanes = consecutive columns, r_pad odd: conflict-free
+                for (int e = 0; e < 16; e += 2) {  // value = (hi 2^14 + mid 2^7 + lo) 2^-s, two rows per f32x2 op
+                    const float2 fh = make_float2(float(int(hi[e])), float(int(hi[e + 1])));
+                    const float2 fl = make_float2(float(int(mid[e]) * 128 + int(lo[e])), float(int(mid[e + 1]) * 128 + int(lo[e + 1])));
+                    float2 r = make_float2(0.f, 0.f);
+                    ffma2(r, fl, scale);
+                    ffma2(r, fh, scale_hi);
+                    v2[e / 2] = r;
+                }
+                if (nv >= 16) {  // lanes = consecutive columns, r_pad odd: conflict-free
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) { t[e] = v2[e / 2].x; t[e + 1] = v2[e / 2].y; }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        if (uint32_t(e) < nv) t[e] = v2[e / 2].x;
+                        if (uint32_t(e + 1) < nv) t[e + 1] = v2[e / 2].y;
+                    }
                 }
             }
         }
@@ -303,17 +334,21 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 float4 w0, w1, w2, w3;
                 uint32_t cnt;
             };
-            const float *pva = tmp + size_t(sh + h_ch) * r_pad + h_ra, *pvb = tmp + size_t(sh + h_ch) * r_pad + h_rb;
-            const uint32_t cstep = C * r_pad, pstep = 2 * C * r_pad;
-            const float4 *wp = reinterpret_cast<const float4 *>(hw_s);
-            const uint32_t last = n_pairs - 1;
-            auto load = [&](PairRegs &P, uint32_t pi) {
-                pi = min(pi, last);
-                const float *qa = pva + size_t(pi) * pstep, *qb = pvb + size_t(pi) * pstep;
-                P.va = make_float2(qa[0], qb[0]);
-                P.vb = make_float2(qa[cstep], qb[cstep]);
-                P.w0 = wp[4 * pi]; P.w1 = wp[4 * pi + 1]; P.w2 = wp[4 * pi + 2]; P.w3 = wp[4 * pi + 3];
-                P.cnt = hinfo_s[pi];
+            // running shared-memory byte addresses of the next pair to load: rows ra / rb of the pair's
+            // first pixel (the second is cstep4 further), its 16 weights and its count; they stop
+            // advancing at the last pair, so the look-ahead loads never leave the chunk
+            uint32_t a_va = smem_u32(tmp + size_t(sh + h_ch) * r_pad + h_ra), a_vb = smem_u32(tmp + size_t(sh + h_ch) * r_pad + h_rb);
+            uint32_t a_w = smem_u32(hw_s), a_n = smem_u32(hinfo_s);
+            const uint32_t cstep4 = C * r_pad * 4, pstep4 = 2 * cstep4;
+            uint32_t left = n_pairs - 1;  // pairs after the one the addresses point to
+            auto load = [&](PairRegs &P) {
+                P.va = make_float2(lds_f32(a_va), lds_f32(a_vb));
+                P.vb = make_float2(lds_f32(a_va + cstep4), lds_f32(a_vb + cstep4));
+                P.w0 = lds_f32x4(a_w); P.w1 = lds_f32x4(a_w + 16); P.w2 = lds_f32x4(a_w + 32); P.w3 = lds_f32x4(a_w + 48);
+                P.cnt = lds_u32(a_n);
+                const uint32_t go = left ? 1u : 0u;
+                left -= go;
+                a_va += go * pstep4; a_vb += go * pstep4; a_w += go * 64; a_n += go * 4;
             };
             auto compute = [&](const PairRegs &P) {
                 const float wa[S] = {P.w0.x, P.w0.y, P.w0.z, P.w0.w, P.w1.x, P.w1.y, P.w1.z, P.w1.w};
@@ -322,6 +357,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 for (int j = 0; j < S; j++) ffma2(hacc[j], P.va, wa[j]);
 #pragma unroll
                 for (int j = 0; j < S; j++) ffma2(hacc[j], P.vb, wb[j]);
+#pragma unroll 1
                 for (uint32_t n = 0; n < ((dbg & 2) ? 0u : P.cnt); n++) {  // uniform over the CTA: write out slot 0, shift the rest down
                     const uint32_t ua = round_u8(hacc[0].x), ub = round_u8(hacc[0].y);
 #pragma unroll
@@ -362,11 +398,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 }
             };
             PairRegs A, B;
-            load(A, 0);
+            load(A);
             for (uint32_t p = 0; p < n_pairs; p += 2) {
-                load(B, p + 1);
+                load(B);
                 compute(A);
-                load(A, p + 2);
+                load(A);
                 if (p + 1 < n_pairs) compute(B);
             }
         }

@@ -50,6 +50,12 @@ def process_image(dev: Device, img: np.ndarray, params: Query) -> np.ndarray:
     return _run(dev, [make_job(img, params)])[0]
 
 
+def process_images(dev: Device, imgs, params: Query):
+    """Several decoded images with the same request in one ragged launch (what the batcher
+    does with concurrent requests); same-shaped images share CTA pairs on the device."""
+    return _run(dev, [make_job(im, params) for im in imgs])
+
+
 def process_gif_frames(dev: Device, frames, params: Query):
     """All composited RGBA8 frames of a GIF in one ragged launch; RGBA8 frames out."""
     return _run(dev, [make_job(f, params, gif=True) for f in frames])

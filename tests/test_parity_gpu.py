@@ -204,6 +204,24 @@ def test_resample_paths_agree(fanlin, dev, dev_cuda_cores, dev_exact, seed, h, w
         assert hh[1] <= 0.002 * want.size, (name, hh)  # off-by-one only where the f32 sum sits on a rounding boundary
 
 
+# ---- same-shaped images in one launch --------------------------------------------------------
+
+@pytest.mark.parametrize("h,w,c,qs", [(1080, 1920, 3, "w=300&h=200&rgb=32,32,32"), (600, 800, 3, "w=200&h=200&crop=true"),
+                                      (512, 768, 1, "w=100&h=100&rgb=1,2,3"), (480, 640, 4, "w=160&h=90&rgb=9,9,9")])
+def test_batch_matches_single_requests(fanlin, dev, h, w, c, qs):
+    """Images of one launch share the geometry tables (same shape) or not (the odd one): each
+    result equals the one the image gets when it is processed alone, and the oracle's within 1 LSB."""
+    q = fanlin.Query(qs)
+    kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+    kw["w"], kw["h"] = q.dimensions()
+    imgs = [synth_image(700 + i, h, w, c) for i in range(5)] + [synth_image(800, h // 2, w // 2, c)]
+    together = fanlin.process_images(dev, imgs, q)
+    for im, a in zip(imgs, together):
+        assert np.array_equal(a, fanlin.process_image(dev, im, q))
+        hh = hist(a, O.process(im, **kw))
+        assert hh[">=2"] == 0 and hh[1] <= 0.002 * a.size, hh
+
+
 # ---- request batcher ------------------------------------------------------------------------
 
 def test_concurrent_requests_are_merged_and_isolated(fanlin):
