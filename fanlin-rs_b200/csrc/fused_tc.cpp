@@ -16,7 +16,7 @@ struct TcBand {
 };
 struct TcGeom {
     bool ok = false;
-    uint32_t px0 = 0, n_px = 0, hw_off = 0, hinfo_off = 0, cpre_off = 0, out_stride = 1;
+    uint32_t b0 = 0, n_chunks = 0, chunk_off = 0, hw_off = 0, hinfo_off = 0, cpre_off = 0, out_stride = 1;
     float scale = 1.f;
     std::vector<TcBand> bands;
 };
@@ -32,25 +32,30 @@ uint32_t r_pad_for(uint32_t rows, uint32_t c) {
 }
 
 // Horizontal scatter table of the tensor-core kernel, one record per PAIR of source pixels
-// (x0 = px0 + 2p, x0 + 1): w[p][0..8) / w[p][8..16) are the weights of the two pixels for
-// the outputs base(p) + j, j < 8, where base(p) is the first output whose window has not ended
-// before x0; cnt[p] = outputs whose window ends inside the pair.  The kernel keeps the 8
-// accumulators as a shift register: after the pair it writes out and shifts cnt[p] times, so
-// slot j always means "j-th unfinished output" and no slot index is ever computed.
-bool tc_pair_table(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t px0, uint32_t n_px, float *w, uint32_t *cnt) {
-    const uint32_t n_pairs = (n_px + 1) / 2, o_end = o0 + n;
+// (x0, x0 + 1; the second is absent in a chunk's odd last pair): w[p][0..8) / w[p][8..16) are
+// the weights of the two pixels for the outputs base(p) + j, j < 8, where base(p) is the
+// first output whose window has not ended before x0; cnt[p] = outputs whose window ends inside
+// the pair.  The kernel keeps the 8 accumulators as a shift register: after the pair it writes
+// out and shifts cnt[p] times, so slot j always means "j-th unfinished output" and no slot
+// index is ever computed.
+struct PxPair {
+    uint32_t x0;
+    bool two;
+};
+bool tc_pair_table(const AxisTable &t, uint32_t o0, uint32_t n, const std::vector<PxPair> &pairs, float *w, uint32_t *cnt) {
+    const uint32_t o_end = o0 + n;
     uint32_t base = o0;
-    for (uint32_t p = 0; p < n_pairs; p++) {
-        const uint32_t x0 = px0 + 2 * p, x1 = x0 + 1;
-        for (uint32_t o = base; o < o_end && t.entries[o].left <= x1; o++) {
+    for (size_t p = 0; p < pairs.size(); p++) {
+        const uint32_t x0 = pairs[p].x0, x1 = x0 + 1, x_last = pairs[p].two ? x1 : x0;
+        for (uint32_t o = base; o < o_end && t.entries[o].left <= x_last; o++) {
             const TapEntry &e = t.entries[o];
             const uint32_t j = o - base;
             if (j >= FUSED_SLOTS) return false;  // more than 8 unfinished outputs
-            if (x0 >= e.left && x0 < e.left + e.count) w[size_t(p) * 16 + j] = t.weights[e.woff + (x0 - e.left)];
-            if (x1 >= e.left && x1 < e.left + e.count) w[size_t(p) * 16 + 8 + j] = t.weights[e.woff + (x1 - e.left)];
+            if (x0 >= e.left && x0 < e.left + e.count) w[p * 16 + j] = t.weights[e.woff + (x0 - e.left)];
+            if (pairs[p].two && x1 >= e.left && x1 < e.left + e.count) w[p * 16 + 8 + j] = t.weights[e.woff + (x1 - e.left)];
         }
         uint32_t c = 0;
-        while (base < o_end && t.entries[base].left + t.entries[base].count <= x0 + 2) { base++; c++; }
+        while (base < o_end && t.entries[base].left + t.entries[base].count <= x_last + 1) { base++; c++; }
         cnt[p] = c;
     }
     return base == o_end;  // every output was finished, in order
@@ -58,17 +63,19 @@ bool tc_pair_table(const AxisTable &t, uint32_t o0, uint32_t n, uint32_t px0, ui
 
 }  // namespace
 
-// chunk bytes + the <= 15 bytes of alignment padding in front of them fit the 128-byte tile row
-uint32_t fused_tc_chunk_px(uint32_t c) { return c == 1 ? 112u : c == 2 ? 60u : c == 3 ? 38u : 32u; }
+// A chunk is 128 source bytes per row; with the <= c - 1 bytes carried over from the chunk before
+// it holds at most (128 + c - 1) / c whole pixels.
+uint32_t fused_tc_max_pairs(uint32_t c) { return ((TC_M + c - 1) / c + 1) / 2; }
 
-static const size_t TC_SMEM_LIMIT = 232448 - 3072 - 256;  // the kernel also has 3 KB of static shared memory
+// dynamic shared memory the kernel may ask for: the opt-in maximum minus its static shared memory
+#define TC_SMEM_LIMIT fused_tc_smem_limit()
 
 size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max, uint32_t out_stride, uint32_t n_a) {
-    const size_t tmp = size_t(TC_M) * r_pad_for(band_rows, c) * 4;
+    const size_t tmp = ((size_t(TC_M + c - 1) * r_pad_for(band_rows, c) + 3) & ~size_t(3)) * 4;  // + the columns carried over from the previous chunk
     const size_t a = size_t(n_a) * kg_max * TC_M, b = 2 * size_t(TC_N) * kg_max;       // source slots, two weight-tile slots
-    const size_t ht = 2 * ((size_t(fused_tc_chunk_px(c)) * 36 + 15) & ~size_t(15));  // two copies of the chunk's horizontal table slice
+    const size_t ht = 2 * ((size_t(fused_tc_max_pairs(c)) * 68 + 15) & ~size_t(15));  // two copies of the chunk's horizontal table slice
     const size_t out = size_t(band_rows) * out_stride * 4;                            // output pixels finished in the chunk
-    return tmp + a + b + ht + out + 1024 + 128;  // + slack to align the slots to 1024 bytes
+    return tmp + a + b + ht + out + 1024;  // + slack to align the slots to 1024 bytes
 }
 
 // Source slots take the shared memory the band leaves: the more groups are in flight, the
@@ -112,31 +119,57 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
     auto it = cache->geoms.find(key);
     if (it != cache->geoms.end()) return it->second;
     TcGeom g;
-    // horizontal: pair table with true-scale weights (the tile holds true-scale f32)
-    g.px0 = s.sx0 / 4 * 4;
-    g.n_px = s.sx0 + s.n_sx - g.px0;
+    // horizontal: the row is cut into chunks of 128 bytes starting at the 16-byte aligned b0 (the TMA
+    // coordinate).  A pixel that straddles a chunk boundary waits: its leading bytes are carried to
+    // the front of the next chunk's tile.  Per chunk {first pair, pairs | odd << 16, carried columns,
+    // tile column of its first pixel}; per pair the weights (true scale: the tile holds true-scale f32).
+    bool ok = true;
+    const uint32_t C = s.c, xa = s.sx0, xe = s.sx0 + s.n_sx;
+    g.b0 = (xa * C) & ~15u;
+    g.n_chunks = (xe * C - g.b0 + TC_M - 1) / TC_M;
+    std::vector<PxPair> pairs;
+    std::vector<uint32_t> recs;
+    {
+        uint32_t x = xa, carry = 0;
+        for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+            const uint32_t tile_byte0 = g.b0 + TC_M * ch - carry, end_byte = g.b0 + TC_M * (ch + 1);
+            uint32_t npx = 0;
+            while (x + npx < xe && (x + npx + 1) * C <= end_byte) npx++;
+            recs.push_back(uint32_t(pairs.size()));
+            recs.push_back(((npx + 1) / 2) | (npx & 1) << 16);
+            recs.push_back(carry);
+            recs.push_back(x * C - tile_byte0);
+            for (uint32_t q = 0; q < npx; q += 2) pairs.push_back(PxPair{x + q, q + 1 < npx});
+            x += npx;
+            carry = x < xe ? end_byte - x * C : 0;
+            if (carry >= C) ok = false;  // cannot happen: the pixel would have been whole
+        }
+        if (x != xe) ok = false;
+    }
     tabs->w.resize((tabs->w.size() + 3) & ~size_t(3), 0.0f);  // the kernel stages the table with 16-byte copies
     g.hw_off = uint32_t(tabs->w.size());
     g.hinfo_off = uint32_t(tabs->info.size());
-    const uint32_t n_pairs = (g.n_px + 1) / 2;
+    const uint32_t n_pairs = uint32_t(pairs.size());
     tabs->w.resize(tabs->w.size() + size_t(n_pairs) * 16, 0.0f);
     tabs->info.resize(tabs->info.size() + n_pairs, 0u);
-    bool ok = tc_pair_table(*s.htab, s.ox0, s.n_cols, g.px0, g.n_px, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
+    ok = ok && tc_pair_table(*s.htab, s.ox0, s.n_cols, pairs, &tabs->w[g.hw_off], &tabs->info[g.hinfo_off]);
+    g.chunk_off = uint32_t(tabs->info.size());
+    tabs->info.insert(tabs->info.end(), recs.begin(), recs.end());
     // outputs finished before each chunk; the widest chunk sizes the output staging buffer
     {
-        const uint32_t chunk_pairs = fused_tc_chunk_px(s.c) / 2, n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
         g.cpre_off = uint32_t(tabs->info.size());
-        tabs->info.resize(tabs->info.size() + n_chunks + 1, 0u);
+        tabs->info.resize(tabs->info.size() + g.n_chunks + 1, 0u);
         uint32_t acc = 0, widest = 0;
-        for (uint32_t ch = 0; ch < n_chunks; ch++) {
+        for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
             tabs->info[g.cpre_off + ch] = acc;
             uint32_t here = 0;
-            for (uint32_t p = ch * chunk_pairs; p < std::min(n_pairs, (ch + 1) * chunk_pairs); p++) here += tabs->info[g.hinfo_off + p];
+            const uint32_t p0 = recs[4 * ch], np = recs[4 * ch + 1] & 0xffffu;
+            for (uint32_t p = p0; p < p0 + np; p++) here += tabs->info[g.hinfo_off + p];
             acc += here;
             widest = std::max(widest, here);
         }
-        tabs->info[g.cpre_off + n_chunks] = acc;
-        g.out_stride = ((widest * s.c_out + 6) / 4 + 1) | 1u;  // + 3 bytes of alignment phase; odd: rows hit distinct banks
+        tabs->info[g.cpre_off + g.n_chunks] = acc;
+        g.out_stride = (widest * s.c_out + 6) / 4;  // ceil((3 bytes of alignment phase + pixels) / 4) words
     }
     // vertical: q = round(w * 2^sh) split into three signed base-128 digits
     float maxw = 0.f;
@@ -224,13 +257,12 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
     (void)job;
     const TcGeom &g = geom_of(s, cache, tabs, tct);
     if (!g.ok) return FANLIN_EINVAL;
-    const uint32_t chunk_px = fused_tc_chunk_px(s.c);
     for (size_t b = 0; b < g.bands.size(); b++) {
         const TcBand &bt = g.bands[b];
         FusedTcItem f{};
         f.src = src; f.dst = dst; f.src_pitch = src_pitch; f.src_h = s.in_h;
         f.c = s.c;
-        f.px0 = g.px0; f.n_px = g.n_px; f.chunk_px = chunk_px; f.n_chunks = (g.n_px + chunk_px - 1) / chunk_px;
+        f.b0 = g.b0; f.n_chunks = g.n_chunks; f.chunk_off = g.chunk_off; f.max_pairs = fused_tc_max_pairs(s.c);
         f.band_r0 = bt.r0; f.band_rows = bt.rows; f.r_pad = r_pad_for(bt.rows, s.c);
         f.grp_off = bt.grp_off; f.n_groups = bt.n_groups; f.kg_max = bt.kg_max; f.grp_rows = bt.grp_rows;
         f.scale = g.scale;

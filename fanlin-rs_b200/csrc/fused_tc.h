@@ -33,14 +33,14 @@ struct FusedTcItem {
     uint8_t *dst;
     uint32_t src_pitch, src_h;
     uint32_t c;
-    uint32_t px0, n_px, chunk_px, n_chunks;
+    uint32_t b0, n_chunks, chunk_off, max_pairs;  // first source byte (16-byte aligned); 128-byte chunks; u32 offset of their records
     uint32_t band_r0, band_rows, r_pad;   // r_pad: floats per tile column (see r_pad_for)
     uint32_t grp_rows;                    // output rows per group (<= 32), chosen to minimise MMAs per row
     uint32_t grp_off, n_groups, kg_max;   // grp_off: u32 offset of {k0, kg, b_off, rows} x n_groups
     float scale;                          // 2^-s
     uint32_t hw_off, hinfo_off;           // horizontal pair table (unscaled weights), outputs finished per pair
     uint32_t cpre_off;                    // u32 offset of the per-chunk prefix of finished outputs (n_chunks + 1)
-    uint32_t out_stride;                  // words per row of the shared-memory output staging buffer (odd)
+    uint32_t out_stride;                  // words per row of the shared-memory output staging buffer
     uint32_t n_a;                         // shared-memory slots for a group's source rows (2..4): as many as fit
     uint32_t n_cols;
     uint32_t dst_pitch, c_out, canvas_w, canvas_h, dst_x, dst_y, epi, fill;
@@ -59,7 +59,8 @@ bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *
 int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
                    FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs, std::vector<FusedTcItem> *items);
 
-uint32_t fused_tc_chunk_px(uint32_t c);
+uint32_t fused_tc_max_pairs(uint32_t c);
+size_t fused_tc_smem_limit();  // kernels_fused_tc.cu: opt-in shared memory per block minus the kernel's static part
 size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max, uint32_t out_stride, uint32_t n_a);
 uint32_t fused_tc_source_slots(uint32_t c, uint32_t band_rows, uint32_t kg_max, uint32_t out_stride);
 uint32_t fused_tc_max_band(uint32_t c, uint32_t out_stride);

@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const uint32_t n_a = it.n_a;
     uint8_t *sA = smem;                                                // n_a x [kg_max rows][128 B], 128-byte swizzle (1024-aligned)
     uint8_t *sB = sA + size_t(n_a) * kg_max * TC_M;                    // NB x [96][kg_max], core-matrix layout
-    float *tmp = reinterpret_cast<float *>(sB + NB * size_t(TC_N) * kg_max);  // [128][r_pad]
-    float *hw_s0 = tmp + size_t(TC_M) * r_pad;                         // 2 x ([chunk_px / 2][16] weights + [chunk_px / 2] counts)
-    const uint32_t chunk_px = it.chunk_px, n_px = it.n_px, n_chunks = it.n_chunks, n_groups = it.n_groups;
-    const uint32_t htab_words = (chunk_px * (S + 1) + 3) & ~3u;  // each copy stays 16-byte aligned
+    float *tmp = reinterpret_cast<float *>(sB + NB * size_t(TC_N) * kg_max);  // [128 + C - 1 columns][r_pad]
+    float *hw_s0 = tmp + ((size_t(TC_M + C - 1) * r_pad + 3) & ~size_t(3));  // 2 x ([max_pairs][16] weights + [max_pairs] counts), 16-byte aligned
+    const uint32_t max_pairs = it.max_pairs, n_chunks = it.n_chunks, n_groups = it.n_groups;
+    const uint32_t htab_words = (max_pairs * (2 * S + 1) + 3) & ~3u;  // each copy stays 16-byte aligned
+    const uint32_t *crec = tinfo + it.chunk_off;  // per chunk {first pair, pairs | odd << 16, carried columns, tile column of its first pixel}
     // pixels finished during a chunk wait here, [band row][out_stride words], and leave as whole
     // words per row segment after the chunk (scattered 1-byte stores cost one LSU slot per row)
     uint32_t *out_s = reinterpret_cast<uint32_t *>(hw_s0 + 2 * htab_words);
@@ -184,7 +185,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const uint32_t *cpre = tinfo + it.cpre_off;
     const uint32_t h_epi = it.epi, h_fill = it.fill;
 
-    auto chunk_seg0 = [&](uint32_t chunk) { return ((it.px0 + chunk * chunk_px) * C) >> 4; };
     // Groups are numbered flat across chunks (gg = chunk * n_groups + g): source slot gg % n_a,
     // weight-tile slot gg % NB, TMEM region gg % NR.
     const uint32_t total = n_chunks * n_groups;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M) : "memory");
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                                  sA_u + slot * kg_max * TC_M),
-                             "l"(tmap), "r"(bar), "r"(chunk_seg0(chunk) * 16), "r"(grp[4 * g])
+                             "l"(tmap), "r"(bar), "r"(it.b0 + TC_M * chunk), "r"(grp[4 * g])
                              : "memory");
                 if (++slot == n_a) slot = 0;
                 if (++g == n_groups) { g = 0; chunk++; }
@@ -254,22 +254,19 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     } else {
     // ================= consumer warps =================
     auto stage_htab = [&](uint32_t chunk) {  // the chunk's slice of the horizontal table -> its shared-memory copy
-        const uint32_t cpx0 = chunk * chunk_px, npx = min(chunk_px, n_px - cpx0);
+        const uint32_t pair0 = __ldg(crec + 4 * chunk), npairs = __ldg(crec + 4 * chunk + 1) & 0xffffu;
         float *dstw = hw_s0 + (chunk & 1) * htab_words;
-        const uint32_t sa_w = smem_u32(dstw), sa_i = smem_u32(dstw + size_t(chunk_px) * S);
-        const uint32_t *gw = reinterpret_cast<const uint32_t *>(hw + size_t(cpx0) * S);
-        const uint32_t npairs = (npx + 1) / 2;  // cpx0 and chunk_px are even
+        const uint32_t sa_w = smem_u32(dstw), sa_i = smem_u32(dstw + size_t(max_pairs) * 2 * S);
+        const uint32_t *gw = reinterpret_cast<const uint32_t *>(hw + size_t(pair0) * 2 * S);
         for (uint32_t k = tid; k < npairs * 4; k += NT) cp_async16(sa_w + 16 * k, gw + 4 * k);
-        for (uint32_t k = tid; k < npairs; k += NT) cp_async4(sa_i + 4 * k, hinfo + cpx0 / 2 + k, true);
+        for (uint32_t k = tid; k < npairs; k += NT) cp_async4(sa_i + 4 * k, hinfo + pair0 + k, true);
         cp_async_commit();
     };
     stage_htab(0);
 
     uint32_t gg = 0;
     for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
-        const uint32_t cpx0 = chunk * chunk_px;
-        const uint32_t npx = min(chunk_px, n_px - cpx0);
-        const uint32_t sh = ((it.px0 + cpx0) * C) & 15u;  // padding columns in front of the chunk
+        const uint32_t rec_pairs = __ldg(crec + 4 * chunk + 1), carry = __ldg(crec + 4 * chunk + 2), hstart = __ldg(crec + 4 * chunk + 3);
         const uint32_t o_first = __ldg(cpre + chunk), o_count = __ldg(cpre + chunk + 1) - o_first;  // output pixels finished by this chunk
         // ================= vertical stage: drain the tensor-core results =================
         for (uint32_t g = 0; g < n_groups; g++, gg++) {
@@ -289,7 +286,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[region])) : "memory");
                 const uint32_t jn = grp[4 * g + 3];  // output rows in this group
-                float *t = tmp + size_t(m) * r_pad + g * grp_rows + half * 16;
+                float *t = tmp + size_t(m + carry) * r_pad + g * grp_rows + half * 16;  // behind the columns carried over
                 const uint32_t nv = jn > half * 16 ? jn - half * 16 : 0;  // rows of this half that exist
                 float2 v2[8];
 #pragma unroll
@@ -320,8 +317,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         // ================= horizontal stage: CUDA cores =================
         if (h_warp && !(dbg & 1)) {
             const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
-            const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(chunk_px) * S);
-            const uint32_t n_pairs = (npx + 1) / 2;
+            const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(max_pairs) * 2 * S);
+            const uint32_t n_pairs = rec_pairs & 0xffffu;
+            const bool odd = rec_pairs >> 16;  // the last pair has no second pixel: its weights are zero, its address the first pixel's
             // staging byte addresses of this lane's channel in rows ra / rb: the row segment keeps the
             // alignment phase of its canvas address so that staged words are canvas words
             uint32_t sa = out_u + (h_ra * out_stride) * 4 + ((h_pha + o_first * h_cout) & 3u) + h_ch;
@@ -337,13 +335,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             // running shared-memory byte addresses of the next pair to load: rows ra / rb of the pair's
             // first pixel (the second is cstep4 further), its 16 weights and its count; they stop
             // advancing at the last pair, so the look-ahead loads never leave the chunk
-            uint32_t a_va = smem_u32(tmp + size_t(sh + h_ch) * r_pad + h_ra), a_vb = smem_u32(tmp + size_t(sh + h_ch) * r_pad + h_rb);
+            uint32_t a_va = smem_u32(tmp + size_t(hstart + h_ch) * r_pad + h_ra), a_vb = smem_u32(tmp + size_t(hstart + h_ch) * r_pad + h_rb);
             uint32_t a_w = smem_u32(hw_s), a_n = smem_u32(hinfo_s);
             const uint32_t cstep4 = C * r_pad * 4, pstep4 = 2 * cstep4;
             uint32_t left = n_pairs - 1;  // pairs after the one the addresses point to
             auto load = [&](PairRegs &P) {
+                const uint32_t second = (odd && left == 0) ? 0u : cstep4;
                 P.va = make_float2(lds_f32(a_va), lds_f32(a_vb));
-                P.vb = make_float2(lds_f32(a_va + cstep4), lds_f32(a_vb + cstep4));
+                P.vb = make_float2(lds_f32(a_va + second), lds_f32(a_vb + second));
                 P.w0 = lds_f32x4(a_w); P.w1 = lds_f32x4(a_w + 16); P.w2 = lds_f32x4(a_w + 32); P.w3 = lds_f32x4(a_w + 48);
                 P.cnt = lds_u32(a_n);
                 const uint32_t go = left ? 1u : 0u;
@@ -407,6 +406,15 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the tile may be overwritten; the staged pixels are complete
+        // a pixel cut by the chunk boundary: its leading columns move to the front of the tile
+        if (chunk + 1 < n_chunks) {
+            const uint32_t cn = __ldg(crec + 4 * (chunk + 1) + 2);
+            if (cn) {
+                const float *from = tmp + size_t(carry + TC_M - cn) * r_pad;
+                for (uint32_t k = tid; k < cn * r_pad; k += NT) tmp[k] = from[k];
+                asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // before the next drain overwrites the source columns
+            }
+        }
         // ================= write out the pixels finished in this chunk =================
         if (const uint32_t nb = o_count * h_cout) {
             for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8) {  // 8 lanes per row segment
@@ -460,10 +468,32 @@ int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_
 
 }  // namespace fanlin
 
-// ---- host: tensor maps ---------------------------------------------------------------------
+// ---- host: shared-memory budget, tensor maps ---------------------------------------------------------------------
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+
 namespace fanlin {
+
+size_t fused_tc_smem_limit() {
+    static size_t limit = 0;
+    if (!limit) {
+        size_t stat = 0;
+        const void *kerns[4] = {reinterpret_cast<const void *>(fused_resample_tc_kernel<1>), reinterpret_cast<const void *>(fused_resample_tc_kernel<2>),
+                                reinterpret_cast<const void *>(fused_resample_tc_kernel<3>), reinterpret_cast<const void *>(fused_resample_tc_kernel<4>)};
+        bool ok = true;
+        for (const void *k : kerns) {
+            cudaFuncAttributes fa{};
+            ok = ok && cudaFuncGetAttributes(&fa, k) == cudaSuccess;
+            stat = std::max(stat, fa.sharedSizeBytes);
+        }
+        int dev = 0, optin = 0;
+        ok = ok && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); return 232448 - 4096; }  // no device (host-only tests): a conservative figure
+        limit = size_t(optin) - stat;
+    }
+    return limit;
+}
 
 bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t rows, uint32_t box_rows) {
     static PFN_cuTensorMapEncodeTiled enc = nullptr;
