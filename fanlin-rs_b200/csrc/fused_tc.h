@@ -1,6 +1,6 @@
 // Fused separable resample, tensor-core vertical stage (sm_100a tcgen05 kind::i8).
 //
-// Same decomposition as fused.h (one CTA per image band, sweep of column chunks,
+// Same decomposition as fused.h (one CTA per image band, sweep of 128-byte column chunks,
 // f32 tile in shared memory, scatter horizontal stage on the CUDA cores), but the
 // vertical pass -- 6 FMA per source byte at Lanczos3, which no CUDA-core schedule
 // gets under the HBM time on B200 -- runs as a banded integer
@@ -9,8 +9,8 @@
 //   D[128 columns x 96] (s32, TMEM) += A[128 columns x 32 rows] (u8) * B[32 rows x 96] (s8)
 //
 // A is the source tile exactly as it lies in the image (rows = K, bytes of a row =
-// M, "MN-major"), staged by cp.async into the no-swizzle core-matrix layout; no byte
-// is converted or shuffled by a thread.  B holds, for a group of 32 output rows, the
+// M, "MN-major"), fetched by TMA with the 128-byte swizzle; no byte is converted or
+// shuffled by a thread.  B holds, for a group of 32 output rows, the
 // filter weights as three signed base-128 digits of round(w * 2^s) (columns 0-31 hi,
 // 32-63 mid, 64-95 lo); the epilogue recombines the three s32 sums exactly.  Integer
 // arithmetic is exact; the only deviation from the f32 recipe is the 2^-s weight

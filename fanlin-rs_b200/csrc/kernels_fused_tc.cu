@@ -1,29 +1,31 @@
 // Fused separable Lanczos3 resample with the vertical pass on the sm_100a tensor
 // cores (tcgen05.mma kind::i8, accumulators in TMEM).  See fused_tc.h.
 //
-// Per CTA (1 CTA / SM): 8 consumer warps + an MMA-issuing warp + two TMA-issuing warps; one band of <= 192 output rows
-// of one image, swept left to right in chunks of 128 source bytes per row.  Per chunk, per
-// group of 32 output rows:
-//   * the TMA thread fetches the group's source rows with a single TMA tensor copy
+// Per CTA (1 CTA / SM): 8 consumer warps, an MMA-issuing warp and two TMA-issuing warps; one
+// band of <= 192 output rows of one image, swept left to right in chunks of 128 source bytes
+// per row (a pixel cut by a chunk boundary waits: its leading bytes are carried to the front of
+// the next chunk's tile).  Per chunk, per group of <= 32 output rows:
+//   * the source TMA thread fetches the group's source rows with one tensor copy
 //     (cp.async.bulk.tensor.2d; tensor map {row bytes, rows}, box {128 B, kg rows}, 128-byte
-//     swizzle) -- the box lands as [row][128 B] with the hardware swizzle, which is the
-//     MN-major SWIZZLE_128B operand layout the tensor core reads directly (measured:
-//     profiles/microbench/umma_i8_tma128.cu); rows / columns past the image are zero-filled
-//     -- and the s8 weight-digit tile with one cp.async.bulk (two shared-memory slots);
+//     swizzle) into one of 2-4 slots -- the box lands as [row][128 B] with the hardware
+//     swizzle, which is the MN-major SWIZZLE_128B operand layout the tensor core reads
+//     directly (measured: profiles/microbench/umma_i8_tma128.cu); rows / columns past the
+//     image are zero-filled -- and the weight TMA thread the s8 digit tile with one
+//     cp.async.bulk into one of two slots;
 //   * the MMA thread issues kg/32 tcgen05.mma (M = 128 bytes of the row, N = 96 = 3
 //     digits x 32 output rows, K = 32 source rows) into one of FIVE accumulator regions of
-//     TMEM and commits to an mbarrier.  It runs ahead of the consumers as far as TMEM
-//     allows: while they execute the horizontal stage of chunk c, the tensor core already
-//     computes (almost all of) the vertical pass of chunk c + 1 -- TMEM is the double buffer;
+//     TMEM and commits to an mbarrier, which also frees the operand slots.  It runs ahead of
+//     the consumers as far as TMEM allows: while they execute the horizontal stage of chunk
+//     c, the tensor core computes the vertical pass of chunk c + 1 -- TMEM is the double buffer;
 //   * the consumers drain a region (tcgen05.ld 32x32b), recombine the three s32 digit sums
 //     into the f32 value of the crate's vertical pass, store it to the tile
 //     tmp[element][row] and hand the region back;
-// then the consumers run the horizontal stage on the CUDA cores: the scatter of
-// kernels_fused.cu (<= 8 live output pixels per row), with one lane per (pair of output rows,
-// channel) so that every consumer warp takes part, f32x2 FMAs over the row pair, and a warp
-// shuffle that gathers a finished pixel's channels for the epilogue.
+// then the consumers run the horizontal stage on the CUDA cores: a scatter into the <= 8
+// unfinished output pixels of a row, one thread per (pair of output rows, channel), f32x2
+// FMAs over the row pair, weights per pixel pair from a table staged in shared memory, the
+// accumulators a shift register that is written out whenever a pixel's window ends.  Finished
+// pixels are staged in shared memory and leave as whole words per row after the chunk.
 #include <cuda.h>
-#include <cstdlib>
 
 #include "fused_device.cuh"
 #include "fused_tc.h"
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                                                                   const CUtensorMap *__restrict__ tmaps,
                                                                   const uint8_t *__restrict__ tb,
                                                                   const float *__restrict__ tw,
-                                                                  const uint32_t *__restrict__ tinfo, uint32_t dbg) {
+                                                                  const uint32_t *__restrict__ tinfo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // swizzle atoms need 1024-byte alignment
     __shared__ FusedTcItem it_s;
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const bool h_has_b = h_lane && h_slot + h_half < it.band_rows;
     const uint32_t h_pha = uint32_t(reinterpret_cast<uintptr_t>(h_row0 + size_t(h_ra) * it.dst_pitch));  // low bits: alignment phase
     const uint32_t h_phb = uint32_t(reinterpret_cast<uintptr_t>(h_row0 + size_t(h_rb) * it.dst_pitch));
+    const bool h_words = h_cout == 4 && ((reinterpret_cast<uintptr_t>(h_row0) | h_pitch) & 3) == 0;
     const uint32_t out_u = smem_u32(out_s);
     const uint32_t *cpre = tinfo + it.cpre_off;
     const uint32_t h_epi = it.epi, h_fill = it.fill;
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
         cp_async_wait<1>();  // this chunk's table slice (committed one chunk ago) has landed
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // consumers only: the tile is complete
         // ================= horizontal stage: CUDA cores =================
-        if (h_warp && !(dbg & 1)) {
+        if (h_warp) {
             const float *hw_s = hw_s0 + (chunk & 1) * htab_words;
             const uint32_t *hinfo_s = reinterpret_cast<const uint32_t *>(hw_s + size_t(max_pairs) * 2 * S);
             const uint32_t n_pairs = rec_pairs & 0xffffu;
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
 #pragma unroll
                 for (int j = 0; j < S; j++) ffma2(hacc[j], P.vb, wb[j]);
 #pragma unroll 1
-                for (uint32_t n = 0; n < ((dbg & 2) ? 0u : P.cnt); n++) {  // uniform over the CTA: write out slot 0, shift the rest down
+                for (uint32_t n = 0; n < P.cnt; n++) {  // uniform over the CTA: write out slot 0, shift the rest down
                     const uint32_t ua = round_u8(hacc[0].x), ub = round_u8(hacc[0].y);
 #pragma unroll
                     for (int j = 0; j + 1 < S; j++) hacc[j] = hacc[j + 1];
@@ -416,7 +419,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
             }
         }
         // ================= write out the pixels finished in this chunk =================
-        if (const uint32_t nb = o_count * h_cout) {
+        if (const uint32_t nb = o_count * h_cout; nb && h_words) {
+            // RGBA rows at aligned addresses: every staged word is a whole canvas word
+            uint32_t *gq = reinterpret_cast<uint32_t *>(h_row0) + o_first + (tid >> 3) * (h_pitch >> 2) + (tid & 7);
+            const uint32_t *sq = out_s + (tid >> 3) * out_stride + (tid & 7);
+            const uint32_t g_step = (NT / 8) * (h_pitch >> 2), s_step = (NT / 8) * out_stride;
+            for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8, gq += g_step, sq += s_step)
+                for (uint32_t k = tid & 7; k < o_count; k += 8) gq[k - (tid & 7)] = sq[k - (tid & 7)];
+        } else if (nb) {
             for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8) {  // 8 lanes per row segment
                 uint8_t *g0 = h_row0 + size_t(r) * h_pitch + size_t(o_first) * h_cout;
                 const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(g0)) & 3u;
@@ -448,7 +458,7 @@ void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t
     auto kern = fused_resample_tc_kernel<C>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     lc.begin("fused_resample_tc_kernel");
-    kern<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info, getenv("TC_DBG") ? atoi(getenv("TC_DBG")) : 0);
+    kern<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info);
     lc.end();
 }
 
