@@ -374,6 +374,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                             if (h_lane) { sts8(sa + 1, ua); sts8(sa + 2, ua); }
                             if (h_has_b) { sts8(sb + 1, ub); sts8(sb + 2, ub); }
                         }
+                    } else if (h_epi == EPI_PLAIN) {  // LA / RGBA out as they are: every lane stages its own channel byte
+                        if (h_lane) sts8(sa, ua);
+                        if (h_has_b) sts8(sb, ub);
                     } else {
                         // gather the pixel's channels from the C lanes of this row slot; the channel-0 lane
                         // stages row ra, the channel-1 lane row rb
@@ -384,15 +387,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                         for (int k = 0; k < C; k++) u[k] = (__shfl_sync(0xffffffffu, mine, int(lane - h_ch) + k) >> sel) & 0xffu;
                         if (h_ch == 0 ? h_lane : (h_ch == 1 && h_has_b)) {
                             const uint32_t s0 = (h_ch == 1 ? sb : sa) - h_ch;
-                            if (h_epi == EPI_PLAIN) {
+                            uint32_t px = to_rgba_packed(u, C);
+                            if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
 #pragma unroll
-                                for (int k = 0; k < C; k++) sts8(s0 + k, u[k]);
-                            } else {
-                                uint32_t px = to_rgba_packed(u, C);
-                                if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
-#pragma unroll
-                                for (int k = 0; k < 4; k++) sts8(s0 + k, px >> (8 * k));
-                            }
+                            for (int k = 0; k < 4; k++) sts8(s0 + k, px >> (8 * k));
                         }
                     }
                     sa += h_cout;

@@ -30,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0, help="scale the batch sizes")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--only", default="", help="run only the configs whose name contains this text")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -44,6 +45,8 @@ def main():
     stream = torch.cuda.Stream(device)
     out = []
     for name, h, w, c, qs, gif, batch in CONFIGS:
+        if args.only and args.only not in name:
+            continue
         n = max(1, int(batch * args.scale))
         base = [torch.from_numpy(synth_image(900 + i, h, w, c)).to(device) for i in range(4)]
         src = torch.stack([base[i % 4] for i in range(n)]).contiguous()
