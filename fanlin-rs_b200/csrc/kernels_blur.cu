@@ -10,7 +10,7 @@
 // factor after accumulating with the interior weights and zeros outside the image; that is the
 // same value up to f32 rounding (the parity tests bound the result to 1 LSB).
 #include "blur.h"
-#include "device_common.cuh"
+#include "fused_device.cuh"
 #include "kernels.h"
 
 namespace fanlin {
@@ -34,24 +34,40 @@ __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__
     float *tile = sm + taps_pad;
     const uint32_t t = threadIdx.x, warp = t >> 5, lane = t & 31;
     for (uint32_t k = t; k < taps_pad; k += VT) u_s[k] = tw[it.u_off + k];
-    // stage rows [y0 - R, y0 + V_ROWS + R + 7): one warp per row, 4 bytes per lane
+    __shared__ float corr_s[V_ROWS];  // border correction per output row of the block
+    if (t < V_ROWS) corr_s[t] = y0 + t < it.h ? tw[it.corrv_off + y0 + t] : 0.f;
+    // stage rows [y0 - R, y0 + V_ROWS + R + 7): one warp per row, 4 bytes per lane; the loads of
+    // SB rows are issued together (one row at a time is bound by the global-load latency: measured,
+    // 48 % of the kernel's samples were long-scoreboard stalls here)
     const uint32_t n_rows_tile = V_ROWS + 2 * R + 8;  // + 8: the window reads ahead inside the last (zero-weight) taps
-    for (uint32_t r = warp; r < n_rows_tile; r += VT / 32) {
-        const int y = int(y0 + r) - int(R);
-        float f[4] = {0.f, 0.f, 0.f, 0.f};
-        if (y >= 0 && y < int(it.h)) {
-            const uint8_t *row = it.src + size_t(y) * it.src_pitch;
-            const uint32_t e = e0 + 4 * lane;
-            if (it.aligned4 && e + 3 < n_e) {
-                const uint32_t wv = __ldg(reinterpret_cast<const uint32_t *>(row + e));
-                f[0] = float(wv & 0xff); f[1] = float((wv >> 8) & 0xff); f[2] = float((wv >> 16) & 0xff); f[3] = float(wv >> 24);
-            } else {
+    constexpr uint32_t SB = 8;
+    const uint32_t e4 = e0 + 4 * lane;
+    const bool vec = it.aligned4 && e4 + 3 < n_e;
+    for (uint32_t rb0 = warp; rb0 < n_rows_tile; rb0 += SB * (VT / 32)) {
+        uint32_t wv[SB];
 #pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (e + q < n_e) f[q] = float(row[e + q]);
+        for (uint32_t q = 0; q < SB; q++) {
+            const uint32_t r = rb0 + q * (VT / 32);
+            const int y = int(y0 + r) - int(R);
+            wv[q] = 0;
+            if (r < n_rows_tile && y >= 0 && y < int(it.h)) {
+                const uint8_t *row = it.src + size_t(y) * it.src_pitch;
+                if (vec) {
+                    wv[q] = __ldg(reinterpret_cast<const uint32_t *>(row + e4));
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; b++)
+                        if (e4 + b < n_e) wv[q] |= uint32_t(row[e4 + b]) << (8 * b);
+                }
             }
         }
-        *reinterpret_cast<float4 *>(tile + size_t(r) * VT + 4 * lane) = make_float4(f[0], f[1], f[2], f[3]);
+#pragma unroll
+        for (uint32_t q = 0; q < SB; q++) {
+            const uint32_t r = rb0 + q * (VT / 32);
+            if (r < n_rows_tile)
+                *reinterpret_cast<float4 *>(tile + size_t(r) * VT + 4 * lane) =
+                    make_float4(float(wv[q] & 0xff), float((wv[q] >> 8) & 0xff), float((wv[q] >> 16) & 0xff), float(wv[q] >> 24));
+        }
     }
     __syncthreads();
     const uint32_t e = e0 + t;
@@ -77,7 +93,7 @@ __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__
         if (e < n_e) {
 #pragma unroll
             for (int jj = 0; jj < 8; jj++)
-                if (j0 + jj < it.h) it.tmp[size_t(j0 + jj) * n_e + e] = acc[jj] * tw[it.corrv_off + j0 + jj];
+                if (j0 + jj < it.h) it.tmp[size_t(j0 + jj) * n_e + e] = acc[jj] * corr_s[8 * p + jj];
         }
     }
 }
@@ -99,19 +115,27 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
     uint8_t *out_s = reinterpret_cast<uint8_t *>(tile + size_t(rb) * pitch);  // [rb][H_PX * C]
     const uint32_t t = threadIdx.x;
     for (uint32_t k = t; k < taps_pad; k += HT) u_s[k] = tw[it.u_off + k];
+    __shared__ float corr_s[H_PX];  // border correction per output pixel of the block
+    if (t < H_PX) corr_s[t] = x0 + t < it.w ? tw[it.corrh_off + x0 + t] : 0.f;
     const uint32_t n_e = it.w * C;
     // stage: tile row r <- tmp[y0 + r][(x0 - R) * C ...), zeros outside the image
     const uint32_t row_elems = n_px_tile * C;
-    for (uint32_t r = t >> 5; r < rb; r += HT / 32) {  // one warp per row: coalesced, no index division
+    // one warp per row: coalesced, no index division.  cp.async (global -> shared, no register hop)
+    // keeps every load of the block in flight at once; a row-at-a-time register copy was bound by
+    // the load latency (54 % long-scoreboard samples).
+    for (uint32_t r = t >> 5; r < rb; r += HT / 32) {
         const uint32_t y = y0 + r;
         const float *src = it.tmp + size_t(y) * n_e;
         const int ge0 = int(x0 * C) - int(R * C);
-#pragma unroll 4
+        float *trow = tile + size_t(r) * pitch;
         for (uint32_t i = t & 31; i < row_elems; i += 32) {
             const int ge = ge0 + int(i);
-            tile[size_t(r) * pitch + i] = (y < it.h && ge >= 0 && ge < int(n_e)) ? __ldg(src + ge) : 0.f;
+            if (y < it.h && ge >= 0 && ge < int(n_e)) cp_async4(smem_u32(trow + i), src + ge, true);
+            else trow[i] = 0.f;
         }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     const uint32_t rows_here = min(rb, it.h - y0);
     if (t < rb * C) {
@@ -135,8 +159,7 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
             }
 #pragma unroll
             for (int jj = 0; jj < 8; jj++) {
-                const uint32_t x = x0 + 8 * p + jj;
-                const float cf = x < it.w ? tw[it.corrh_off + x] : 0.f;
+                const float cf = corr_s[8 * p + jj];
                 out_s[size_t(r) * (H_PX * C) + (8 * p + jj) * C + ch] = uint8_t(round_u8(acc[jj] * cf));
             }
         }
