@@ -3,7 +3,7 @@
 // 2*floor(2 sigma)+1 taps (41..81), windows truncated at the borders and renormalised.
 //
 // Both passes stage a tile with its halo in shared memory as f32 and slide a register window
-// along the filtered axis: per 8 taps a thread loads 8 new values and issues 64 FMAs for its 8
+// along the filtered axis: per 8 taps a thread loads 8 new values and issues 128 FMAs for its 16
 // outputs (weights broadcast from shared memory), so the kernels run near the FP32 issue rate
 // instead of one shared-memory load per FMA.  The crate's border handling -- weights divided by
 // the sum of the taps that fall inside the image -- is applied as one per-row / per-column
@@ -21,6 +21,7 @@ constexpr int VT = 128;    // vertical kernel: threads = element columns per blo
 constexpr int V_ROWS = 64; // output rows per block
 constexpr int HT = 256;    // horizontal kernel threads
 constexpr int H_PX = 32;   // output pixels per block row
+constexpr int J = 16;      // outputs per thread and window pass: J + 8 live values, 8 J FMAs per 8 loads
 
 // ---- vertical pass: src u8 [h][pitch] -> tmp f32 [h][w*c] ------------------------------------
 __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__ items, const float *__restrict__ tw) {
@@ -72,28 +73,28 @@ __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__
     __syncthreads();
     const uint32_t e = e0 + t;
     const float *col = tile + t;
-    for (uint32_t p = 0; p < V_ROWS / 8; p++) {
-        const uint32_t j0 = y0 + 8 * p;
+    for (uint32_t p = 0; p < V_ROWS / J; p++) {
+        const uint32_t j0 = y0 + J * p;
         if (j0 >= it.h) break;
-        float acc[8], x[16];
+        float acc[J], x[J + 8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) { acc[i] = 0.f; x[i] = col[size_t(8 * p + i) * VT]; }
+        for (int i = 0; i < J; i++) { acc[i] = 0.f; x[i] = col[size_t(J * p + i) * VT]; }
         for (uint32_t k0 = 0; k0 < taps_pad; k0 += 8) {
             const float4 w0 = *reinterpret_cast<const float4 *>(u_s + k0), w1 = *reinterpret_cast<const float4 *>(u_s + k0 + 4);
             const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[8 + i] = col[size_t(8 * p + k0 + 8 + i) * VT];
+            for (int i = 0; i < 8; i++) x[J + i] = col[size_t(J * p + k0 + J + i) * VT];
 #pragma unroll
             for (int kk = 0; kk < 8; kk++)
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
+                for (int jj = 0; jj < J; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
 #pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = x[8 + i];
+            for (int i = 0; i < J; i++) x[i] = x[8 + i];
         }
         if (e < n_e) {
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++)
-                if (j0 + jj < it.h) it.tmp[size_t(j0 + jj) * n_e + e] = acc[jj] * corr_s[8 * p + jj];
+            for (int jj = 0; jj < J; jj++)
+                if (j0 + jj < it.h) it.tmp[size_t(j0 + jj) * n_e + e] = acc[jj] * corr_s[J * p + jj];
         }
     }
 }
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
     pitch += (C + 32 - (pitch & 31)) & 31;
     float *u_s = sm;
     float *tile = sm + taps_pad;
-    uint8_t *out_s = reinterpret_cast<uint8_t *>(tile + size_t(rb) * pitch);  // [rb][H_PX * C]
+    uint8_t *out_s = reinterpret_cast<uint8_t *>(tile + size_t(rb) * pitch);  // [rb][H_PX * C + 4]: rows on different banks
+    const uint32_t out_pitch = H_PX * C + 4;
     const uint32_t t = threadIdx.x;
     for (uint32_t k = t; k < taps_pad; k += HT) u_s[k] = tw[it.u_off + k];
     __shared__ float corr_s[H_PX];  // border correction per output pixel of the block
@@ -141,26 +143,26 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
     if (t < rb * C) {
         const uint32_t r = t / C, ch = t - r * C;
         const float *rowp = tile + size_t(r) * pitch + ch;
-        for (uint32_t p = 0; p < H_PX / 8; p++) {
-            float acc[8], x[16];
+        for (uint32_t p = 0; p < H_PX / J; p++) {
+            float acc[J], x[J + 8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { acc[i] = 0.f; x[i] = rowp[size_t(8 * p + i) * C]; }
+            for (int i = 0; i < J; i++) { acc[i] = 0.f; x[i] = rowp[size_t(J * p + i) * C]; }
             for (uint32_t k0 = 0; k0 < taps_pad; k0 += 8) {
                 const float4 w0 = *reinterpret_cast<const float4 *>(u_s + k0), w1 = *reinterpret_cast<const float4 *>(u_s + k0 + 4);
                 const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int i = 0; i < 8; i++) x[8 + i] = rowp[size_t(8 * p + k0 + 8 + i) * C];
+                for (int i = 0; i < 8; i++) x[J + i] = rowp[size_t(J * p + k0 + J + i) * C];
 #pragma unroll
                 for (int kk = 0; kk < 8; kk++)
 #pragma unroll
-                    for (int jj = 0; jj < 8; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
+                    for (int jj = 0; jj < J; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
 #pragma unroll
-                for (int i = 0; i < 8; i++) x[i] = x[8 + i];
+                for (int i = 0; i < J; i++) x[i] = x[8 + i];
             }
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
-                const float cf = corr_s[8 * p + jj];
-                out_s[size_t(r) * (H_PX * C) + (8 * p + jj) * C + ch] = uint8_t(round_u8(acc[jj] * cf));
+            for (int jj = 0; jj < J; jj++) {
+                const float cf = corr_s[J * p + jj];
+                out_s[size_t(r) * out_pitch + (J * p + jj) * C + ch] = uint8_t(round_u8(acc[jj] * cf));
             }
         }
     }
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
     const uint32_t px_here = min(uint32_t(H_PX), it.w - x0), bytes_row = px_here * C;
     for (uint32_t r = t >> 5; r < rows_here; r += HT / 32) {  // one warp per row
         uint8_t *d = it.dst + size_t(y0 + r) * n_e + size_t(x0) * C;
-        for (uint32_t i = t & 31; i < bytes_row; i += 32) d[i] = out_s[size_t(r) * (H_PX * C) + i];
+        for (uint32_t i = t & 31; i < bytes_row; i += 32) d[i] = out_s[size_t(r) * out_pitch + i];
     }
 }
 
@@ -180,7 +182,7 @@ size_t blur_h_smem(uint32_t radius, uint32_t taps_pad, uint32_t c) {
     const uint32_t rb = HT / c;
     uint32_t pitch = (H_PX + 2 * radius + 8) * c;
     pitch += (c + 32 - (pitch & 31)) & 31;
-    return (size_t(taps_pad) + size_t(rb) * pitch) * 4 + size_t(rb) * H_PX * c + 16;
+    return (size_t(taps_pad) + size_t(rb) * pitch) * 4 + size_t(rb) * (H_PX * c + 4) + 16;
 }
 
 int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
