@@ -104,8 +104,8 @@ bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
     if (s.n_rows == 0 || s.n_cols == 0) return false;
     if (s.v_kind != KIND_LANCZOS3) return false;  // Nearest is a gather (bit-exact on the CUDA-core path); blur has its own kernel
     if (s.color_op != COLOR_NONE || s.c_mem != s.c) return false;
-    const uint32_t pitch = s.src_is_input ? (job.src_pitch ? job.src_pitch : job.src_w * job.src_channels) : s.in_w * s.c_mem;
-    if (pitch % 16 != 0) return false;  // rows are staged with 16-byte cp.async
+    const uint32_t pitch = s.src_is_input ? (job.src_pitch ? job.src_pitch : job.src_w * job.src_channels) : (s.in_pitch ? s.in_pitch : s.in_w * s.c_mem);
+    if (pitch % 16 != 0) return false;  // TMA: the row stride is a multiple of 16 bytes
     if (s.src_is_input && (reinterpret_cast<uintptr_t>(job.src) & 15)) return false;
     // a 32-row output group must fit 256 source rows, and the horizontal pass 8 live outputs
     const double ratio = double(s.in_h) / double(std::max(1u, s.v_out));

@@ -58,5 +58,7 @@ int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint3
                 uint32_t taps_pad, const float *d_w, LaunchCtx &lc);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+// Colour op alone over the needed source rows (in front of the tensor-core resample).
+int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 
 }  // namespace fanlin

@@ -36,6 +36,7 @@ struct StagePlan {
     bool present = false;
     bool separable = false;  // false: compose only (colour op / letterbox / to_rgba8 / copy)
     bool src_is_input = true;  // else reads the previous stage's canvas
+    uint32_t in_pitch = 0;     // bytes per row of that canvas when it is not tightly packed (0: in_w * c_mem)
     uint32_t in_w = 0, in_h = 0, c_mem = 0, c = 0, color_op = COLOR_NONE;
     uint32_t v_kind = 0, h_kind = 0;
     float sigma = 0.f;

@@ -198,8 +198,8 @@ extern "C" void fanlin_host_free(fanlin_ctx *ctx, void *p) {
 namespace {
 
 struct JobScratch {
-    size_t inter = 0, tmp = 0;          // bytes
-    size_t inter_off = 0, tmp_off = 0;  // offsets inside the chunk's scratch
+    size_t pre = 0, inter = 0, tmp = 0;               // bytes
+    size_t pre_off = 0, inter_off = 0, tmp_off = 0;   // offsets inside the chunk's scratch
 };
 
 void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t *inter, float *tmp,
@@ -283,6 +283,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     std::unique_ptr<FusedCache, void (*)(FusedCache *)> fcache(fused_cache_new(), fused_cache_free);
     FusedTables ftabs;
     std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
+    std::vector<StagePlan> a_pre(n_jobs);     // present: stage A as the tensor-core kernel sees it behind a colour-op pass
     std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(), fused_tc_cache_free);
     FusedTcTables tctabs;
     const bool use_tc = ctx->cfg.vertical_path == 0;
@@ -311,8 +312,25 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
         const JobPlan &p = b->plans[i];
-        if (!exact && use_tc && fused_tc_eligible(p.a, jobs[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) fused_a[i] = 2;
-        else fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
+        fused_a[i] = 0;
+        if (!exact && use_tc) {
+            if (fused_tc_eligible(p.a, jobs[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) {
+                fused_a[i] = 2;
+            } else if (p.a.present && p.a.separable && p.a.color_op != COLOR_NONE && p.a.src_is_input) {
+                // Grayscale / inverse keep the tensor-core path: the source bytes reach the tensor core
+                // straight from memory, so the colour op runs first as a pass of its own into scratch
+                // (1 + 2 c / c_mem times the source bytes instead of once, at several times the speed of
+                // the CUDA-core resample that would apply it on load).
+                StagePlan m = p.a;
+                m.color_op = COLOR_NONE; m.c_mem = m.c; m.src_is_input = false;
+                m.in_pitch = uint32_t(align_up(size_t(m.in_w) * m.c, 16));
+                if (fused_tc_eligible(m, jobs[i]) && fused_tc_geometry_ok(m, tcache.get(), &ftabs, &tctabs)) {
+                    fused_a[i] = 2;
+                    a_pre[i] = m;
+                }
+            }
+        }
+        if (!fused_a[i]) fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         fast_b[i] = !exact && blur_eligible(p.b);
         if (!fast_b[i]) { add_table(p.b.vtab); add_table(p.b.htab); }
@@ -326,18 +344,20 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         size_t cur = 0;
         for (uint32_t i = 0; i < n_jobs; i++) {
             const JobPlan &p = b->plans[i];
+            if (a_pre[i].present) js[i].pre = align_up(size_t(a_pre[i].in_pitch) * a_pre[i].in_h, 256);
             if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_w) * p.a.canvas_h * p.a.c_out, 256);
             size_t ta = 0, tb = 0;
             if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
             if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of either blur path
             js[i].tmp = align_up(std::max(ta, tb), 256);
-            const size_t need = js[i].inter + js[i].tmp;
+            const size_t need = js[i].pre + js[i].inter + js[i].tmp;
             if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
                 chunk_end.push_back(i);
                 cur = 0;
             }
-            js[i].inter_off = cur;
-            js[i].tmp_off = cur + js[i].inter;
+            js[i].pre_off = cur;
+            js[i].inter_off = cur + js[i].pre;
+            js[i].tmp_off = cur + js[i].pre + js[i].inter;
             cur += need;
             scratch_bytes = std::max(scratch_bytes, cur);
         }
@@ -361,13 +381,34 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (fused_a[i] == 1) by_variant[fused_variant(b->plans[i].a)].push_back(i);
             if (fused_a[i] == 2) tc_by_c[b->plans[i].a.c].push_back(i);
         }
+        {  // colour-op passes in front of the tensor-core resample: the needed source rows, op applied, into scratch
+            HostStep hs{5, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+            for (uint32_t i = begin; i < end; i++) {
+                if (!a_pre[i].present) continue;
+                const StagePlan &a = b->plans[i].a;
+                StageDesc d;
+                std::memset(&d, 0, sizeof(d));
+                d.src = jobs[i].src;
+                d.src_pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
+                d.src_w = a.in_w; d.src_h = a.in_h; d.c_mem = a.c_mem; d.c = a.c; d.color_op = a.color_op;
+                d.v_tab = d.h_tab = NO_TABLE;
+                d.oy0 = a.sy0; d.n_rows = a.n_sy; d.ox0 = 0; d.n_cols = a.in_w;
+                d.dst = static_cast<uint8_t *>(b->d_scratch) + js[i].pre_off + size_t(a.sy0) * a_pre[i].in_pitch;
+                d.dst_pitch = a_pre[i].in_pitch; d.c_out = a.c; d.canvas_w = a.in_w; d.canvas_h = a.n_sy; d.epi = EPI_PLAIN;
+                geom_add(&hs.g, d);
+                descs.push_back(d);
+            }
+            if (hs.g.n_jobs) hsteps.push_back(hs);
+        }
         for (auto &kv : tc_by_c) {
             HostStep hs{3, tcitems.size(), LaunchGeom{}, kv.first, 0, 0, 0};
             for (uint32_t i : kv.second) {
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
-                const uint32_t pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
-                const int rc = fused_tc_build(p.a, jobs[i], jobs[i].src, pitch, p.b.present ? inter : jobs[i].dst, tcache.get(), &ftabs,
+                const bool pre = a_pre[i].present;
+                const uint8_t *tsrc = pre ? static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off : jobs[i].src;
+                const uint32_t pitch = pre ? a_pre[i].in_pitch : jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
+                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, jobs[i], tsrc, pitch, p.b.present ? inter : jobs[i].dst, tcache.get(), &ftabs,
                                               &tctabs, &tcitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core tables"); return rc; }
             }
@@ -554,7 +595,8 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
             const int k = launch_fused(s.items, s.n_items, s.variant, s.max_band, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no fused kernel variant"); return FANLIN_EINVAL; }
             n += k;
-        } else if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
+        } else if (s.kind == 5) n += launch_color_pass(s.descs, s.geom, lc);
+        else if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
         else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, lc);
     }
     if (b->timing) b->ev_used = lc.used;
