@@ -39,6 +39,7 @@ struct StageDesc {
     uint32_t epi;
     uint32_t fill;          // r | g<<8 | b<<16 | 255<<24
     uint32_t v_max_taps, h_max_taps;
+    uint32_t orient;        // orientation pass only: EXIF orientation (2..8) of the stored image
 };
 
 }  // namespace fanlin

@@ -60,5 +60,7 @@ int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint3
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 // Colour op alone over the needed source rows (in front of the tensor-core resample).
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+// EXIF orientation (+ colour op) of the stored image into scratch, in front of every other stage.
+int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 
 }  // namespace fanlin

@@ -124,7 +124,68 @@ __global__ void __launch_bounds__(256) color_pass_kernel(const StageDesc *__rest
     }
 }
 
+// EXIF orientation (+ colour op) of the stored image: oriented rows [oy0, oy0 + n_rows) -> dst rows
+// [0, n_rows).  Orientation::from_exif / apply_orientation of the image crate (handler.rs:221-223):
+//   2 flip horizontal, 3 rotate 180, 4 flip vertical, 5 transpose (rotate90 + flip_horizontal),
+//   6 rotate 90 clockwise, 7 transverse (rotate270 + flip_horizontal), 8 rotate 270.
+// A block moves a 32 x 32 pixel tile; the transposing cases go through shared memory so that both
+// the reads (along stored rows) and the writes (along oriented rows) are coalesced.
+__global__ void __launch_bounds__(256) orient_pass_kernel(const StageDesc *__restrict__ descs) {
+    __shared__ uint32_t tile[32][33];
+    const StageDesc d = descs[blockIdx.z];
+    const uint32_t ow = d.canvas_w;  // oriented width; the oriented height is the other stored dimension
+    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    if (bx >= ow || by >= d.n_rows) return;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t W = d.src_w, H = d.src_h;
+    const bool swap = d.orient >= 5;
+    auto pack = [&](uint32_t sx, uint32_t sy) {
+        uint32_t v[4] = {0, 0, 0, 0};
+        load_px(d, sx, sy, v);
+        return v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24;
+    };
+    if (swap) {
+        // stored x runs along oriented y: read with tx along oriented y, write with tx along oriented x
+        for (uint32_t k = ty; k < 32; k += 8) {
+            const uint32_t xo = bx + k, yo = d.oy0 + by + tx;  // oriented pixel this thread fetches
+            if (xo < ow && by + tx < d.n_rows) {
+                const uint32_t sx = (d.orient == 5 || d.orient == 6) ? yo : W - 1 - yo;
+                const uint32_t sy = (d.orient == 5 || d.orient == 8) ? xo : H - 1 - xo;
+                tile[k][tx] = pack(sx, sy);
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = ty; k < 32; k += 8) {
+            const uint32_t xo = bx + tx, row = by + k;
+            if (xo < ow && row < d.n_rows) {
+                const uint32_t v = tile[tx][k];
+                uint8_t *q = d.dst + size_t(row) * d.dst_pitch + size_t(xo) * d.c;
+                for (uint32_t c = 0; c < d.c; c++) q[c] = uint8_t(v >> (8 * c));
+            }
+        }
+    } else {
+        for (uint32_t k = ty; k < 32; k += 8) {
+            const uint32_t xo = bx + tx, row = by + k, yo = d.oy0 + row;
+            if (xo < ow && row < d.n_rows) {
+                const uint32_t sx = (d.orient == 2 || d.orient == 3) ? W - 1 - xo : xo;
+                const uint32_t sy = (d.orient == 3 || d.orient == 4) ? H - 1 - yo : yo;
+                const uint32_t v = pack(sx, sy);
+                uint8_t *q = d.dst + size_t(row) * d.dst_pitch + size_t(xo) * d.c;
+                for (uint32_t c = 0; c < d.c; c++) q[c] = uint8_t(v >> (8 * c));
+            }
+        }
+    }
+}
+
 }  // namespace
+
+int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
+    if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;
+    lc.begin("orient_pass_kernel");
+    orient_pass_kernel<<<dim3((g.max_canvas_w + 31) / 32, (g.max_canvas_h + 31) / 32, g.n_jobs), 256, 0, lc.st>>>(d_descs);
+    lc.end();
+    return 1;
+}
 
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;

@@ -164,6 +164,39 @@ static void axis_window(uint32_t kind, float sigma, uint32_t n_in, uint32_t n_ou
 static uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; }
 
 int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
+    if (job.orientation > 8) { set_error("fanlin: orientation must be an EXIF value 0..8"); return FANLIN_EINVAL; }
+    if (job.orientation >= 2 && !(job.flags & FANLIN_TO_RGBA8)) {
+        // Orientation::from_exif + apply_orientation: 5..8 swap width and height.  Plan the request as it
+        // looks behind the orientation pass, which also applies the colour op.
+        if (job.src_w == 0 || job.src_h == 0 || job.src_channels < 1 || job.src_channels > 4) {
+            set_error("fanlin: bad source image");
+            return FANLIN_EINVAL;
+        }
+        OrientPlan pre;
+        pre.present = true;
+        pre.orient = job.orientation;
+        pre.c_mem = pre.c = job.src_channels;
+        pre.color_op = COLOR_NONE;
+        if (job.flags & FANLIN_GRAYSCALE) {
+            if (job.src_channels >= 3) { pre.color_op = COLOR_GRAY; pre.c = job.src_channels - 2; }
+        } else if (job.flags & FANLIN_INVERSE) {
+            pre.color_op = COLOR_INVERT;
+        }
+        fanlin_job &ej = pre.job;
+        ej = job;
+        ej.orientation = 0;
+        ej.flags &= ~uint32_t(FANLIN_GRAYSCALE | FANLIN_INVERSE);
+        if (job.orientation >= 5) { ej.src_w = job.src_h; ej.src_h = job.src_w; }
+        ej.src_channels = pre.c;
+        ej.src_pitch = (ej.src_w * pre.c + 15u) & ~15u;
+        ej.src = nullptr;
+        const int rc = plan_job(ej, out, with_tables);
+        if (rc != FANLIN_OK) return rc;
+        out->pre = pre;
+        out->pub.stages |= pre.color_op != COLOR_NONE ? 1u : 0u;
+        out->pub.algorithmic_bytes = uint64_t(out->pub.src_x1 - out->pub.src_x0) * (out->pub.src_y1 - out->pub.src_y0) * job.src_channels + out->pub.out_bytes;
+        return FANLIN_OK;
+    }
     JobPlan p;
     const uint32_t W = job.src_w, H = job.src_h, c0 = job.src_channels;
     if (W == 0 || H == 0) { set_error("fanlin: empty source image"); return FANLIN_EINVAL; }

@@ -47,8 +47,19 @@ struct StagePlan {
     std::shared_ptr<const AxisTable> vtab, htab;
 };
 
+// EXIF orientation (apply_orientation, handler.rs:221-223): the stored image is turned -- and the
+// colour op applied, it commutes with a permutation of pixels -- by a pass of its own into
+// scratch; stages a / b are planned for `job`, the request as it looks behind that pass.
+struct OrientPlan {
+    bool present = false;
+    uint32_t orient = 0;                    // 2..8
+    uint32_t c_mem = 0, c = 0, color_op = 0;  // the stored image's channels, after the colour op, the op
+    fanlin_job job{};                       // oriented size, c channels, 16-byte aligned pitch, no colour flags; src unset
+};
+
 struct JobPlan {
     fanlin_plan pub{};
+    OrientPlan pre;
     StagePlan a;  // colour op + resample + letterbox (+ to_rgba8), or compose
     StagePlan b;  // blur
 };

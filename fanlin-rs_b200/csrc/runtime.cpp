@@ -302,9 +302,11 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         for (const TapEntry &e : t->entries) entries.push_back(TapEntry{e.left, e.count, e.woff + wb});
         weights.insert(weights.end(), t->weights.begin(), t->weights.end());
     };
+    std::vector<fanlin_job> ej(jobs, jobs + n_jobs);  // the request as stages a / b see it: behind the orientation pass, if any
     for (uint32_t i = 0; i < n_jobs; i++) {
         const int rc = plan_job(jobs[i], &b->plans[i], true);
         if (rc != FANLIN_OK) return rc;
+        if (b->plans[i].pre.present) ej[i] = b->plans[i].pre.job;  // src: its scratch image, set once the scratch is laid out
         if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
         if (jobs[i].dst_capacity < b->plans[i].pub.out_bytes) {
             set_error("fanlin: dst_capacity smaller than the planned output");
@@ -314,7 +316,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         const JobPlan &p = b->plans[i];
         fused_a[i] = 0;
         if (!exact && use_tc) {
-            if (fused_tc_eligible(p.a, jobs[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) {
+            if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) {
                 fused_a[i] = 2;
             } else if (p.a.present && p.a.separable && p.a.color_op != COLOR_NONE && p.a.src_is_input) {
                 // Grayscale / inverse keep the tensor-core path: the source bytes reach the tensor core
@@ -324,13 +326,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 StagePlan m = p.a;
                 m.color_op = COLOR_NONE; m.c_mem = m.c; m.src_is_input = false;
                 m.in_pitch = uint32_t(align_up(size_t(m.in_w) * m.c, 16));
-                if (fused_tc_eligible(m, jobs[i]) && fused_tc_geometry_ok(m, tcache.get(), &ftabs, &tctabs)) {
+                if (fused_tc_eligible(m, ej[i]) && fused_tc_geometry_ok(m, tcache.get(), &ftabs, &tctabs)) {
                     fused_a[i] = 2;
                     a_pre[i] = m;
                 }
             }
         }
-        if (!fused_a[i]) fused_a[i] = !exact && fused_eligible(p.a, jobs[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
+        if (!fused_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         fast_b[i] = !exact && blur_eligible(p.b);
         if (!fast_b[i]) { add_table(p.b.vtab); add_table(p.b.htab); }
@@ -345,6 +347,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         for (uint32_t i = 0; i < n_jobs; i++) {
             const JobPlan &p = b->plans[i];
             if (a_pre[i].present) js[i].pre = align_up(size_t(a_pre[i].in_pitch) * a_pre[i].in_h, 256);
+            if (p.pre.present) js[i].pre = align_up(size_t(p.pre.job.src_pitch) * p.pre.job.src_h, 256);
             if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_w) * p.a.canvas_h * p.a.c_out, 256);
             size_t ta = 0, tb = 0;
             if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
@@ -365,6 +368,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     }
     b->alloc_stream = up_stream;
     if (scratch_bytes) CUDA_TRY(cudaMallocAsync(&b->d_scratch, scratch_bytes, up_stream));  // stream-ordered pool: no device sync
+    for (uint32_t i = 0; i < n_jobs; i++)
+        if (b->plans[i].pre.present) ej[i].src = static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off;
 
     // 3. descriptors per chunk and stage kind
     std::vector<StageDesc> descs;
@@ -380,6 +385,26 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         for (uint32_t i = begin; i < end; i++) {
             if (fused_a[i] == 1) by_variant[fused_variant(b->plans[i].a)].push_back(i);
             if (fused_a[i] == 2) tc_by_c[b->plans[i].a.c].push_back(i);
+        }
+        {  // orientation passes: the stored image turned (and its colour op applied) into scratch, in front of everything
+            HostStep hs{6, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+            for (uint32_t i = begin; i < end; i++) {
+                const JobPlan &p = b->plans[i];
+                if (!p.pre.present) continue;
+                StageDesc d;
+                std::memset(&d, 0, sizeof(d));
+                d.src = jobs[i].src;
+                d.src_pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
+                d.src_w = jobs[i].src_w; d.src_h = jobs[i].src_h;
+                d.c_mem = p.pre.c_mem; d.c = p.pre.c; d.color_op = p.pre.color_op; d.orient = p.pre.orient;
+                d.v_tab = d.h_tab = NO_TABLE;
+                d.oy0 = p.pub.src_y0; d.n_rows = p.pub.src_y1 - p.pub.src_y0; d.ox0 = 0; d.n_cols = ej[i].src_w;
+                d.dst = const_cast<uint8_t *>(ej[i].src) + size_t(d.oy0) * ej[i].src_pitch;
+                d.dst_pitch = ej[i].src_pitch; d.c_out = p.pre.c; d.canvas_w = ej[i].src_w; d.canvas_h = d.n_rows; d.epi = EPI_PLAIN;
+                geom_add(&hs.g, d);
+                descs.push_back(d);
+            }
+            if (hs.g.n_jobs) hsteps.push_back(hs);
         }
         {  // colour-op passes in front of the tensor-core resample: the needed source rows, op applied, into scratch
             HostStep hs{5, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
@@ -406,9 +431,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 const bool pre = a_pre[i].present;
-                const uint8_t *tsrc = pre ? static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off : jobs[i].src;
-                const uint32_t pitch = pre ? a_pre[i].in_pitch : jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
-                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, jobs[i], tsrc, pitch, p.b.present ? inter : jobs[i].dst, tcache.get(), &ftabs,
+                const uint8_t *tsrc = pre ? static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off : ej[i].src;
+                const uint32_t pitch = pre ? a_pre[i].in_pitch : ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
+                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, p.b.present ? inter : jobs[i].dst, tcache.get(), &ftabs,
                                               &tctabs, &tcitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core tables"); return rc; }
             }
@@ -422,8 +447,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             for (uint32_t i : kv.second) {
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
-                const uint32_t pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
-                const int rc = fused_build(p.a, jobs[i].src, pitch, p.b.present ? inter : jobs[i].dst, fcache.get(), &ftabs, &fitems);
+                const uint32_t pitch = ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
+                const int rc = fused_build(p.a, ej[i].src, pitch, p.b.present ? inter : jobs[i].dst, fcache.get(), &ftabs, &fitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: fused tables"); return rc; }
             }
             hs.n_items = uint32_t(fitems.size() - hs.first);
@@ -443,7 +468,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 float *tmp = js[i].tmp ? reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off) : nullptr;
                 StageDesc d;
                 const bool last = pass == 2 || !p.b.present;
-                fill_desc(&d, s, jobs[i], inter, tmp, tab_base, last);
+                fill_desc(&d, s, ej[i], inter, tmp, tab_base, last);
                 geom_add(&hs.g, d);
                 descs.push_back(d);
             }
@@ -464,8 +489,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 BlurItem bi{};
                 blur_build(p.b, &btabs, &ftabs.w, &bi);
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
-                bi.src = p.b.src_is_input ? jobs[i].src : inter;
-                bi.src_pitch = p.b.src_is_input ? (jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels) : p.b.in_w * p.b.c;
+                bi.src = p.b.src_is_input ? ej[i].src : inter;
+                bi.src_pitch = p.b.src_is_input ? (ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels) : p.b.in_w * p.b.c;
                 bi.dst = jobs[i].dst;
                 bi.tmp = reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off);
                 bi.aligned4 = (bi.src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(bi.src) & 3) == 0);
@@ -595,7 +620,8 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
             const int k = launch_fused(s.items, s.n_items, s.variant, s.max_band, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no fused kernel variant"); return FANLIN_EINVAL; }
             n += k;
-        } else if (s.kind == 5) n += launch_color_pass(s.descs, s.geom, lc);
+        } else if (s.kind == 6) n += launch_orient_pass(s.descs, s.geom, lc);
+        else if (s.kind == 5) n += launch_color_pass(s.descs, s.geom, lc);
         else if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
         else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, lc);
     }

@@ -25,7 +25,7 @@ class Job(C.Structure):
         ("src_w", C.c_uint32), ("src_h", C.c_uint32), ("src_channels", C.c_uint32), ("src_pitch", C.c_uint32),
         ("flags", C.c_uint32), ("filter", C.c_uint32),
         ("req_w", C.c_uint32), ("req_h", C.c_uint32),
-        ("fill_rgb", C.c_uint8 * 3), ("reserved0", C.c_uint8),
+        ("fill_rgb", C.c_uint8 * 3), ("orientation", C.c_uint8),
         ("blur_sigma", C.c_float),
         ("dst", C.c_void_p),
         ("dst_capacity", C.c_uint64),

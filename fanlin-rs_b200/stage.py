@@ -21,10 +21,13 @@ def _as_img(a) -> np.ndarray:
     return a
 
 
-def make_job(img: np.ndarray, params: Query, *, gif: bool = False) -> Job:
+def make_job(img: np.ndarray, params: Query, *, gif: bool = False, orientation: int = 1) -> Job:
+    """orientation: the EXIF value decoder.orientation() reported for a still (src/handler.rs:206);
+    the device turns the image instead of img.apply_orientation(o) on the host (:221-223)."""
     a = _as_img(img)
     j = Job()
     lib().fanlin_job_from_query(C.byref(params._q), int(gif), C.byref(j))
+    j.orientation = int(orientation)
     j.src = a.ctypes.data
     j.src_h, j.src_w, j.src_channels = a.shape
     j._keep = a
@@ -45,9 +48,10 @@ def _run(dev: Device, jobs):
     return outs
 
 
-def process_image(dev: Device, img: np.ndarray, params: Query) -> np.ndarray:
-    """Pixel section of State::process_image: decoded pixels in, transformed pixels out."""
-    return _run(dev, [make_job(img, params)])[0]
+def process_image(dev: Device, img: np.ndarray, params: Query, *, orientation: int = 1) -> np.ndarray:
+    """Pixel section of State::process_image: decoded pixels (as stored, with their EXIF
+    orientation) in, transformed pixels out."""
+    return _run(dev, [make_job(img, params, orientation=orientation)])[0]
 
 
 def process_images(dev: Device, imgs, params: Query):

@@ -65,7 +65,10 @@ typedef struct fanlin_job {
     uint32_t filter;       /* enum fanlin_filter */
     uint32_t req_w, req_h; /* used when FANLIN_HAS_DIMS */
     uint8_t fill_rgb[3];   /* Query::fill_color()  src/query.rs:35-49 */
-    uint8_t reserved0;
+    uint8_t orientation;   /* EXIF orientation of a decoded still: 0 / 1 = none, 2..8 as ImageDecoder::orientation()
+                              reports it; replaces img.apply_orientation(o) at src/handler.rs:206,221-223.  The source
+                              fields describe the image as stored; the stage sees it oriented.  Ignored for GIF frames
+                              (process_gif never reads EXIF). */
     float blur_sigma;      /* Query::blur(): 0 = off, else already clamped to [10,20]  src/query.rs:59-62 */
     uint8_t *dst;          /* host (fanlin_run) or device (fanlin_batch_*) pointer, tight rows */
     uint64_t dst_capacity; /* bytes available at dst */
@@ -78,7 +81,7 @@ typedef struct fanlin_plan {
     uint32_t resized_w, resized_h; /* resize_dimensions() result before crop; 0 if no resample */
     uint32_t crop_x, crop_y;       /* resize_to_fill crop origin inside the resized image */
     uint32_t overlay_x, overlay_y; /* letterbox offset (handler.rs:244-245) */
-    uint32_t src_x0, src_y0, src_x1, src_y1; /* source window the output depends on */
+    uint32_t src_x0, src_y0, src_x1, src_y1; /* source window the output depends on (in the oriented image) */
     uint32_t stages;               /* bit0 colour op, bit1 resample, bit2 letterbox, bit3 blur, bit4 to_rgba8 */
     uint64_t out_bytes;
     uint64_t algorithmic_bytes;    /* src window bytes + out_bytes */

@@ -54,7 +54,7 @@ typedef struct {
     uint32_t flags;
     uint32_t req_w, req_h;
     uint8_t fill[3];
-    uint8_t pad_;
+    uint8_t orientation; /* EXIF orientation of the decoded still, 0 / 1 = none, 2..8 (handler.rs:206,221-223) */
     float blur_sigma; /* already through Query::blur(): 0 or clamp(.,10,20) */
     uint8_t *dst;
     uint64_t dst_cap;
@@ -402,6 +402,58 @@ static void crop_copy(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, ui
 
 /* ---- the stage: src/handler.rs:224-255 (still) and :329-355 (GIF frame) -- */
 
+/* ---- metadata.rs Orientation::from_exif + dynimage.rs apply_orientation ---------------
+ * (handler.rs:221-223).  EXIF 1 NoTransforms, 2 FlipHorizontal, 3 Rotate180, 4 FlipVertical,
+ * 5 Rotate90FlipH, 6 Rotate90, 7 Rotate270FlipH, 8 Rotate270.  The crate composes them from
+ * imageops::{rotate90, rotate180, rotate270, flip_horizontal, flip_vertical}:
+ *   rotate90 (clockwise):  out.put_pixel(h - 1 - y, x, p)   -> out is h x w
+ *   rotate270:             out.put_pixel(y, w - 1 - x, p)   -> out is h x w
+ *   rotate180:             out.put_pixel(w - 1 - x, h - 1 - y, p)
+ *   flip_horizontal:       out.put_pixel(w - 1 - x, y, p);   flip_vertical: (x, h - 1 - y)
+ * Rotate90FlipH = rotate90 then flip_horizontal; Rotate270FlipH = rotate270 then flip_horizontal. */
+static void px_copy(uint8_t *d, const uint8_t *s, uint32_t c) { for (uint32_t k = 0; k < c; k++) d[k] = s[k]; }
+
+static void op_rotate90(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, uint8_t *dst) { /* dst: h x w */
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) px_copy(dst + ((size_t)x * h + (h - 1 - y)) * c, src + ((size_t)y * w + x) * c, c);
+}
+static void op_rotate270(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, uint8_t *dst) { /* dst: h x w */
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) px_copy(dst + ((size_t)(w - 1 - x) * h + y) * c, src + ((size_t)y * w + x) * c, c);
+}
+static void op_rotate180(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, uint8_t *dst) {
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) px_copy(dst + ((size_t)(h - 1 - y) * w + (w - 1 - x)) * c, src + ((size_t)y * w + x) * c, c);
+}
+static void op_fliph(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, uint8_t *dst) {
+    for (uint32_t y = 0; y < h; y++)
+        for (uint32_t x = 0; x < w; x++) px_copy(dst + ((size_t)y * w + (w - 1 - x)) * c, src + ((size_t)y * w + x) * c, c);
+}
+static void op_flipv(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, uint8_t *dst) {
+    for (uint32_t y = 0; y < h; y++) memcpy(dst + (size_t)(h - 1 - y) * w * c, src + (size_t)y * w * c, (size_t)w * c);
+}
+
+/* dst holds w*h*c bytes; *ow, *oh receive the oriented size.  Returns FO_EINVAL for exif > 8. */
+int fo_apply_orientation(const uint8_t *src, uint32_t w, uint32_t h, uint32_t c, uint32_t exif, uint8_t *dst, uint32_t *ow,
+                         uint32_t *oh) {
+    size_t n = (size_t)w * h * c;
+    *ow = w; *oh = h;
+    if (exif > 8) return FO_EINVAL;
+    if (exif <= 1) { memcpy(dst, src, n); return FO_OK; }
+    if (exif == 2) { op_fliph(src, w, h, c, dst); return FO_OK; }
+    if (exif == 3) { op_rotate180(src, w, h, c, dst); return FO_OK; }
+    if (exif == 4) { op_flipv(src, w, h, c, dst); return FO_OK; }
+    *ow = h; *oh = w;
+    if (exif == 6) { op_rotate90(src, w, h, c, dst); return FO_OK; }
+    if (exif == 8) { op_rotate270(src, w, h, c, dst); return FO_OK; }
+    uint8_t *t = (uint8_t *)malloc(n);
+    if (!t) return FO_ENOMEM;
+    if (exif == 5) op_rotate90(src, w, h, c, t); else op_rotate270(src, w, h, c, t); /* 5, 7: then flip_horizontal */
+    op_fliph(t, h, w, c, dst);
+    free(t);
+    return FO_OK;
+}
+
 int fo_process(fo_job *job) {
     uint32_t w = job->src_w, h = job->src_h, c = job->src_c;
     if (!job->src || w == 0 || h == 0 || c < 1 || c > 4) return FO_EINVAL;
@@ -410,8 +462,13 @@ int fo_process(fo_job *job) {
     int filter = gif ? FO_NEAREST : FO_LANCZOS3; /* handler.rs:233,235 vs :338,:340 */
     uint8_t *img = (uint8_t *)malloc((size_t)w * h * c);
     if (!img) return FO_ENOMEM;
-    memcpy(img, job->src, (size_t)w * h * c);
     int rc = FO_OK;
+    if (!gif && job->orientation > 1) { /* handler.rs:221-223: stills only; process_gif never looks at EXIF */
+        rc = fo_apply_orientation(job->src, w, h, c, job->orientation, img, &w, &h);
+        if (rc != FO_OK) { free(img); return rc; }
+    } else {
+        memcpy(img, job->src, (size_t)w * h * c);
+    }
 
     /* handler.rs:224-228 / :329-333 -- grayscale wins, inverse only otherwise */
     if (job->flags & FO_GRAYSCALE) {

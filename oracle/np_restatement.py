@@ -201,11 +201,35 @@ def overlay(bottom, top, x, y):
     return out
 
 
+def apply_orientation(img, exif):
+    """Orientation::from_exif + apply_orientation, written with whole-array operations
+    (independent of the per-pixel put_pixel loops of the C restatement): rotate90 is clockwise."""
+    if exif in (0, 1):
+        return img
+    if exif == 2:
+        return img[:, ::-1]
+    if exif == 3:
+        return img[::-1, ::-1]
+    if exif == 4:
+        return img[::-1]
+    if exif == 5:  # Rotate90FlipH = transpose
+        return np.rot90(img, k=-1)[:, ::-1]
+    if exif == 6:
+        return np.rot90(img, k=-1)
+    if exif == 7:  # Rotate270FlipH = transverse
+        return np.rot90(img, k=1)[:, ::-1]
+    if exif == 8:
+        return np.rot90(img, k=1)
+    raise ValueError("orientation")
+
+
 def process(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur_sigma=0.0, gray=False,
-            inverse=False, gif=False):
+            inverse=False, gif=False, orientation=1):
     if img.ndim == 2:
         img = img[:, :, None]
     kind = "nearest" if gif else "lanczos3"
+    if not gif:
+        img = np.ascontiguousarray(apply_orientation(img, orientation))
     if gray:
         img = grayscale(img)
     elif inverse:

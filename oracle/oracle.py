@@ -30,7 +30,7 @@ class Job(C.Structure):
         ("src_w", C.c_uint32), ("src_h", C.c_uint32), ("src_c", C.c_uint32),
         ("flags", C.c_uint32),
         ("req_w", C.c_uint32), ("req_h", C.c_uint32),
-        ("fill", C.c_uint8 * 3), ("pad_", C.c_uint8),
+        ("fill", C.c_uint8 * 3), ("orientation", C.c_uint8),
         ("blur_sigma", C.c_float),
         ("dst", C.c_void_p),
         ("dst_cap", C.c_uint64),
@@ -71,6 +71,7 @@ def lib():
         L.fo_overlay.restype = None
         L.fo_weight_table.argtypes = [C.c_int, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.fo_weight_table.restype = C.c_uint32
+        L.fo_apply_orientation.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -151,7 +152,7 @@ def weight_table(kind, n_in, n_out, sigma=0.0):
 
 
 def make_job(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0, grayscale=False,
-             inverse=False, gif=False):
+             inverse=False, gif=False, orientation=1):
     """Job from the accessor values of query::Query (src/query.rs:28-70)."""
     a = _img(img)
     j = Job()
@@ -172,8 +173,21 @@ def make_job(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0, gra
     j.flags = fl
     j.fill[0], j.fill[1], j.fill[2] = rgb
     j.blur_sigma = float(blur)
+    j.orientation = int(orientation)
     j._keep = a
     return j
+
+
+def apply_orientation(img, exif: int) -> np.ndarray:
+    """DynamicImage::apply_orientation for an EXIF orientation value (handler.rs:221-223)."""
+    a = _img(img)
+    h, w, c = a.shape
+    out = np.empty(a.size, np.uint8)
+    ow, oh = C.c_uint32(), C.c_uint32()
+    rc = lib().fo_apply_orientation(C.c_void_p(a.ctypes.data), w, h, c, int(exif), C.c_void_p(out.ctypes.data), C.byref(ow), C.byref(oh))
+    if rc:
+        raise ValueError(f"fo_apply_orientation rc={rc}")
+    return out.reshape(oh.value, ow.value, c)
 
 
 def out_capacity(j: Job) -> int:

@@ -60,6 +60,10 @@ CASES = [
     ("tiny_Nx1", [24, 77, 1, 4], dict(w=20, h=20, crop=True)),
     ("ragged_prime", [25, 211, 307, 3], dict(w=97, h=89, crop=True, blur=15.0)),
     ("blur_sigma20_small_img", [26, 17, 23, 4], dict(blur=20.0)),
+    # EXIF orientation (handler.rs:221-223): rotate 180, rotate 90 clockwise, transverse
+    ("orient3_lenna_fit_fill", "lenna", dict(w=300, h=200, rgb=[32, 32, 32], orientation=3)),
+    ("orient6_portrait_crop_gray", [31, 300, 200, 3], dict(w=120, h=90, crop=True, grayscale=True, orientation=6)),
+    ("orient7_rgba_fit_blur", [32, 150, 260, 4], dict(w=100, h=100, rgb=[5, 6, 7], blur=10.0, orientation=7)),
 ]
 
 

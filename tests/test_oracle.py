@@ -75,7 +75,7 @@ def test_two_restatements_agree_bit_for_bit(case, lenna):
     p = dict(case["params"])
     kw = dict(w=p.get("w"), h=p.get("h"), rgb=tuple(p.get("rgb", (32, 32, 32))), crop=p.get("crop", False),
               blur_sigma=p.get("blur", 0.0), gray=p.get("grayscale", False), inverse=p.get("inverse", False),
-              gif=p.get("gif", False))
+              gif=p.get("gif", False), orientation=p.get("orientation", 1))
     a = O.process(img, **_okw(case["params"]))
     b = N.process(img, **kw)
     assert a.shape == b.shape
@@ -177,3 +177,45 @@ def test_batch_driver_matches_single():
     outs = O.process_batch(imgs, n_threads=3, w=30, h=30)
     for im, o in zip(imgs, outs):
         assert np.array_equal(o, O.process(im, w=30, h=30))
+
+
+# ---- EXIF orientation (handler.rs:206,221-223) ------------------------
+
+@pytest.mark.parametrize("exif", range(0, 9))
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_orientation_c_and_numpy_restatements_agree(exif, c):
+    img = synth_image(40 + exif, 7, 11, c)
+    got = O.apply_orientation(img, exif)
+    want = N.apply_orientation(img, exif)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    if exif >= 5:
+        assert got.shape[:2] == (11, 7)
+
+
+def test_orientation_known_answers():
+    """2x3 image with pixel value 10*y + x: the eight EXIF cases spelled out by hand."""
+    img = np.array([[0, 1, 2], [10, 11, 12]], np.uint8)[:, :, None]
+    want = {
+        1: [[0, 1, 2], [10, 11, 12]],
+        2: [[2, 1, 0], [12, 11, 10]],          # mirror left-right
+        3: [[12, 11, 10], [2, 1, 0]],          # rotate 180
+        4: [[10, 11, 12], [0, 1, 2]],          # mirror top-bottom
+        5: [[0, 10], [1, 11], [2, 12]],        # transpose
+        6: [[10, 0], [11, 1], [12, 2]],        # rotate 90 clockwise
+        7: [[12, 2], [11, 1], [10, 0]],        # transverse
+        8: [[2, 12], [1, 11], [0, 10]],        # rotate 90 counter-clockwise
+    }
+    for exif, w in want.items():
+        assert O.apply_orientation(img, exif)[:, :, 0].tolist() == w, exif
+
+
+@pytest.mark.parametrize("exif", [2, 3, 6, 7])
+def test_orientation_then_pipeline(exif):
+    """The stage sees the oriented image: process(orientation=e) == process(apply_orientation(img, e))."""
+    img = synth_image(77, 60, 90, 3)
+    kw = dict(w=40, h=30, rgb=(1, 2, 3), grayscale=True)
+    a = O.process(img, orientation=exif, **kw)
+    b = O.process(np.ascontiguousarray(O.apply_orientation(img, exif)), **kw)
+    assert np.array_equal(a, b)
+    n = N.process(img, w=40, h=30, rgb=(1, 2, 3), gray=True, orientation=exif)
+    assert np.array_equal(a, n)

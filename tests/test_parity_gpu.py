@@ -75,7 +75,7 @@ def _is_interp(params):
 @pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
 def test_golden_cases_exact_mode_bit_exact(fanlin, dev_exact, lenna, case):
     img = _input(case["input"], lenna)
-    got = fanlin.process_image(dev_exact, img, fanlin.Query(_qs(case["params"]))) if not case["params"].get("gif") \
+    got = fanlin.process_image(dev_exact, img, fanlin.Query(_qs(case["params"])), orientation=case["params"].get("orientation", 1)) if not case["params"].get("gif") \
         else fanlin.process_gif_frames(dev_exact, [img], fanlin.Query(_qs(case["params"])))[0]
     assert got.shape == (case["out_h"], case["out_w"], case["out_c"])
     assert hashlib.sha256(got.tobytes()).hexdigest() == case["sha256"], hist(got, O.process(img, **_okw(case["params"])))
@@ -85,7 +85,7 @@ def test_golden_cases_exact_mode_bit_exact(fanlin, dev_exact, lenna, case):
 def test_golden_cases_fast_mode(fanlin, dev, lenna, case):
     img = _input(case["input"], lenna)
     want = O.process(img, **_okw(case["params"]))
-    got = fanlin.process_image(dev, img, fanlin.Query(_qs(case["params"]))) if not case["params"].get("gif") \
+    got = fanlin.process_image(dev, img, fanlin.Query(_qs(case["params"])), orientation=case["params"].get("orientation", 1)) if not case["params"].get("gif") \
         else fanlin.process_gif_frames(dev, [img], fanlin.Query(_qs(case["params"])))[0]
     assert got.shape == want.shape
     h = hist(got, want)
@@ -202,6 +202,57 @@ def test_resample_paths_agree(fanlin, dev, dev_cuda_cores, dev_exact, seed, h, w
         print(name, qs, "mismatch histogram", hh)
         assert hh[">=2"] == 0, (name, hh)
         assert hh[1] <= 0.002 * want.size, (name, hh)  # off-by-one only where the f32 sum sits on a rounding boundary
+
+
+# ---- EXIF orientation on the device (handler.rs:206,221-223) ------------------
+
+ORIENT_CASES = [
+    # (h, w, c, query)
+    (300, 420, 3, "w=128&h=96&rgb=3,4,5"),              # tensor-core resample + letterbox
+    (300, 420, 3, "w=128&h=96&crop=true&grayscale=true"),  # colour op folded into the orientation pass
+    (201, 333, 4, "w=90&h=70&inverse=true"),            # odd sizes, RGBA, inverse keeps alpha
+    (160, 240, 1, "w=100&h=100&blur=12"),               # blur after the letterbox
+    (120, 90, 3, "blur=10"),                            # no resize: blur reads the oriented image directly
+    (64, 48, 2, "grayscale=true"),                      # nothing but the orientation (+ no-op grayscale on LA)
+]
+
+
+@pytest.mark.parametrize("exif", [2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("h,w,c,qs", ORIENT_CASES, ids=[f"{p[0]}x{p[1]}x{p[2]}-{p[3]}" for p in ORIENT_CASES])
+def test_orientation_on_device(fanlin, dev, dev_cuda_cores, dev_exact, exif, h, w, c, qs):
+    """The orientation pass is a permutation (+ the integer colour op): the exact context stays
+    bit-identical to the oracle, the fast paths within 1 LSB, for all seven EXIF transforms."""
+    img = synth_image(500 + exif, h, w, c)
+    q = fanlin.Query(qs)
+    kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+    dims = q.dimensions()
+    if dims is not None:
+        kw["w"], kw["h"] = dims
+    want = O.process(img, orientation=exif, **kw)
+    exact = fanlin.process_image(dev_exact, img, q, orientation=exif)
+    assert exact.shape == want.shape and np.array_equal(exact, want), hist(exact, want)
+    for name, d in (("tensor-core", dev), ("cuda-core", dev_cuda_cores)):
+        got = fanlin.process_image(d, img, q, orientation=exif)
+        assert got.shape == want.shape
+        hh = hist(got, want)
+        assert hh[">=2"] == 0 and hh[1] <= 0.002 * want.size + 2, (name, hh)
+
+
+def test_orientation_rejects_bad_value_and_ignores_gif_frames(fanlin, dev):
+    img = synth_image(5, 20, 30, 4)
+    j = fanlin.make_job(img, fanlin.Query("w=10&h=10"), orientation=9)
+    o = np.zeros(10 * 10 * 4, np.uint8)
+    j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
+    with pytest.raises(fanlin.FanlinError):
+        dev.run([j])
+    # process_gif never reads EXIF: a frame job with an orientation is processed as stored
+    q = fanlin.Query("w=10&h=10")
+    a = fanlin.process_gif_frames(dev, [img], q)[0]
+    j2 = fanlin.make_job(img, q, gif=True, orientation=6)
+    o2 = np.zeros(a.size, np.uint8)
+    j2.dst, j2.dst_capacity = o2.ctypes.data, o2.nbytes
+    dev.run([j2])
+    assert np.array_equal(o2.reshape(a.shape), a)
 
 
 # ---- same-shaped images in one launch --------------------------------------------------------
