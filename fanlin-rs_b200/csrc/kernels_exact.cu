@@ -130,49 +130,80 @@ __global__ void __launch_bounds__(256) color_pass_kernel(const StageDesc *__rest
 //   6 rotate 90 clockwise, 7 transverse (rotate270 + flip_horizontal), 8 rotate 270.
 // A block moves a 32 x 32 pixel tile; the transposing cases go through shared memory so that both
 // the reads (along stored rows) and the writes (along oriented rows) are coalesced.
+// One stored pixel of CM channels with the colour op applied, packed one channel per byte.
+template <int CM>
+__device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t color_op) {
+    uint32_t b[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < CM; k++) b[k] = p[k];
+    if (color_op == COLOR_GRAY && CM >= 3) return luma_u8(b[0], b[1], b[2]) | (CM == 4 ? b[3] << 8 : 0u);
+    if (color_op == COLOR_INVERT) {
+        constexpr int NCOL = (CM == 2 || CM == 4) ? CM - 1 : CM;  // alpha stays
+#pragma unroll
+        for (int k = 0; k < NCOL; k++) b[k] = 255u - b[k];
+    }
+    return b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
+}
+
 __global__ void __launch_bounds__(256) orient_pass_kernel(const StageDesc *__restrict__ descs) {
-    __shared__ uint32_t tile[32][33];
-    const StageDesc d = descs[blockIdx.z];
+    constexpr uint32_t TK = 64;  // tile extent across the stored rows: 8 pixels per thread in flight
+    __shared__ uint32_t tile[TK][33];  // [k][tx]: k counts stored rows (oriented rows, or oriented columns when the axes swap)
+    const StageDesc &d = descs[blockIdx.z];
     const uint32_t ow = d.canvas_w;  // oriented width; the oriented height is the other stored dimension
-    const uint32_t bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const uint32_t orient = d.orient, c_mem = d.c_mem, color_op = d.color_op, src_pitch = d.src_pitch, oy0 = d.oy0, n_rows = d.n_rows;
+    const uint8_t *src = d.src;
+    const bool swap = d.orient >= 5;
+    const uint32_t bx = blockIdx.x * (swap ? TK : 32), by = blockIdx.y * (swap ? 32 : TK);
     if (bx >= ow || by >= d.n_rows) return;
     const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const uint32_t W = d.src_w, H = d.src_h;
-    const bool swap = d.orient >= 5;
-    auto pack = [&](uint32_t sx, uint32_t sy) {
-        uint32_t v[4] = {0, 0, 0, 0};
-        load_px(d, sx, sy, v);
-        return v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24;
-    };
-    if (swap) {
-        // stored x runs along oriented y: read with tx along oriented y, write with tx along oriented x
-        for (uint32_t k = ty; k < 32; k += 8) {
-            const uint32_t xo = bx + k, yo = d.oy0 + by + tx;  // oriented pixel this thread fetches
-            if (xo < ow && by + tx < d.n_rows) {
-                const uint32_t sx = (d.orient == 5 || d.orient == 6) ? yo : W - 1 - yo;
-                const uint32_t sy = (d.orient == 5 || d.orient == 8) ? xo : H - 1 - xo;
-                tile[k][tx] = pack(sx, sy);
+    // fetch: tx runs along the stored rows (oriented y when the axes swap), four pixels per thread, all loads in flight
+    uint32_t px[TK / 8];
+#pragma unroll
+    for (uint32_t q = 0; q < TK / 8; q++) {
+        const uint32_t k = ty + 8 * q;
+        const uint32_t xo = swap ? bx + k : bx + tx, row = swap ? by + tx : by + k, yo = oy0 + row;
+        px[q] = 0;
+        if (xo < ow && row < n_rows) {
+            uint32_t sx, sy;
+            if (swap) {
+                sx = (orient == 5 || orient == 6) ? yo : W - 1 - yo;
+                sy = (orient == 5 || orient == 8) ? xo : H - 1 - xo;
+            } else {
+                sx = (orient == 2 || orient == 3) ? W - 1 - xo : xo;
+                sy = (orient == 3 || orient == 4) ? H - 1 - yo : yo;
             }
+            const uint8_t *p = src + size_t(sy) * src_pitch + size_t(sx) * c_mem;
+            px[q] = c_mem == 3 ? fetch_packed<3>(p, color_op) : c_mem == 4 ? fetch_packed<4>(p, color_op)
+                  : c_mem == 1 ? fetch_packed<1>(p, color_op) : fetch_packed<2>(p, color_op);
         }
-        __syncthreads();
-        for (uint32_t k = ty; k < 32; k += 8) {
-            const uint32_t xo = bx + tx, row = by + k;
-            if (xo < ow && row < d.n_rows) {
-                const uint32_t v = tile[tx][k];
-                uint8_t *q = d.dst + size_t(row) * d.dst_pitch + size_t(xo) * d.c;
-                for (uint32_t c = 0; c < d.c; c++) q[c] = uint8_t(v >> (8 * c));
+    }
+#pragma unroll
+    for (uint32_t q = 0; q < TK / 8; q++) tile[ty + 8 * q][tx] = px[q];
+    __syncthreads();
+    // store: oriented row segments of the tile as whole words, 8 threads per row
+    const uint32_t C = d.c, sub = threadIdx.x & 7;
+    const uint32_t tile_w = swap ? TK : 32, tile_h = swap ? 32 : TK;
+    const uint32_t n_px = min(tile_w, ow - bx), n_bytes = n_px * C;
+    for (uint32_t row = threadIdx.x >> 3; row < tile_h; row += 32) {
+        if (by + row >= n_rows) break;
+        uint8_t *q0 = d.dst + size_t(by + row) * d.dst_pitch + size_t(bx) * C;
+        auto at = [&](uint32_t p) { return swap ? tile[p][row] : tile[row][p]; };  // pixel p of this oriented row
+        if ((reinterpret_cast<uintptr_t>(q0) & 3) == 0) {
+            for (uint32_t w = sub; 4 * w < n_bytes; w += 8) {
+                uint32_t out = 0;
+                uint32_t p = C == 4 ? w : C == 2 ? 2 * w : C == 1 ? 4 * w : (4 * w) / 3, ch = 4 * w - p * C;  // C is 1..4: constant divisors
+#pragma unroll
+                for (uint32_t bb = 0; bb < 4; bb++) {
+                    out |= ((at(min(p, tile_w - 1)) >> (8 * ch)) & 0xffu) << (8 * bb);
+                    if (++ch == C) { ch = 0; p++; }
+                }
+                if (4 * w + 4 <= n_bytes) *reinterpret_cast<uint32_t *>(q0 + 4 * w) = out;
+                else for (uint32_t bb = 0; 4 * w + bb < n_bytes; bb++) q0[4 * w + bb] = uint8_t(out >> (8 * bb));
             }
-        }
-    } else {
-        for (uint32_t k = ty; k < 32; k += 8) {
-            const uint32_t xo = bx + tx, row = by + k, yo = d.oy0 + row;
-            if (xo < ow && row < d.n_rows) {
-                const uint32_t sx = (d.orient == 2 || d.orient == 3) ? W - 1 - xo : xo;
-                const uint32_t sy = (d.orient == 3 || d.orient == 4) ? H - 1 - yo : yo;
-                const uint32_t v = pack(sx, sy);
-                uint8_t *q = d.dst + size_t(row) * d.dst_pitch + size_t(xo) * d.c;
-                for (uint32_t c = 0; c < d.c; c++) q[c] = uint8_t(v >> (8 * c));
-            }
+        } else {
+            for (uint32_t p = sub; p < n_px; p += 8)
+                for (uint32_t ch = 0; ch < C; ch++) q0[p * C + ch] = uint8_t(at(p) >> (8 * ch));
         }
     }
 }
@@ -182,6 +213,7 @@ __global__ void __launch_bounds__(256) orient_pass_kernel(const StageDesc *__res
 int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;
     lc.begin("orient_pass_kernel");
+    // tiles are 32 x 64 or 64 x 32 (axes swapped); the grid covers the larger count either way
     orient_pass_kernel<<<dim3((g.max_canvas_w + 31) / 32, (g.max_canvas_h + 31) / 32, g.n_jobs), 256, 0, lc.st>>>(d_descs);
     lc.end();
     return 1;

@@ -23,6 +23,9 @@ CONFIGS = [
     ("C5 12MP RGB crop+gray (no blur)", 3000, 4000, 3, "w=1618&h=1000&crop=true&grayscale=true", False, 148),
     ("C5 12MP RGB fit+fill+gray (no blur)", 3000, 4000, 3, "w=1618&h=1000&grayscale=true", False, 148),
     ("C5 12MP RGB crop+gray+blur=10", 3000, 4000, 3, "w=1618&h=1000&crop=true&grayscale=true&blur=10", False, 32),
+    # EXIF orientation on the device (stored portrait 1080x1920 shown as 1920x1080)
+    ("C2 stored rotated, EXIF 6 (rotate 90)", 1920, 1080, 3, "w=300&h=200", False, 592, 6),
+    ("C2 EXIF 3 (rotate 180)", 1080, 1920, 3, "w=300&h=200", False, 592, 3),
 ]
 
 
@@ -44,7 +47,9 @@ def main():
     device = torch.device("cuda", 0)
     stream = torch.cuda.Stream(device)
     out = []
-    for name, h, w, c, qs, gif, batch in CONFIGS:
+    for cfg in CONFIGS:
+        name, h, w, c, qs, gif, batch = cfg[:7]
+        exif = cfg[7] if len(cfg) > 7 else 1
         if args.only and args.only not in name:
             continue
         n = max(1, int(batch * args.scale))
@@ -54,6 +59,7 @@ def main():
         proto = pkg.Job()
         pkg.lib().fanlin_job_from_query(C.byref(q._q), int(gif), C.byref(proto))
         proto.src_w, proto.src_h, proto.src_channels = w, h, c
+        proto.orientation = exif
         plan = pkg.plan_job(proto)
         dst = torch.zeros((n, plan.out_h, plan.out_w, plan.out_channels), dtype=torch.uint8, device=device)
         jobs = (pkg.Job * n)()
@@ -77,7 +83,7 @@ def main():
         kt = {}
         for k, v in b.kernel_times():
             kt.setdefault(k, []).append(v)
-        kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=0.0 if gif else q.blur(), rgb=q.fill_color(), gif=gif)
+        kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=0.0 if gif else q.blur(), rgb=q.fill_color(), gif=gif, orientation=exif)
         if q.dimensions():
             kw["w"], kw["h"] = q.dimensions()
         want = O.process(base[1].cpu().numpy(), **kw)
