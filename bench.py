@@ -274,13 +274,26 @@ def main():
         assert d2 == 0, parity
 
     # dominant kernel and its roofline
+    def ncu_traffic(kernel, images):
+        """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of
+        this workload, scaled from the captured launch's image count to this launch's (the kernel
+        streams every image once: traffic is per image)."""
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01", "ncu_traffic_c2.json")
+        try:
+            t = json.load(open(path))
+        except OSError:
+            return None
+        if t.get("kernel") != kernel:
+            return None
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["images"] * images
+
     dom = max(ktimes, key=lambda k: sum(ktimes[k])) if ktimes else None
     roofline = None
     if dom:
         avg_ms = sum(ktimes[dom]) / len(ktimes[dom])
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": None if args.exact else ncu_traffic(dom, n), "peak_source": peak_src,
                     "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                     "kernel_share_of_step": avg_ms / ms_per_step,
                     "all_kernels_ms": {k: sum(v) / len(v) for k, v in ktimes.items()}}
