@@ -706,7 +706,8 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         in_off.clear();
         out_off.clear();
         while (end < n && end - begin < per) {
-            const size_t ib = align_up(size_t(jobs[end].src_w) * jobs[end].src_channels * jobs[end].src_h, 256);
+            // device rows start every 16 bytes whatever the width: the tensor-core path (TMA) needs that stride
+            const size_t ib = align_up(align_up(size_t(jobs[end].src_w) * jobs[end].src_channels, 16) * jobs[end].src_h, 256);
             if (end > begin && in_bytes + ib > max_bytes) break;
             in_off.push_back(in_bytes);
             out_off.push_back(out_bytes);
@@ -726,13 +727,13 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         for (uint32_t i = 0; i < m && rc == FANLIN_OK; i++) {
             const fanlin_job &j = jobs[begin + i];
             const size_t row = size_t(j.src_w) * j.src_channels;
-            const size_t pitch = j.src_pitch ? j.src_pitch : row;
-            const cudaError_t e = pitch == row
+            const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
+            const cudaError_t e = pitch == row && dpitch == row
                                       ? cudaMemcpyAsync(f.d_in + in_off[i], j.src, row * j.src_h, cudaMemcpyHostToDevice, f.st)
-                                      : cudaMemcpy2DAsync(f.d_in + in_off[i], row, j.src, pitch, row, j.src_h, cudaMemcpyHostToDevice, f.st);
+                                      : cudaMemcpy2DAsync(f.d_in + in_off[i], dpitch, j.src, pitch, row, j.src_h, cudaMemcpyHostToDevice, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; }
             djobs[i].src = f.d_in + in_off[i];
-            djobs[i].src_pitch = 0;
+            djobs[i].src_pitch = uint32_t(dpitch);
             djobs[i].dst = f.d_out + out_off[i];
             djobs[i].dst_capacity = pl[begin + i].out_bytes;
             ctx->h2d_bytes += row * j.src_h;
