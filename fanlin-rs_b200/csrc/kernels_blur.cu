@@ -130,10 +130,21 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
         const float *src = it.tmp + size_t(y) * n_e;
         const int ge0 = int(x0 * C) - int(R * C);
         float *trow = tile + size_t(r) * pitch;
-        for (uint32_t i = t & 31; i < row_elems; i += 32) {
-            const int ge = ge0 + int(i);
-            if (y < it.h && ge >= 0 && ge < int(n_e)) cp_async4(smem_u32(trow + i), src + ge, true);
-            else trow[i] = 0.f;
+        // four floats per copy when both sides are 16-byte aligned (always for RGBA rows of even width)
+        const bool quad = (row_elems & 3) == 0 && (ge0 & 3) == 0 && (n_e & 3) == 0 &&
+                          ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(trow)) & 15) == 0;
+        if (quad) {
+            for (uint32_t i = 4 * (t & 31); i < row_elems; i += 128) {
+                const int ge = ge0 + int(i);  // ge, n_e multiples of 4: a group is inside or outside as a whole
+                if (y < it.h && ge >= 0 && ge < int(n_e)) cp_async16(smem_u32(trow + i), src + ge);
+                else *reinterpret_cast<float4 *>(trow + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (uint32_t i = t & 31; i < row_elems; i += 32) {
+                const int ge = ge0 + int(i);
+                if (y < it.h && ge >= 0 && ge < int(n_e)) cp_async4(smem_u32(trow + i), src + ge, true);
+                else trow[i] = 0.f;
+            }
         }
     }
     cp_async_commit();
