@@ -153,7 +153,7 @@ int fused_build(const StagePlan &s, const uint8_t *src, uint32_t src_pitch, uint
         f.vw_off = bt.vw_off; f.vinfo_off = bt.vinfo_off; f.vinfo_stride = bt.vinfo_stride;
         f.hw_off = g.hw_off; f.hinfo_off = g.hinfo_off;
         f.n_cols = s.n_cols;
-        f.dst_pitch = s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
+        f.dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
         f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;
         f.first_band = b == 0; f.last_band = b + 1 == g.bands.size();
         items->push_back(f);

@@ -114,6 +114,83 @@ bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
     return true;
 }
 
+// One band of output rows [oy0 + r0, + rows) of a vertical filter: its groups of <= 32 rows, their
+// source-row windows (in 32-row K steps) and their weight-digit tiles.  min_grp: smallest group size
+// tried -- every MMA costs the same ~112 clk floor whatever N is, so the group size that minimises
+// the number of K steps over the band wins (C2: 29 rows -> 6 x 7 instead of 6 x 8 at 32).
+static bool build_band(const AxisTable &vt, uint32_t oy0, uint32_t r0, uint32_t rows, int sh, uint32_t min_grp, FusedTables *tabs,
+                       FusedTcTables *tct, TcBand *out) {
+    TcBand bt{};
+    bt.r0 = r0;
+    bt.rows = rows;
+    // source rows spanned by output rows [ra, rb) of the band
+    auto span = [&](uint32_t ra, uint32_t rb, uint32_t *k0) {
+        *k0 = vt.entries[oy0 + r0 + ra].left;
+        uint32_t k1 = 0;
+        for (uint32_t r = ra; r < rb; r++) {
+            const TapEntry &e = vt.entries[oy0 + r0 + r];
+            k1 = std::max(k1, e.left + e.count);
+        }
+        return k1 - *k0;
+    };
+    uint32_t best_r = 0, best_cost = ~0u;
+    for (uint32_t gr = TC_GROUP_ROWS; gr >= min_grp; gr--) {
+        uint32_t cost = 0;
+        bool fits = true;
+        for (uint32_t ra = 0; ra < bt.rows && fits; ra += gr) {
+            uint32_t k0;
+            const uint32_t kspan = span(ra, std::min(bt.rows, ra + gr), &k0);
+            fits = kspan <= TC_KG_MAX;
+            cost += (kspan + 31) / 32;
+        }
+        if (fits && cost < best_cost) { best_cost = cost; best_r = gr; }
+    }
+    if (!best_r || (bt.rows + best_r - 1) / best_r > 24) return false;  // the kernels keep <= 24 group records in shared memory
+    bt.grp_rows = best_r;
+    bt.n_groups = (bt.rows + best_r - 1) / best_r;
+    bt.grp_off = uint32_t(tabs->info.size());
+    tabs->info.resize(tabs->info.size() + size_t(bt.n_groups) * 4, 0u);
+    for (uint32_t gi = 0; gi < bt.n_groups; gi++) {
+        const uint32_t ra = gi * best_r, rb = std::min(bt.rows, ra + best_r);
+        uint32_t k0;
+        const uint32_t kg = (span(ra, rb, &k0) + 31) / 32 * 32;
+        bt.kg_max = std::max(bt.kg_max, kg);
+        const size_t b_off = (tct->b.size() + 127) & ~size_t(127);
+        tct->b.resize(b_off + size_t(TC_N) * kg, 0);
+        int8_t *tile = reinterpret_cast<int8_t *>(&tct->b[b_off]);
+        for (uint32_t r = ra; r < rb; r++) {
+            const TapEntry &e = vt.entries[oy0 + bt.r0 + r];
+            for (uint32_t t = 0; t < e.count; t++) {
+                const long q = std::lround(std::ldexp(double(vt.weights[e.woff + t]), sh));
+                const long lo = ((q + 64) & 127) - 64;
+                const long q1 = (q - lo) / 128;
+                const long mid = ((q1 + 64) & 127) - 64;
+                const long hi = (q1 - mid) / 128;
+                if (hi < -128 || hi > 127) return false;
+                const uint32_t k = e.left + t - k0, j = r - ra;
+                const long dig[3] = {hi, mid, lo};
+                for (uint32_t d = 0; d < 3; d++) {
+                    const uint32_t n = d * TC_GROUP_ROWS + j;  // B row: digit-major
+                    tile[(size_t(n / 8) * (kg / 16) + k / 16) * 128 + (n % 8) * 16 + k % 16] = int8_t(dig[d]);
+                }
+            }
+        }
+        uint32_t *gw = &tabs->info[bt.grp_off + size_t(gi) * 4];
+        gw[0] = k0; gw[1] = kg; gw[2] = uint32_t(b_off); gw[3] = rb - ra;
+    }
+    *out = bt;
+    return true;
+}
+
+// q = round(w * 2^sh) must fit three signed base-128 digits
+static int weight_shift(const AxisTable &vt) {
+    float maxw = 0.f;
+    for (float w : vt.weights) maxw = std::max(maxw, std::fabs(w));
+    int sh = 30;
+    while (sh > 0 && std::ldexp(double(maxw), sh) > 2080000.0) sh--;
+    return sh;
+}
+
 static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
     const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c | (s.c_out << 8));
     auto it = cache->geoms.find(key);
@@ -172,76 +249,15 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
         g.out_stride = (widest * s.c_out + 6) / 4;  // ceil((3 bytes of alignment phase + pixels) / 4) words
     }
     // vertical: q = round(w * 2^sh) split into three signed base-128 digits
-    float maxw = 0.f;
-    for (float w : s.vtab->weights) maxw = std::max(maxw, std::fabs(w));
-    int sh = 30;
-    while (sh > 0 && std::ldexp(double(maxw), sh) > 2080000.0) sh--;
+    const int sh = weight_shift(*s.vtab);
     g.scale = std::ldexp(1.0f, -sh);
     const uint32_t max_band = fused_tc_max_band(s.c, g.out_stride);
     if (max_band < 32) ok = false;  // strong upscales finish too many pixels per chunk to stage: CUDA-core path
     const uint32_t n_bands = (s.n_rows + max_band - 1) / max_band;
     const uint32_t band_rows = (s.n_rows + n_bands - 1) / n_bands;
-    // source rows spanned by output rows [ra, rb) of the band starting at b0
-    auto span = [&](uint32_t b0, uint32_t ra, uint32_t rb, uint32_t *k0) {
-        *k0 = s.vtab->entries[s.oy0 + b0 + ra].left;
-        uint32_t k1 = 0;
-        for (uint32_t r = ra; r < rb; r++) {
-            const TapEntry &e = s.vtab->entries[s.oy0 + b0 + r];
-            k1 = std::max(k1, e.left + e.count);
-        }
-        return k1 - *k0;
-    };
     for (uint32_t b0 = 0; b0 < s.n_rows && ok; b0 += band_rows) {
         TcBand bt{};
-        bt.r0 = b0;
-        bt.rows = std::min(band_rows, s.n_rows - b0);
-        // rows per group: every MMA costs the same ~112 clk floor whatever N is, so minimise the
-        // number of 32-row K steps over the band (C2: 29 rows -> 6 x 7 instead of 6 x 8 at 32)
-        uint32_t best_r = 0, best_cost = ~0u;
-        for (uint32_t gr = TC_GROUP_ROWS; gr >= 8; gr--) {
-            uint32_t cost = 0;
-            bool fits = true;
-            for (uint32_t ra = 0; ra < bt.rows && fits; ra += gr) {
-                uint32_t k0;
-                const uint32_t kspan = span(b0, ra, std::min(bt.rows, ra + gr), &k0);
-                fits = kspan <= TC_KG_MAX;
-                cost += (kspan + 31) / 32;
-            }
-            if (fits && cost < best_cost) { best_cost = cost; best_r = gr; }
-        }
-        if (!best_r || (bt.rows + best_r - 1) / best_r > 24) { ok = false; break; }  // the kernel keeps <= 24 group records in shared memory
-        bt.grp_rows = best_r;
-        bt.n_groups = (bt.rows + best_r - 1) / best_r;
-        bt.grp_off = uint32_t(tabs->info.size());
-        tabs->info.resize(tabs->info.size() + size_t(bt.n_groups) * 4, 0u);
-        for (uint32_t gi = 0; gi < bt.n_groups && ok; gi++) {
-            const uint32_t ra = gi * best_r, rb = std::min(bt.rows, ra + best_r);
-            uint32_t k0;
-            const uint32_t kg = (span(b0, ra, rb, &k0) + 31) / 32 * 32;
-            bt.kg_max = std::max(bt.kg_max, kg);
-            const size_t b_off = (tct->b.size() + 127) & ~size_t(127);
-            tct->b.resize(b_off + size_t(TC_N) * kg, 0);
-            int8_t *tile = reinterpret_cast<int8_t *>(&tct->b[b_off]);
-            for (uint32_t r = ra; r < rb; r++) {
-                const TapEntry &e = s.vtab->entries[s.oy0 + bt.r0 + r];
-                for (uint32_t t = 0; t < e.count; t++) {
-                    const long q = std::lround(std::ldexp(double(s.vtab->weights[e.woff + t]), sh));
-                    const long lo = ((q + 64) & 127) - 64;
-                    const long q1 = (q - lo) / 128;
-                    const long mid = ((q1 + 64) & 127) - 64;
-                    const long hi = (q1 - mid) / 128;
-                    if (hi < -128 || hi > 127) { ok = false; break; }
-                    const uint32_t k = e.left + t - k0, j = r - ra;
-                    const long dig[3] = {hi, mid, lo};
-                    for (uint32_t d = 0; d < 3; d++) {
-                        const uint32_t n = d * TC_GROUP_ROWS + j;  // B row: digit-major
-                        tile[(size_t(n / 8) * (kg / 16) + k / 16) * 128 + (n % 8) * 16 + k % 16] = int8_t(dig[d]);
-                    }
-                }
-            }
-            uint32_t *gw = &tabs->info[bt.grp_off + size_t(gi) * 4];
-            gw[0] = k0; gw[1] = kg; gw[2] = uint32_t(b_off); gw[3] = rb - ra;
-        }
+        ok = build_band(*s.vtab, s.oy0, b0, std::min(band_rows, s.n_rows - b0), sh, 8, tabs, tct, &bt);
         g.bands.push_back(bt);
     }
     g.ok = ok;
@@ -269,9 +285,71 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         f.hw_off = g.hw_off; f.hinfo_off = g.hinfo_off; f.cpre_off = g.cpre_off; f.out_stride = g.out_stride;
         f.n_a = fused_tc_source_slots(s.c, bt.rows, bt.kg_max, g.out_stride);
         f.n_cols = s.n_cols;
-        f.dst_pitch = s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
+        f.dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
         f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;
         f.first_band = b == 0; f.last_band = b + 1 == g.bands.size();
+        items->push_back(f);
+    }
+    return FANLIN_OK;
+}
+
+// ---- vertical blur on the tensor cores ------------------------------------------------------
+
+size_t blur_v_tc_smem_bytes(uint32_t kg_max, uint32_t n_a) {
+    return size_t(n_a) * kg_max * TC_M + 2 * size_t(TC_N) * kg_max + 1024;
+}
+
+bool blur_v_tc_eligible(const StagePlan &s, uint32_t pitch, const uint8_t *src) {
+    if (!s.present || !s.separable || s.v_kind != KIND_GAUSSIAN || !s.vtab) return false;
+    if (s.color_op != COLOR_NONE || s.c_mem != s.c) return false;
+    if (s.n_rows != s.in_h || s.n_cols != s.in_w || s.oy0 != 0) return false;
+    if (pitch % 16 != 0 || (reinterpret_cast<uintptr_t>(src) & 15)) return false;  // TMA
+    return 32 + s.vtab->max_taps <= TC_KG_MAX;
+}
+
+namespace {
+struct BlurVGeom {
+    bool ok = false;
+    float scale = 1.f;
+    std::vector<TcBand> bands;
+};
+}  // namespace
+
+int blur_v_tc_build(const StagePlan &s, const uint8_t *src, uint32_t src_pitch, float *dst, FusedTcCache *cache, FusedTables *tabs,
+                    FusedTcTables *tct, std::vector<BlurVTcItem> *items) {
+    // geometry per (table, rows): cached next to the resample geometries under a key no resample uses (htab = null)
+    const TcKey key(s.vtab.get(), nullptr, s.n_rows, 0u, 0u);
+    auto it = cache->geoms.find(key);
+    if (it == cache->geoms.end()) {
+        TcGeom g;
+        const int sh = weight_shift(*s.vtab);
+        g.scale = std::ldexp(1.0f, -sh);
+        bool ok = true;
+        // bands of <= 8 groups: a band re-reads 2 * radius source rows (u8, against 4 bytes written per element),
+        // and small batches of large images still fill the SMs
+        const uint32_t max_band = 8 * TC_GROUP_ROWS;
+        const uint32_t n_bands = (s.n_rows + max_band - 1) / max_band;
+        const uint32_t band_rows = ((s.n_rows + n_bands - 1) / n_bands + TC_GROUP_ROWS - 1) / TC_GROUP_ROWS * TC_GROUP_ROWS;
+        for (uint32_t b0 = 0; b0 < s.n_rows && ok; b0 += band_rows) {
+            TcBand bt{};
+            ok = build_band(*s.vtab, 0, b0, std::min(band_rows, s.n_rows - b0), sh, TC_GROUP_ROWS, tabs, tct, &bt);  // groups of exactly 32 rows
+            g.bands.push_back(bt);
+        }
+        g.ok = ok;
+        it = cache->geoms.emplace(key, std::move(g)).first;
+    }
+    const TcGeom &g = it->second;
+    if (!g.ok) return FANLIN_EINVAL;
+    const uint32_t n_e = s.in_w * s.c;
+    for (const TcBand &bt : g.bands) {
+        BlurVTcItem f{};
+        f.src = src; f.dst = dst; f.src_pitch = src_pitch; f.src_h = s.in_h;
+        f.n_e = n_e; f.n_chunks = (n_e + TC_M - 1) / TC_M;
+        f.band_r0 = bt.r0; f.band_rows = bt.rows;
+        f.grp_off = bt.grp_off; f.n_groups = bt.n_groups; f.kg_max = bt.kg_max;
+        f.n_a = 4;
+        while (f.n_a > 2 && blur_v_tc_smem_bytes(f.kg_max, f.n_a) > TC_SMEM_LIMIT) f.n_a--;
+        f.scale = g.scale;
         items->push_back(f);
     }
     return FANLIN_OK;

@@ -47,6 +47,20 @@ struct FusedTcItem {
     uint32_t first_band, last_band;
 };
 
+// Vertical Gaussian pass of the blur on the tensor cores (kernels_fused_tc.cu blur_v_tc_kernel):
+// the same banded integer contraction, output rows = input rows, written as the f32 intermediate
+// [h][w * c] the horizontal blur kernel reads (imageops::blur, handler.rs:250-255).
+struct BlurVTcItem {
+    const uint8_t *src;
+    float *dst;
+    uint32_t src_pitch, src_h;
+    uint32_t n_e, n_chunks;               // elements per row (w * c); 128-element column chunks
+    uint32_t band_r0, band_rows;          // <= 24 groups of 32 rows
+    uint32_t grp_off, n_groups, kg_max;   // u32 offset of {k0, kg, b_off, rows} x n_groups
+    uint32_t n_a;                         // source slots
+    float scale;                          // 2^-s
+};
+
 struct FusedTcTables {
     std::vector<uint8_t> b;  // weight digit tiles, core-matrix layout, 128-byte aligned per tile
 };
@@ -59,6 +73,11 @@ bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *
 int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
                    FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs, std::vector<FusedTcItem> *items);
 
+// Vertical blur: eligibility of a Gaussian stage whose input rows are `pitch` bytes apart, and its items (one per band).
+bool blur_v_tc_eligible(const StagePlan &s, uint32_t pitch, const uint8_t *src);
+int blur_v_tc_build(const StagePlan &s, const uint8_t *src, uint32_t src_pitch, float *dst, FusedTcCache *cache, FusedTables *tabs,
+                    FusedTcTables *tctabs, std::vector<BlurVTcItem> *items);
+size_t blur_v_tc_smem_bytes(uint32_t kg_max, uint32_t n_a);
 uint32_t fused_tc_max_pairs(uint32_t c);
 size_t fused_tc_smem_limit();  // kernels_fused_tc.cu: opt-in shared memory per block minus the kernel's static part
 size_t fused_tc_smem_bytes(uint32_t c, uint32_t band_rows, uint32_t kg_max, uint32_t out_stride, uint32_t n_a);

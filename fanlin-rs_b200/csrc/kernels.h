@@ -55,9 +55,13 @@ bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t r
 // Fast Gaussian blur (kernels_blur.cu): items share channel count, radius and padded tap count.
 struct BlurItem;
 int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
-                uint32_t taps_pad, const float *d_w, LaunchCtx &lc);
+                uint32_t taps_pad, const float *d_w, bool skip_v, LaunchCtx &lc);
 // Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+// Vertical blur pass on the tensor cores (kernels_fused_tc.cu); writes the f32 intermediate the horizontal blur kernel reads.
+struct BlurVTcItem;
+int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
+                     const uint32_t *d_info, LaunchCtx &lc);
 // Colour op alone over the needed source rows (in front of the tensor-core resample).
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 // EXIF orientation (+ colour op) of the stored image into scratch, in front of every other stage.

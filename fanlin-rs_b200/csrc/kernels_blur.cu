@@ -197,19 +197,21 @@ size_t blur_h_smem(uint32_t radius, uint32_t taps_pad, uint32_t c) {
 }
 
 int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
-                uint32_t taps_pad, const float *d_w, LaunchCtx &lc) {
+                uint32_t taps_pad, const float *d_w, bool skip_v, LaunchCtx &lc) {
     if (n_items == 0) return 0;
     const size_t sv = blur_v_smem(radius, taps_pad), sh = blur_h_smem(radius, taps_pad, c);
     cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv));
     cudaFuncSetAttribute(blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sh));
     const uint32_t rb = HT / c;
-    lc.begin("blur_v_kernel");
-    blur_v_kernel<<<dim3((max_w * c + VT - 1) / VT, (max_h + V_ROWS - 1) / V_ROWS, n_items), VT, sv, lc.st>>>(d_items, d_w);
-    lc.end();
+    if (!skip_v) {  // else the f32 intermediate was written by blur_v_tc_kernel
+        lc.begin("blur_v_kernel");
+        blur_v_kernel<<<dim3((max_w * c + VT - 1) / VT, (max_h + V_ROWS - 1) / V_ROWS, n_items), VT, sv, lc.st>>>(d_items, d_w);
+        lc.end();
+    }
     lc.begin("blur_h_kernel");
     blur_h_kernel<<<dim3((max_w + H_PX - 1) / H_PX, (max_h + rb - 1) / rb, n_items), HT, sh, lc.st>>>(d_items, d_w);
     lc.end();
-    return 2;
+    return skip_v ? 1 : 2;
 }
 
 }  // namespace fanlin

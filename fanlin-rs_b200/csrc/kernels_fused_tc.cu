@@ -100,6 +100,83 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
         : "r"(taddr));
 }
 
+// ---- the operand / MMA pipeline, shared by the resample kernel and the vertical-blur kernel ----
+// Groups are numbered flat across chunks (gg = chunk * n_groups + g): source slot gg % n_a,
+// weight-tile slot gg % NB, TMEM region gg % NR.
+struct TcPipe {
+    uint32_t mbar, tmem_free, a_full, b_full;  // shared-memory addresses of the mbarrier arrays (8 bytes per entry)
+    uint32_t sA_u, sB_u;                        // source slots [n_a][kg_max rows][128 B]; weight slots [NB][96][kg_max]
+    uint32_t kg_max, n_a, n_chunks, n_groups;
+    uint32_t x0;                                // byte offset of chunk 0 in a row (16-byte aligned)
+    uint32_t tmem_base;
+    const uint32_t *grp;                        // {k0, kg, b_off, rows} x n_groups, in shared memory
+};
+
+// source TMA thread: one tensor copy per group (kg_max rows x 128 B), n_a groups deep
+__device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMap *tmap) {
+    const uint32_t total = p.n_chunks * p.n_groups;
+    uint32_t g = 0, chunk = 0, slot = 0;
+    for (uint32_t gg = 0; gg < total; gg++) {
+        if (gg >= p.n_a) mbar_wait(p.mbar + 8 * ((gg - p.n_a) % NR), ((gg - p.n_a) / NR) & 1);  // the slot was read by the MMAs of group gg - n_a
+        const uint32_t bar = p.a_full + 8 * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.kg_max * TC_M) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                         p.sA_u + slot * p.kg_max * TC_M),
+                     "l"(tmap), "r"(bar), "r"(p.x0 + TC_M * chunk), "r"(p.grp[4 * g])
+                     : "memory");
+        if (++slot == p.n_a) slot = 0;
+        if (++g == p.n_groups) { g = 0; chunk++; }
+    }
+}
+
+// weight TMA thread: one bulk copy per group into slot gg % NB
+__device__ __forceinline__ void tc_weight_role(const TcPipe &p, const uint8_t *tb) {
+    const uint32_t total = p.n_chunks * p.n_groups;
+    uint32_t g = 0;
+    for (uint32_t gg = 0; gg < total; gg++) {
+        if (gg >= NB) mbar_wait(p.mbar + 8 * ((gg - NB) % NR), ((gg - NB) / NR) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
+        const uint32_t kg = p.grp[4 * g + 1], b_off = p.grp[4 * g + 2];
+        const uint32_t bar = p.b_full + 8 * (gg % NB);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         p.sB_u + (gg % NB) * TC_N * p.kg_max),
+                     "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
+                     : "memory");
+        if (++g == p.n_groups) g = 0;
+    }
+}
+
+// MMA thread: issues every tcgen05.mma; the commit of a group frees its operand slots and hands its TMEM region to the consumers
+__device__ __forceinline__ void tc_mma_role(const TcPipe &p) {
+    const uint32_t total = p.n_chunks * p.n_groups;
+    uint32_t g = 0, slot = 0, suse = 0;
+    for (uint32_t gg = 0; gg < total; gg++) {
+        const uint32_t region = gg % NR, ruse = gg / NR, bslot = gg % NB;
+        const uint32_t kg = p.grp[4 * g + 1];
+        mbar_wait(p.b_full + 8 * bslot, (gg / NB) & 1);                        // the weight tile has landed
+        mbar_wait(p.a_full + 8 * slot, suse & 1);                              // the source rows have landed
+        if (ruse > 0) mbar_wait(p.tmem_free + 8 * region, (ruse - 1) & 1);     // consumers drained the region's previous contents
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // descriptors advance by a constant per K step: 32 rows x 128 B of A, 2 core matrices of B
+        uint64_t da = umma_desc(p.sA_u + slot * p.kg_max * TC_M, 16, 1024, 2);  // SBO = 8-row atom stride
+        uint64_t db = umma_desc(p.sB_u + bslot * TC_N * p.kg_max, 128, (kg / 16) * 128);
+        const uint32_t d_tmem = p.tmem_base + region * TC_N;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "l"(da), "l"(db), "r"(UMMA_IDESC)
+                     : "memory");
+        for (uint32_t ks = 1; ks < kg / 32; ks++) {
+            da += SLAB >> 4;
+            db += (2 * 128) >> 4;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                         "l"(da), "l"(db), "r"(UMMA_IDESC)
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(p.mbar + 8 * region) : "memory");
+        if (++slot == p.n_a) { slot = 0; suse++; }
+        if (++g == p.n_groups) g = 0;
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const FusedTcItem *__restrict__ items,
                                                                   const CUtensorMap *__restrict__ tmaps,
@@ -188,72 +265,17 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     const uint32_t *cpre = tinfo + it.cpre_off;
     const uint32_t h_epi = it.epi, h_fill = it.fill;
 
-    // Groups are numbered flat across chunks (gg = chunk * n_groups + g): source slot gg % n_a,
-    // weight-tile slot gg % NB, TMEM region gg % NR.
-    const uint32_t total = n_chunks * n_groups;
+    TcPipe pipe;
+    pipe.mbar = smem_u32(&mbar[0]); pipe.tmem_free = smem_u32(&tmem_free[0]); pipe.a_full = smem_u32(&a_full[0]); pipe.b_full = smem_u32(&b_full[0]);
+    pipe.sA_u = sA_u; pipe.sB_u = sB_u; pipe.kg_max = kg_max; pipe.n_a = n_a; pipe.n_chunks = n_chunks; pipe.n_groups = n_groups;
+    pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp;
 
     if (warp == NT / 32 + 1) {
-        // ===== source TMA warp: one tensor copy per group (kg_max rows x 128 B), n_a groups deep =====
-        if (lane == 0) {
-            uint32_t g = 0, chunk = 0, slot = 0;
-            for (uint32_t gg = 0; gg < total; gg++) {
-                if (gg >= n_a) mbar_wait(smem_u32(&mbar[(gg - n_a) % NR]), ((gg - n_a) / NR) & 1);  // the slot was read by the MMAs of group gg - n_a
-                const uint32_t bar = smem_u32(&a_full[slot]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M) : "memory");
-                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                                 sA_u + slot * kg_max * TC_M),
-                             "l"(tmap), "r"(bar), "r"(it.b0 + TC_M * chunk), "r"(grp[4 * g])
-                             : "memory");
-                if (++slot == n_a) slot = 0;
-                if (++g == n_groups) { g = 0; chunk++; }
-            }
-        }
+        if (lane == 0) tc_source_role(pipe, tmap);
     } else if (warp == NT / 32 + 2) {
-        // ===== weight TMA warp: one bulk copy per group into slot gg % NB =====
-        if (lane == 0) {
-            uint32_t g = 0;
-            for (uint32_t gg = 0; gg < total; gg++) {
-                if (gg >= NB) mbar_wait(smem_u32(&mbar[(gg - NB) % NR]), ((gg - NB) / NR) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
-                const uint32_t kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
-                const uint32_t bar = smem_u32(&b_full[gg % NB]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 sB_u + (gg % NB) * TC_N * kg_max),
-                             "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
-                             : "memory");
-                if (++g == n_groups) g = 0;
-            }
-        }
+        if (lane == 0) tc_weight_role(pipe, tb);
     } else if (warp == NT / 32) {
-        // ===== MMA warp: one thread issues every tcgen05.mma =====
-        if (lane == 0) {
-            uint32_t g = 0, slot = 0, suse = 0;
-            for (uint32_t gg = 0; gg < total; gg++) {
-                const uint32_t region = gg % NR, ruse = gg / NR, bslot = gg % NB;
-                const uint32_t kg = grp[4 * g + 1];
-                mbar_wait(smem_u32(&b_full[bslot]), (gg / NB) & 1);                      // the weight tile has landed
-                mbar_wait(smem_u32(&a_full[slot]), suse & 1);                           // the source rows have landed
-                if (ruse > 0) mbar_wait(smem_u32(&tmem_free[region]), (ruse - 1) & 1);  // consumers drained the region's previous contents
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // descriptors advance by a constant per K step: 32 rows x 128 B of A, 2 core matrices of B
-                uint64_t da = umma_desc(sA_u + slot * kg_max * TC_M, 16, 1024, 2);  // SBO = 8-row atom stride
-                uint64_t db = umma_desc(sB_u + bslot * TC_N * kg_max, 128, (kg / 16) * 128);
-                const uint32_t d_tmem = tmem_base + region * TC_N;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                             "l"(da), "l"(db), "r"(UMMA_IDESC)
-                             : "memory");
-                for (uint32_t ks = 1; ks < kg / 32; ks++) {
-                    da += SLAB >> 4;
-                    db += (2 * 128) >> 4;
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                                 "l"(da), "l"(db), "r"(UMMA_IDESC)
-                                 : "memory");
-                }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar[region])) : "memory");
-                if (++slot == n_a) { slot = 0; suse++; }
-                if (++g == n_groups) g = 0;
-            }
-        }
+        if (lane == 0) tc_mma_role(pipe);
     } else {
     // ================= consumer warps =================
     auto stage_htab = [&](uint32_t chunk) {  // the chunk's slice of the horizontal table -> its shared-memory copy
@@ -450,6 +472,88 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
+// ---- vertical Gaussian pass of the blur: the same pipeline, consumers write the f32 intermediate ----
+// One CTA per band of <= 24 groups x 32 rows; per 128-element column chunk and group the consumers
+// drain the TMEM region and store value(row, column) to dst[row][column] -- lanes are consecutive
+// columns, so every store of a warp is one 128-byte line.  No shared-memory tile, no horizontal stage.
+__global__ void __launch_bounds__(NT_ALL, 1) blur_v_tc_kernel(const BlurVTcItem *__restrict__ items, const CUtensorMap *__restrict__ tmaps,
+                                                            const uint8_t *__restrict__ tb, const uint32_t *__restrict__ tinfo) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ BlurVTcItem it_s;
+    __shared__ __align__(8) uint64_t mbar[NR], tmem_free[NR], a_full[NA_MAX], b_full[NB];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t grp[4 * 24];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    if (tid == 0) {
+        it_s = items[blockIdx.x];
+        for (uint32_t r = 0; r < NR; r++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&tmem_free[r])));
+        }
+        for (uint32_t r = 0; r < NA_MAX; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&a_full[r])));
+        for (uint32_t r = 0; r < NB; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&b_full[r])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const BlurVTcItem &it = it_s;
+    for (uint32_t k = tid; k < 4 * it.n_groups; k += NT_ALL) grp[k] = tinfo[it.grp_off + k];
+    __syncthreads();
+    TcPipe pipe;
+    pipe.mbar = smem_u32(&mbar[0]); pipe.tmem_free = smem_u32(&tmem_free[0]); pipe.a_full = smem_u32(&a_full[0]); pipe.b_full = smem_u32(&b_full[0]);
+    pipe.sA_u = smem_u32(smem); pipe.sB_u = pipe.sA_u + it.n_a * it.kg_max * TC_M;
+    pipe.kg_max = it.kg_max; pipe.n_a = it.n_a; pipe.n_chunks = it.n_chunks; pipe.n_groups = it.n_groups;
+    pipe.x0 = 0; pipe.tmem_base = tmem_base_s; pipe.grp = grp;
+    if (warp == NT / 32 + 1) {
+        if (lane == 0) tc_source_role(pipe, tmaps + blockIdx.x);
+    } else if (warp == NT / 32 + 2) {
+        if (lane == 0) tc_weight_role(pipe, tb);
+    } else if (warp == NT / 32) {
+        if (lane == 0) tc_mma_role(pipe);
+    } else {
+        const float scale = it.scale, scale_hi = it.scale * 16384.0f;
+        const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane, n_e = it.n_e;
+        uint32_t gg = 0;
+        for (uint32_t chunk = 0; chunk < it.n_chunks; chunk++) {
+            const uint32_t col = chunk * TC_M + m;
+            for (uint32_t g = 0; g < it.n_groups; g++, gg++) {
+                const uint32_t region = gg % NR;
+                mbar_wait(smem_u32(&mbar[region]), (gg / NR) & 1);  // the MMAs of group gg have retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = pipe.tmem_base + region * TC_N + (((warp & 3) * 32u) << 16) + half * 16;
+                uint32_t hi[16], mid[16], lo[16];
+                tmem_ld16(taddr, hi);
+                tmem_ld16(taddr + 32, mid);
+                tmem_ld16(taddr + 64, lo);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[region])) : "memory");
+                const uint32_t jn = grp[4 * g + 3];
+                const uint32_t nv = jn > half * 16 ? jn - half * 16 : 0;  // rows of this half that exist
+                float *q = it.dst + size_t(it.band_r0 + g * TC_GROUP_ROWS + half * 16) * n_e + col;
+                if (col < n_e) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) {
+                        const float v = fmaf(float(int(hi[e])), scale_hi, float(int(mid[e]) * 128 + int(lo[e])) * scale);
+                        if (uint32_t(e) < nv) q[size_t(e) * n_e] = v;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(TMEM_COLS));
+}
+
 template <int C>
 void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
                        const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
@@ -472,6 +576,16 @@ int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_
     case 4: launch_tc_variant<4>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
     }
     return -1;
+}
+
+int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
+                     const uint32_t *d_info, LaunchCtx &lc) {
+    if (n_items == 0) return 0;
+    cudaFuncSetAttribute(blur_v_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    lc.begin("blur_v_tc_kernel");
+    blur_v_tc_kernel<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
+    lc.end();
+    return 1;
 }
 
 }  // namespace fanlin

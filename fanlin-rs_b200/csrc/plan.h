@@ -44,6 +44,7 @@ struct StagePlan {
     uint32_t oy0 = 0, n_rows = 0, ox0 = 0, n_cols = 0;
     uint32_t sx0 = 0, n_sx = 0, sy0 = 0, n_sy = 0;
     uint32_t canvas_w = 0, canvas_h = 0, c_out = 0, dst_x = 0, dst_y = 0, epi = EPI_PLAIN, fill = 0;
+    uint32_t canvas_pitch = 0;  // bytes per canvas row when the canvas is scratch with padded rows (0: canvas_w * c_out)
     std::shared_ptr<const AxisTable> vtab, htab;
 };
 

@@ -210,7 +210,7 @@ void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t 
         d->src_pitch = job.src_pitch ? job.src_pitch : job.src_w * job.src_channels;
     } else {
         d->src = inter;
-        d->src_pitch = s.in_w * s.c_mem;
+        d->src_pitch = s.in_pitch ? s.in_pitch : s.in_w * s.c_mem;
     }
     d->dst = last_stage ? job.dst : inter;
     d->tmp = tmp;
@@ -223,7 +223,7 @@ void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t 
     d->oy0 = s.oy0; d->n_rows = s.n_rows; d->ox0 = s.ox0; d->n_cols = s.n_cols;
     d->sx0 = s.sx0; d->n_sx = s.n_sx; d->sy0 = s.sy0; d->n_sy = s.n_sy;
     d->tmp_pitch = s.n_sx * s.c;
-    d->dst_pitch = s.canvas_w * s.c_out; d->c_out = s.c_out;
+    d->dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; d->c_out = s.c_out;
     d->canvas_w = s.canvas_w; d->canvas_h = s.canvas_h;
     d->dst_x = s.dst_x; d->dst_y = s.dst_y; d->epi = s.epi; d->fill = s.fill;
 }
@@ -307,6 +307,11 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         const int rc = plan_job(jobs[i], &b->plans[i], true);
         if (rc != FANLIN_OK) return rc;
         if (b->plans[i].pre.present) ej[i] = b->plans[i].pre.job;  // src: its scratch image, set once the scratch is laid out
+        if (b->plans[i].a.present && b->plans[i].b.present) {  // the canvas between the stages: rows on a 16-byte stride (TMA reads it)
+            StagePlan &sa = b->plans[i].a;
+            sa.canvas_pitch = uint32_t(align_up(size_t(sa.canvas_w) * sa.c_out, 16));
+            b->plans[i].b.in_pitch = sa.canvas_pitch;
+        }
         if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
         if (jobs[i].dst_capacity < b->plans[i].pub.out_bytes) {
             set_error("fanlin: dst_capacity smaller than the planned output");
@@ -348,7 +353,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             const JobPlan &p = b->plans[i];
             if (a_pre[i].present) js[i].pre = align_up(size_t(a_pre[i].in_pitch) * a_pre[i].in_h, 256);
             if (p.pre.present) js[i].pre = align_up(size_t(p.pre.job.src_pitch) * p.pre.job.src_h, 256);
-            if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_w) * p.a.canvas_h * p.a.c_out, 256);
+            if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_pitch) * p.a.canvas_h, 256);
             size_t ta = 0, tb = 0;
             if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
             if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of either blur path
@@ -375,7 +380,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     std::vector<StageDesc> descs;
     std::vector<FusedItem> fitems;
     std::vector<FusedTcItem> tcitems;
-    struct HostStep { int kind; size_t first; LaunchGeom g; uint32_t variant, n_items, max_band; size_t smem; };
+    std::vector<BlurVTcItem> bvitems;
+    struct HostStep { int kind; size_t first; LaunchGeom g; uint32_t variant, n_items, max_band; size_t smem; uint32_t n_paired = 0; };
     std::vector<HostStep> hsteps;
     uint32_t begin = 0;
     for (uint32_t end : chunk_end) {
@@ -474,23 +480,35 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             }
             if (hs.g.n_jobs) hsteps.push_back(hs);
         }
-        // stage B through the fast blur kernels, one launch pair per (channels, sigma)
-        std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> blur_groups;
+        // stage B through the fast blur kernels, one launch pair per (channels, sigma); the vertical pass
+        // on the tensor cores where the rows allow TMA (16-byte stride), else on the CUDA cores
+        std::map<std::tuple<uint32_t, uint32_t, uint32_t>, std::vector<uint32_t>> blur_groups;
+        auto b_src = [&](uint32_t i, const uint8_t **src, uint32_t *pitch) {
+            const JobPlan &p = b->plans[i];
+            uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
+            *src = p.b.src_is_input ? ej[i].src : inter;
+            *pitch = p.b.src_is_input ? (ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels)
+                                      : (p.b.in_pitch ? p.b.in_pitch : p.b.in_w * p.b.c);
+        };
         for (uint32_t i = begin; i < end; i++)
             if (fast_b[i]) {
                 uint32_t sb;
                 std::memcpy(&sb, &b->plans[i].b.sigma, 4);
-                blur_groups[{b->plans[i].b.c, sb}].push_back(i);
+                const uint8_t *src; uint32_t pitch;
+                b_src(i, &src, &pitch);
+                const uint32_t vtc = use_tc && blur_v_tc_eligible(b->plans[i].b, pitch, src) ? 1u : 0u;
+                blur_groups[std::make_tuple(b->plans[i].b.c, sb, vtc)].push_back(i);
             }
         for (auto &kv : blur_groups) {
+            const bool vtc = std::get<2>(kv.first) != 0;
+            HostStep hv{7, bvitems.size(), LaunchGeom{}, 0, 0, 0, 0};
             HostStep hs{4, bitems.size(), LaunchGeom{}, 0, 0, 0, 0};
+            hs.n_paired = vtc ? 1 : 0;  // kind 4: the vertical pass was done by the step before
             for (uint32_t i : kv.second) {
                 const JobPlan &p = b->plans[i];
                 BlurItem bi{};
                 blur_build(p.b, &btabs, &ftabs.w, &bi);
-                uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
-                bi.src = p.b.src_is_input ? ej[i].src : inter;
-                bi.src_pitch = p.b.src_is_input ? (ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels) : p.b.in_w * p.b.c;
+                b_src(i, &bi.src, &bi.src_pitch);
                 bi.dst = jobs[i].dst;
                 bi.tmp = reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off);
                 bi.aligned4 = (bi.src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(bi.src) & 3) == 0);
@@ -498,6 +516,15 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 hs.g.max_canvas_h = std::max(hs.g.max_canvas_h, bi.h);
                 hs.variant = bi.c; hs.n_items++; hs.max_band = bi.radius; hs.smem = bi.taps_pad;
                 bitems.push_back(bi);
+                if (vtc) {
+                    const int rc = blur_v_tc_build(p.b, bi.src, bi.src_pitch, bi.tmp, tcache.get(), &ftabs, &tctabs, &bvitems);
+                    if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core blur tables"); return rc; }
+                }
+            }
+            if (vtc) {
+                hv.n_items = uint32_t(bvitems.size() - hv.first);
+                for (size_t k = hv.first; k < bvitems.size(); k++) hv.smem = std::max(hv.smem, blur_v_tc_smem_bytes(bvitems[k].kg_max, bvitems[k].n_a));
+                hsteps.push_back(hv);
             }
             hsteps.push_back(hs);
         }
@@ -514,7 +541,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     const size_t off_tb = off_ti + align_up(tcitems.size() * sizeof(FusedTcItem), 256);
     const size_t off_tm = off_tb + align_up(tctabs.b.size(), 256);
     const size_t off_bi = off_tm + align_up(tcitems.size() * 128, 256);
-    const size_t meta_bytes = off_bi + align_up(bitems.size() * sizeof(BlurItem), 256) + 256;
+    const size_t off_bvi = off_bi + align_up(bitems.size() * sizeof(BlurItem), 256);
+    const size_t off_bvm = off_bvi + align_up(bvitems.size() * sizeof(BlurVTcItem), 256);
+    const size_t meta_bytes = off_bvm + align_up(bvitems.size() * 128, 256) + 256;
     b->h_meta = ctx->pinned.alloc(meta_bytes);  // pinned, kept until the batch is freed: the upload is asynchronous
     if (!b->h_meta) { set_error("fanlin: pinned allocation failed"); return FANLIN_ENOMEM; }
     struct MetaView {
@@ -525,6 +554,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     if (!tcitems.empty()) std::memcpy(meta.data() + off_ti, tcitems.data(), tcitems.size() * sizeof(FusedTcItem));
     if (!tctabs.b.empty()) std::memcpy(meta.data() + off_tb, tctabs.b.data(), tctabs.b.size());
     if (!bitems.empty()) std::memcpy(meta.data() + off_bi, bitems.data(), bitems.size() * sizeof(BlurItem));
+    if (!bvitems.empty()) std::memcpy(meta.data() + off_bvi, bvitems.data(), bvitems.size() * sizeof(BlurVTcItem));
+    for (size_t k = 0; k < bvitems.size(); k++) {
+        if (!encode_row_tile_map(meta.data() + off_bvm + k * 128, bvitems[k].src, bvitems[k].src_pitch, bvitems[k].src_h, bvitems[k].kg_max)) {
+            set_error("fanlin: cuTensorMapEncodeTiled failed");
+            return FANLIN_ECUDA;
+        }
+    }
     for (size_t k = 0; k < tcitems.size(); k++) {  // one TMA tensor map per (image, band): box rows = the band's kg_max
         if (!encode_row_tile_map(meta.data() + off_tm + k * 128, tcitems[k].src, tcitems[k].src_pitch, tcitems[k].src_h, tcitems[k].kg_max)) {
             set_error("fanlin: cuTensorMapEncodeTiled failed");
@@ -554,9 +590,21 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 st.n_items = std::min<uint32_t>(65535, hs.n_items - o);
                 st.max_w = hs.g.max_canvas_w; st.max_h = hs.g.max_canvas_h;
                 st.c = hs.variant; st.radius = hs.max_band; st.taps_pad = uint32_t(hs.smem);
+                st.n_paired = hs.n_paired;  // 1: vertical pass done on the tensor cores by the step before
                 b->steps.push_back(st);
-                b->launches_per_run += 2;
+                b->launches_per_run += hs.n_paired ? 1 : 2;
             }
+            continue;
+        }
+        if (hs.kind == 7) {
+            fanlin_batch::Step st{};
+            st.kind = 7;
+            st.bv_items = reinterpret_cast<const BlurVTcItem *>(mbase + off_bvi) + hs.first;
+            st.tmaps = mbase + off_bvm + hs.first * 128;
+            st.n_items = hs.n_items;
+            st.smem = hs.smem;
+            b->steps.push_back(st);
+            b->launches_per_run += 1;
             continue;
         }
         if (hs.kind == 3) {
@@ -611,7 +659,9 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
     }
     for (const fanlin_batch::Step &s : b->steps) {
         if (s.kind == 4) {
-            n += launch_blur(s.blur_items, s.n_items, s.max_w, s.max_h, s.c, s.radius, s.taps_pad, b->d_fw, lc);
+            n += launch_blur(s.blur_items, s.n_items, s.max_w, s.max_h, s.c, s.radius, s.taps_pad, b->d_fw, s.n_paired != 0, lc);
+        } else if (s.kind == 7) {
+            n += launch_blur_v_tc(s.bv_items, s.tmaps, s.n_items, s.smem, b->d_tb, b->d_finfo, lc);
         } else if (s.kind == 3) {
             const int k = launch_fused_tc(s.tc_items, s.tmaps, s.n_items, s.variant, s.smem, b->d_tb, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no tensor-core kernel variant"); return FANLIN_EINVAL; }

@@ -75,16 +75,18 @@ struct fanlin_batch {
     uint32_t n_jobs = 0;
     std::vector<fanlin::JobPlan> plans;
     struct Step {
-        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores), 4 blur, 5 colour pass, 6 orientation pass
+        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores), 4 blur, 5 colour pass, 6 orientation pass, 7 vertical blur (tensor cores)
         const fanlin::BlurItem *blur_items;
         uint32_t max_w, max_h, c, radius, taps_pad;
         const fanlin::FusedTcItem *tc_items;
+        const fanlin::BlurVTcItem *bv_items;
         const void *tmaps;  // CUtensorMap per tc item
         size_t smem;
         const fanlin::StageDesc *descs;
         fanlin::LaunchGeom geom;
         const fanlin::FusedItem *items;
         uint32_t n_items, variant, max_band;
+        uint32_t n_paired;  // kind 4: 1 = the vertical pass was done by a kind-7 step
     };
     std::vector<Step> steps;
     void *d_meta = nullptr;     // descriptors + tables
