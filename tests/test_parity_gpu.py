@@ -325,3 +325,24 @@ def test_concurrent_requests_are_merged_and_isolated(fanlin):
             assert hist(outs[i], O.process(imgs[i], w=64, h=48, rgb=(5, 6, 7)))[">=2"] == 0
     finally:
         d.close()
+
+
+# ---- several devices in one context (shard by image index, no collective) -----------
+
+def test_two_devices_shard_a_batch(fanlin, dev):
+    """fanlin_run on a context with two devices splits the batch into contiguous blocks
+    (fanlin_shard_range), one host thread per device; results equal the single-device ones."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    imgs = [synth_image(900 + i, 200 + 7 * (i % 3), 320, 3) for i in range(9)]
+    q = fanlin.Query("w=96&h=64&rgb=9,9,9")
+    d2 = fanlin.Device([0, 1])
+    try:
+        assert d2.device_count == 2
+        both = fanlin.process_images(d2, imgs, q)
+    finally:
+        d2.close()
+    one = fanlin.process_images(dev, imgs, q)
+    for a, b in zip(both, one):
+        assert np.array_equal(a, b)
