@@ -23,6 +23,44 @@ constexpr int HT = 256;    // horizontal kernel threads
 constexpr int H_PX = 32;   // output pixels per block row
 constexpr int J = 16;      // outputs per thread and window pass: J + 8 live values, 8 J FMAs per 8 loads
 
+// Register window along the filtered axis.  x[] is a ring of J + 8 values: phase ROT sees its
+// window start at ring index 8 * ROT, takes 8 new values into the 8 slots the previous phase
+// left behind and issues 8 J FMAs.  Three phases bring the ring back to where it started, so a
+// loop unrolled by three needs no register moves at all (shifting the window cost 16 moves per
+// 128 FMAs); taps_pad % 24 leaves one or two phases for the tail, starting again at rotation 0.
+constexpr int XW = J + 8;
+template <int ROT, typename LoadNew>
+__device__ __forceinline__ void window_phase(float (&acc)[J], float (&x)[XW], const float *w8, LoadNew load_new) {
+    const float4 w0 = *reinterpret_cast<const float4 *>(w8), w1 = *reinterpret_cast<const float4 *>(w8 + 4);
+    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[(8 * ROT + J + i) % XW] = load_new(i);
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++)
+#pragma unroll
+        for (int jj = 0; jj < J; jj++) acc[jj] = fmaf(w[kk], x[(8 * ROT + jj + kk) % XW], acc[jj]);
+}
+
+// acc[j] = sum over taps_pad taps of u[k] * value(first + j + k); value(i) for i < J is preloaded here
+template <typename Load>
+__device__ __forceinline__ void window_pass(float (&acc)[J], const float *u_s, uint32_t taps_pad, Load value) {
+    static_assert(XW == 24, "the ring returns to rotation 0 after three phases of 8");
+    float x[XW];
+#pragma unroll
+    for (int i = 0; i < J; i++) { acc[i] = 0.f; x[i] = value(uint32_t(i)); }
+    uint32_t k0 = 0;
+    for (; k0 + 24 <= taps_pad; k0 += 24) {
+        window_phase<0>(acc, x, u_s + k0, [&](int i) { return value(k0 + J + i); });
+        window_phase<1>(acc, x, u_s + k0 + 8, [&](int i) { return value(k0 + 8 + J + i); });
+        window_phase<2>(acc, x, u_s + k0 + 16, [&](int i) { return value(k0 + 16 + J + i); });
+    }
+    if (k0 < taps_pad) {
+        window_phase<0>(acc, x, u_s + k0, [&](int i) { return value(k0 + J + i); });
+        k0 += 8;
+        if (k0 < taps_pad) window_phase<1>(acc, x, u_s + k0, [&](int i) { return value(k0 + J + i); });
+    }
+}
+
 // ---- vertical pass: src u8 [h][pitch] -> tmp f32 [h][w*c] ------------------------------------
 __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__ items, const float *__restrict__ tw) {
     extern __shared__ __align__(16) float sm[];  // u[taps_pad], then tile [(V_ROWS + 2R)][VT]
@@ -76,21 +114,8 @@ __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__
     for (uint32_t p = 0; p < V_ROWS / J; p++) {
         const uint32_t j0 = y0 + J * p;
         if (j0 >= it.h) break;
-        float acc[J], x[J + 8];
-#pragma unroll
-        for (int i = 0; i < J; i++) { acc[i] = 0.f; x[i] = col[size_t(J * p + i) * VT]; }
-        for (uint32_t k0 = 0; k0 < taps_pad; k0 += 8) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(u_s + k0), w1 = *reinterpret_cast<const float4 *>(u_s + k0 + 4);
-            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-            for (int i = 0; i < 8; i++) x[J + i] = col[size_t(J * p + k0 + J + i) * VT];
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++)
-#pragma unroll
-                for (int jj = 0; jj < J; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
-#pragma unroll
-            for (int i = 0; i < J; i++) x[i] = x[8 + i];
-        }
+        float acc[J];
+        window_pass(acc, u_s, taps_pad, [&](uint32_t i) { return col[size_t(J * p + i) * VT]; });
         if (e < n_e) {
 #pragma unroll
             for (int jj = 0; jj < J; jj++)
@@ -155,21 +180,8 @@ __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__
         const uint32_t r = t / C, ch = t - r * C;
         const float *rowp = tile + size_t(r) * pitch + ch;
         for (uint32_t p = 0; p < H_PX / J; p++) {
-            float acc[J], x[J + 8];
-#pragma unroll
-            for (int i = 0; i < J; i++) { acc[i] = 0.f; x[i] = rowp[size_t(J * p + i) * C]; }
-            for (uint32_t k0 = 0; k0 < taps_pad; k0 += 8) {
-                const float4 w0 = *reinterpret_cast<const float4 *>(u_s + k0), w1 = *reinterpret_cast<const float4 *>(u_s + k0 + 4);
-                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-                for (int i = 0; i < 8; i++) x[J + i] = rowp[size_t(J * p + k0 + J + i) * C];
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++)
-#pragma unroll
-                    for (int jj = 0; jj < J; jj++) acc[jj] = fmaf(w[kk], x[jj + kk], acc[jj]);
-#pragma unroll
-                for (int i = 0; i < J; i++) x[i] = x[8 + i];
-            }
+            float acc[J];
+            window_pass(acc, u_s, taps_pad, [&](uint32_t i) { return rowp[size_t(J * p + i) * C]; });
 #pragma unroll
             for (int jj = 0; jj < J; jj++) {
                 const float cf = corr_s[J * p + jj];

@@ -93,6 +93,13 @@ def main():
         rec = dict(config=name, query=qs, batch=n, ms=ms, us_per_image=ms * 1e3 / n, out_mpix_s=n * plan.out_w * plan.out_h / 1e6 / (ms * 1e-3),
                    hbm_frac=alg / (ms * 1e-3) / 1e9 / peak, kernels_ms={k: sum(v) / len(v) for k, v in kt.items()},
                    parity=dict(diff1=int((d == 1).sum()), diff_ge2=int((d >= 2).sum()), n=int(d.size)))
+        if q.blur() and not gif:
+            # blur is FP32-bound in direct form -- report it against the FP32 FMA peak too
+            # (148 SMs x 128 FMA/clk x 1.965 GHz); the vertical pass runs on the tensor cores where eligible
+            taps = 2 * int(2 * q.blur()) + 1
+            fma = 2.0 * taps * plan.out_w * plan.out_h * plan.out_channels * n
+            blur_ms = sum(v for k, v in rec["kernels_ms"].items() if k.startswith("blur_"))
+            rec["blur"] = dict(taps=taps, ms=blur_ms, fp32_fma_frac=fma / (blur_ms * 1e-3) / (148 * 128 * 1.965e9))
         print(json.dumps(rec), flush=True)
         out.append(rec)
         b.free()
