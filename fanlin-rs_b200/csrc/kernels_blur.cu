@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(VT) blur_v_kernel(const BlurItem *__restrict__
 }
 
 // ---- horizontal pass: tmp f32 [h][w*c] -> dst u8 [h][w*c] --------------------------------------
+template <uint32_t C>  // channels: the window's loads are rowp[i * C], constant offsets once C is known
 __global__ void __launch_bounds__(HT) blur_h_kernel(const BlurItem *__restrict__ items, const float *__restrict__ tw) {
     extern __shared__ __align__(16) float sm[];  // u[taps_pad], tile [rb][pitch], then the u8 output tile
     const BlurItem it = items[blockIdx.z];
-    const uint32_t C = it.c;
-    const uint32_t rb = HT / C;  // rows per block
+    constexpr uint32_t rb = HT / C;  // rows per block
     const uint32_t x0 = blockIdx.x * H_PX, y0 = blockIdx.y * rb;
     if (x0 >= it.w || y0 >= it.h) return;
     const uint32_t R = it.radius, taps_pad = it.taps_pad;
@@ -213,7 +213,8 @@ int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint3
     if (n_items == 0) return 0;
     const size_t sv = blur_v_smem(radius, taps_pad), sh = blur_h_smem(radius, taps_pad, c);
     cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv));
-    cudaFuncSetAttribute(blur_h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sh));
+    auto hk = c == 1 ? blur_h_kernel<1> : c == 2 ? blur_h_kernel<2> : c == 3 ? blur_h_kernel<3> : blur_h_kernel<4>;
+    cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sh));
     const uint32_t rb = HT / c;
     if (!skip_v) {  // else the f32 intermediate was written by blur_v_tc_kernel
         lc.begin("blur_v_kernel");
@@ -221,7 +222,7 @@ int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint3
         lc.end();
     }
     lc.begin("blur_h_kernel");
-    blur_h_kernel<<<dim3((max_w + H_PX - 1) / H_PX, (max_h + rb - 1) / rb, n_items), HT, sh, lc.st>>>(d_items, d_w);
+    hk<<<dim3((max_w + H_PX - 1) / H_PX, (max_h + rb - 1) / rb, n_items), HT, sh, lc.st>>>(d_items, d_w);
     lc.end();
     return skip_v ? 1 : 2;
 }
