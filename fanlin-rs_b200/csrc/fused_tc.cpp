@@ -260,6 +260,14 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
         ok = build_band(*s.vtab, s.oy0, b0, std::min(band_rows, s.n_rows - b0), sh, 8, tabs, tct, &bt);
         g.bands.push_back(bt);
     }
+    // An odd staging stride keeps the rows of a warp on distinct banks (a multiple of 16 words is a 4-way conflict
+    // on every staged pixel); taken unless the extra word per row costs a band a source slot (C2 is that tight).
+    if (ok && !(g.out_stride & 1)) {
+        bool same = true;
+        for (const TcBand &bt : g.bands)
+            same = same && fused_tc_source_slots(s.c, bt.rows, bt.kg_max, g.out_stride + 1) == fused_tc_source_slots(s.c, bt.rows, bt.kg_max, g.out_stride);
+        if (same) g.out_stride++;
+    }
     g.ok = ok;
     return cache->geoms.emplace(key, std::move(g)).first->second;
 }
