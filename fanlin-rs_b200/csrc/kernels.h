@@ -64,6 +64,8 @@ int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n
                      const uint32_t *d_info, LaunchCtx &lc);
 // Colour op alone over the needed source rows (in front of the tensor-core resample).
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+// DynamicImage::to_rgb8 of the final image (FANLIN_TO_RGB8), scratch -> dst.
+int launch_to_rgb8(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 // EXIF orientation (+ colour op) of the stored image into scratch, in front of every other stage.
 int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 

@@ -8,6 +8,8 @@
 #include "device_common.cuh"
 #include "kernels.h"
 
+#include <algorithm>
+
 namespace fanlin {
 
 namespace {
@@ -124,6 +126,19 @@ __global__ void __launch_bounds__(256) color_pass_kernel(const StageDesc *__rest
     }
 }
 
+// DynamicImage::to_rgb8 of the final image (handler.rs:274-278, the JPEG branch): src [h][w][c] -> dst
+// [h][w][3], alpha dropped, luma replicated.  The output of the stage is small; one thread per pixel.
+__global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restrict__ descs) {
+    const StageDesc &d = descs[blockIdx.y];
+    const uint32_t n = d.canvas_w * d.canvas_h, c = d.c_mem;
+    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const uint8_t *p = d.src + size_t(i) * c;
+        uint8_t *o = d.dst + size_t(i) * 3;
+        const uint8_t r = p[0], g = c <= 2 ? r : p[1], b = c <= 2 ? r : p[2];
+        o[0] = r; o[1] = g; o[2] = b;
+    }
+}
+
 // EXIF orientation (+ colour op) of the stored image: oriented rows [oy0, oy0 + n_rows) -> dst rows
 // [0, n_rows).  Orientation::from_exif / apply_orientation of the image crate (handler.rs:221-223):
 //   2 flip horizontal, 3 rotate 180, 4 flip vertical, 5 transpose (rotate90 + flip_horizontal),
@@ -215,6 +230,15 @@ int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx 
     lc.begin("orient_pass_kernel");
     // tiles are 32 x 64 or 64 x 32 (axes swapped); the grid covers the larger count either way
     orient_pass_kernel<<<dim3((g.max_canvas_w + 31) / 32, (g.max_canvas_h + 31) / 32, g.n_jobs), 256, 0, lc.st>>>(d_descs);
+    lc.end();
+    return 1;
+}
+
+int launch_to_rgb8(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
+    if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;
+    const uint32_t blocks = std::min<uint32_t>(1024, (g.max_canvas_w * g.max_canvas_h + 255) / 256);
+    lc.begin("to_rgb8_kernel");
+    to_rgb8_kernel<<<dim3(blocks, g.n_jobs), 256, 0, lc.st>>>(d_descs);
     lc.end();
     return 1;
 }

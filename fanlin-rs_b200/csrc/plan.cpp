@@ -165,7 +165,8 @@ static uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; 
 
 int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
     if (job.orientation > 8) { set_error("fanlin: orientation must be an EXIF value 0..8"); return FANLIN_EINVAL; }
-    if (job.orientation >= 2 && !(job.flags & FANLIN_TO_RGBA8)) {
+    if ((job.flags & FANLIN_TO_RGBA8) && (job.flags & FANLIN_TO_RGB8)) { set_error("fanlin: TO_RGBA8 and TO_RGB8 exclude each other"); return FANLIN_EINVAL; }
+    if (job.orientation >= 2) {
         // Orientation::from_exif + apply_orientation: 5..8 swap width and height.  Plan the request as it
         // looks behind the orientation pass, which also applies the colour op.
         if (job.src_w == 0 || job.src_h == 0 || job.src_channels < 1 || job.src_channels > 4) {
@@ -321,6 +322,11 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
             b.vtab = build_axis_table(KIND_GAUSSIAN, b.sigma, img_h, img_h);
             b.htab = build_axis_table(KIND_GAUSSIAN, b.sigma, img_w, img_w);
         }
+    }
+    if ((job.flags & FANLIN_TO_RGB8) && img_c != 3) {  // DynamicImage::to_rgb8 as a last pass over the (small) output
+        p.post_c_in = img_c;
+        img_c = 3;
+        pub.stages |= 32u;
     }
     pub.out_w = img_w;
     pub.out_h = img_h;

@@ -61,6 +61,7 @@ struct OrientPlan {
 struct JobPlan {
     fanlin_plan pub{};
     OrientPlan pre;
+    uint32_t post_c_in = 0;  // FANLIN_TO_RGB8: channels of the final image before to_rgb8 (0: no conversion pass)
     StagePlan a;  // colour op + resample + letterbox (+ to_rgba8), or compose
     StagePlan b;  // blur
 };

@@ -198,8 +198,8 @@ extern "C" void fanlin_host_free(fanlin_ctx *ctx, void *p) {
 namespace {
 
 struct JobScratch {
-    size_t pre = 0, inter = 0, tmp = 0;               // bytes
-    size_t pre_off = 0, inter_off = 0, tmp_off = 0;   // offsets inside the chunk's scratch
+    size_t pre = 0, inter = 0, tmp = 0, fin = 0;                  // bytes
+    size_t pre_off = 0, inter_off = 0, tmp_off = 0, fin_off = 0;  // offsets inside the chunk's scratch
 };
 
 void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t *inter, float *tmp,
@@ -358,7 +358,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
             if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of either blur path
             js[i].tmp = align_up(std::max(ta, tb), 256);
-            const size_t need = js[i].pre + js[i].inter + js[i].tmp;
+            if (p.post_c_in) js[i].fin = align_up(size_t(p.pub.out_w) * p.pub.out_h * p.post_c_in, 256);  // the final image before to_rgb8
+            const size_t need = js[i].pre + js[i].inter + js[i].tmp + js[i].fin;
             if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
                 chunk_end.push_back(i);
                 cur = 0;
@@ -366,6 +367,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             js[i].pre_off = cur;
             js[i].inter_off = cur + js[i].pre;
             js[i].tmp_off = cur + js[i].pre + js[i].inter;
+            js[i].fin_off = js[i].tmp_off + js[i].tmp;
             cur += need;
             scratch_bytes = std::max(scratch_bytes, cur);
         }
@@ -375,6 +377,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     if (scratch_bytes) CUDA_TRY(cudaMallocAsync(&b->d_scratch, scratch_bytes, up_stream));  // stream-ordered pool: no device sync
     for (uint32_t i = 0; i < n_jobs; i++)
         if (b->plans[i].pre.present) ej[i].src = static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off;
+    for (uint32_t i = 0; i < n_jobs; i++)  // FANLIN_TO_RGB8: the stages write the final image to scratch, a last pass converts it into dst
+        if (b->plans[i].post_c_in) ej[i].dst = static_cast<uint8_t *>(b->d_scratch) + js[i].fin_off;
 
     // 3. descriptors per chunk and stage kind
     std::vector<StageDesc> descs;
@@ -439,7 +443,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const bool pre = a_pre[i].present;
                 const uint8_t *tsrc = pre ? static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off : ej[i].src;
                 const uint32_t pitch = pre ? a_pre[i].in_pitch : ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
-                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, p.b.present ? inter : jobs[i].dst, tcache.get(), &ftabs,
+                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, p.b.present ? inter : ej[i].dst, tcache.get(), &ftabs,
                                               &tctabs, &tcitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core tables"); return rc; }
             }
@@ -454,7 +458,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 const uint32_t pitch = ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
-                const int rc = fused_build(p.a, ej[i].src, pitch, p.b.present ? inter : jobs[i].dst, fcache.get(), &ftabs, &fitems);
+                const int rc = fused_build(p.a, ej[i].src, pitch, p.b.present ? inter : ej[i].dst, fcache.get(), &ftabs, &fitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: fused tables"); return rc; }
             }
             hs.n_items = uint32_t(fitems.size() - hs.first);
@@ -509,7 +513,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 BlurItem bi{};
                 blur_build(p.b, &btabs, &ftabs.w, &bi);
                 b_src(i, &bi.src, &bi.src_pitch);
-                bi.dst = jobs[i].dst;
+                bi.dst = ej[i].dst;
                 bi.tmp = reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off);
                 bi.aligned4 = (bi.src_pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(bi.src) & 3) == 0);
                 hs.g.max_canvas_w = std::max(hs.g.max_canvas_w, bi.w);
@@ -527,6 +531,22 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 hsteps.push_back(hv);
             }
             hsteps.push_back(hs);
+        }
+        {  // FANLIN_TO_RGB8: the last pass, scratch -> dst
+            HostStep hs{8, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+            for (uint32_t i = begin; i < end; i++) {
+                const JobPlan &p = b->plans[i];
+                if (!p.post_c_in) continue;
+                StageDesc d;
+                std::memset(&d, 0, sizeof(d));
+                d.src = ej[i].dst; d.dst = jobs[i].dst;
+                d.c_mem = p.post_c_in; d.c = 3; d.c_out = 3;
+                d.canvas_w = p.pub.out_w; d.canvas_h = p.pub.out_h;
+                d.v_tab = d.h_tab = NO_TABLE;
+                geom_add(&hs.g, d);
+                descs.push_back(d);
+            }
+            if (hs.g.n_jobs) hsteps.push_back(hs);
         }
         begin = end;
     }
@@ -670,7 +690,8 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
             const int k = launch_fused(s.items, s.n_items, s.variant, s.max_band, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no fused kernel variant"); return FANLIN_EINVAL; }
             n += k;
-        } else if (s.kind == 6) n += launch_orient_pass(s.descs, s.geom, lc);
+        } else if (s.kind == 8) n += launch_to_rgb8(s.descs, s.geom, lc);
+        else if (s.kind == 6) n += launch_orient_pass(s.descs, s.geom, lc);
         else if (s.kind == 5) n += launch_color_pass(s.descs, s.geom, lc);
         else if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
         else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, lc);

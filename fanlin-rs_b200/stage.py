@@ -21,13 +21,19 @@ def _as_img(a) -> np.ndarray:
     return a
 
 
-def make_job(img: np.ndarray, params: Query, *, gif: bool = False, orientation: int = 1) -> Job:
+TO_RGB8 = 1 << 5  # enum fanlin_flags FANLIN_TO_RGB8
+
+
+def make_job(img: np.ndarray, params: Query, *, gif: bool = False, orientation: int = 1, to_rgb8: bool = False) -> Job:
     """orientation: the EXIF value decoder.orientation() reported for a still (src/handler.rs:206);
-    the device turns the image instead of img.apply_orientation(o) on the host (:221-223)."""
+    the device turns the image instead of img.apply_orientation(o) on the host (:221-223).
+    to_rgb8: the caller will encode JPEG (:274-278) and wants the RGB8 the encoder works on."""
     a = _as_img(img)
     j = Job()
     lib().fanlin_job_from_query(C.byref(params._q), int(gif), C.byref(j))
     j.orientation = int(orientation)
+    if to_rgb8:
+        j.flags |= TO_RGB8
     j.src = a.ctypes.data
     j.src_h, j.src_w, j.src_channels = a.shape
     j._keep = a
@@ -48,10 +54,10 @@ def _run(dev: Device, jobs):
     return outs
 
 
-def process_image(dev: Device, img: np.ndarray, params: Query, *, orientation: int = 1) -> np.ndarray:
+def process_image(dev: Device, img: np.ndarray, params: Query, *, orientation: int = 1, to_rgb8: bool = False) -> np.ndarray:
     """Pixel section of State::process_image: decoded pixels (as stored, with their EXIF
-    orientation) in, transformed pixels out."""
-    return _run(dev, [make_job(img, params, orientation=orientation)])[0]
+    orientation) in, transformed pixels out (RGB8 when the JPEG encoder follows)."""
+    return _run(dev, [make_job(img, params, orientation=orientation, to_rgb8=to_rgb8)])[0]
 
 
 def process_images(dev: Device, imgs, params: Query):

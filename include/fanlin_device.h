@@ -50,7 +50,9 @@ enum fanlin_flags {
     FANLIN_INVERSE = 1u << 1,   /* Query::inverse()    src/query.rs:68-70 */
     FANLIN_HAS_DIMS = 1u << 2,  /* Query::dimensions() is Some((req_w, req_h))  src/query.rs:28-33 */
     FANLIN_CROP = 1u << 3,      /* Query::cropping()   src/query.rs:55-57 -> resize_to_fill */
-    FANLIN_TO_RGBA8 = 1u << 4   /* GIF frames end with img.to_rgba8()  src/handler.rs:355 */
+    FANLIN_TO_RGBA8 = 1u << 4,  /* GIF frames end with img.to_rgba8()  src/handler.rs:355; also the WebP branch's into_rgba8() (:287) */
+    FANLIN_TO_RGB8 = 1u << 5    /* the JPEG branch: the encoder works on RGB8 (src/handler.rs:274-278), DynamicImage::to_rgb8 --
+                                   alpha dropped, luma replicated; not together with FANLIN_TO_RGBA8 */
 };
 
 /* One image (still) or one composited GIF frame and the request parameters the
@@ -67,7 +69,7 @@ typedef struct fanlin_job {
     uint8_t fill_rgb[3];   /* Query::fill_color()  src/query.rs:35-49 */
     uint8_t orientation;   /* EXIF orientation of a decoded still: 0 / 1 = none, 2..8 as ImageDecoder::orientation()
                               reports it; replaces img.apply_orientation(o) at src/handler.rs:206,221-223.  The source
-                              fields describe the image as stored; the stage sees it oriented.  Ignored for GIF frames
+                              fields describe the image as stored; the stage sees it oriented.  Leave it 0 on the GIF path
                               (process_gif never reads EXIF). */
     float blur_sigma;      /* Query::blur(): 0 = off, else already clamped to [10,20]  src/query.rs:59-62 */
     uint8_t *dst;          /* host (fanlin_run) or device (fanlin_batch_*) pointer, tight rows */
@@ -82,7 +84,7 @@ typedef struct fanlin_plan {
     uint32_t crop_x, crop_y;       /* resize_to_fill crop origin inside the resized image */
     uint32_t overlay_x, overlay_y; /* letterbox offset (handler.rs:244-245) */
     uint32_t src_x0, src_y0, src_x1, src_y1; /* source window the output depends on (in the oriented image) */
-    uint32_t stages;               /* bit0 colour op, bit1 resample, bit2 letterbox, bit3 blur, bit4 to_rgba8 */
+    uint32_t stages;               /* bit0 colour op, bit1 resample, bit2 letterbox, bit3 blur, bit4 to_rgba8, bit5 to_rgb8 */
     uint64_t out_bytes;
     uint64_t algorithmic_bytes;    /* src window bytes + out_bytes */
 } fanlin_plan;

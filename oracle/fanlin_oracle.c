@@ -43,7 +43,8 @@ enum {
     FO_INVERSE = 1u << 1,
     FO_HAS_DIMS = 1u << 2,
     FO_CROP = 1u << 3,
-    FO_GIF_FRAME = 1u << 4
+    FO_GIF_FRAME = 1u << 4,
+    FO_TO_RGB8 = 1u << 5 /* still handed to the JPEG encoder: DynamicImage::to_rgb8 (handler.rs:274-278 drops alpha) */
 };
 
 /* One request, the fields of query::Query the stage reads (src/query.rs:28-70)
@@ -329,6 +330,16 @@ static void to_rgba(const uint8_t *p, uint32_t c, uint8_t o[4]) {
 }
 
 /* DynamicImage::to_rgba8 */
+/* DynamicImage::to_rgb8: L -> (l,l,l), La -> (l,l,l), Rgb -> itself, Rgba -> (r,g,b); alpha is dropped, not blended */
+void fo_to_rgb8(const uint8_t *src, size_t npix, uint32_t c, uint8_t *dst) {
+    for (size_t i = 0; i < npix; i++) {
+        const uint8_t *p = src + i * c;
+        uint8_t *o = dst + i * 3;
+        if (c <= 2) { o[0] = o[1] = o[2] = p[0]; }
+        else { o[0] = p[0]; o[1] = p[1]; o[2] = p[2]; }
+    }
+}
+
 void fo_to_rgba8(const uint8_t *src, size_t npix, uint32_t c, uint8_t *dst) {
     for (size_t i = 0; i < npix; i++) to_rgba(src + i * c, c, dst + 4 * i);
 }
@@ -552,6 +563,14 @@ int fo_process(fo_job *job) {
         free(img);
         img = r;
         c = 4;
+    }
+    if (!gif && (job->flags & FO_TO_RGB8) && c != 3) { /* the JPEG branch: the encoder works on RGB8 */
+        uint8_t *r = (uint8_t *)malloc((size_t)w * h * 3);
+        if (!r) { free(img); return FO_ENOMEM; }
+        fo_to_rgb8(img, (size_t)w * h, c, r);
+        free(img);
+        img = r;
+        c = 3;
     }
 
     job->out_w = w;

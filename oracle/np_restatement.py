@@ -224,7 +224,7 @@ def apply_orientation(img, exif):
 
 
 def process(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur_sigma=0.0, gray=False,
-            inverse=False, gif=False, orientation=1):
+            inverse=False, gif=False, orientation=1, to_rgb8=False):
     if img.ndim == 2:
         img = img[:, :, None]
     kind = "nearest" if gif else "lanczos3"
@@ -258,4 +258,6 @@ def process(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur_sigma=0.0
         img = blur(img, blur_sigma)
     if gif:
         img = to_rgba8(img)
+    elif to_rgb8 and img.shape[2] != 3:  # DynamicImage::to_rgb8: alpha dropped, luma replicated
+        img = np.repeat(img[:, :, :1], 3, axis=2) if img.shape[2] <= 2 else img[:, :, :3]
     return np.ascontiguousarray(img)

@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libfanlin_oracle.so")
 
 NEAREST, LANCZOS3, GAUSSIAN_BLUR = 0, 1, 100
-GRAYSCALE, INVERSE, HAS_DIMS, CROP, GIF_FRAME = 1, 2, 4, 8, 16
+GRAYSCALE, INVERSE, HAS_DIMS, CROP, GIF_FRAME, TO_RGB8 = 1, 2, 4, 8, 16, 32
 
 
 class Job(C.Structure):
@@ -152,7 +152,7 @@ def weight_table(kind, n_in, n_out, sigma=0.0):
 
 
 def make_job(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0, grayscale=False,
-             inverse=False, gif=False, orientation=1):
+             inverse=False, gif=False, orientation=1, to_rgb8=False):
     """Job from the accessor values of query::Query (src/query.rs:28-70)."""
     a = _img(img)
     j = Job()
@@ -170,6 +170,8 @@ def make_job(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0, gra
         fl |= CROP
     if gif:
         fl |= GIF_FRAME
+    if to_rgb8:
+        fl |= TO_RGB8
     j.flags = fl
     j.fill[0], j.fill[1], j.fill[2] = rgb
     j.blur_sigma = float(blur)

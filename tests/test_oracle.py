@@ -219,3 +219,20 @@ def test_orientation_then_pipeline(exif):
     assert np.array_equal(a, b)
     n = N.process(img, w=40, h=30, rgb=(1, 2, 3), gray=True, orientation=exif)
     assert np.array_equal(a, n)
+
+
+# ---- encoder layout: RGB8 for the JPEG branch (handler.rs:274-278) ------------
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4])
+def test_to_rgb8_known_answers_and_restatements(c):
+    img = synth_image(60 + c, 9, 13, c)
+    a = O.process(img, to_rgb8=True)
+    assert a.shape == (9, 13, 3)
+    if c <= 2:
+        assert all(np.array_equal(a[:, :, k], img[:, :, 0]) for k in range(3))  # luma replicated, alpha dropped
+    else:
+        assert np.array_equal(a, img[:, :, :3])
+    b = O.process(img, w=20, h=20, rgb=(7, 8, 9), to_rgb8=True)  # letterboxed RGBA canvas -> RGB
+    full = O.process(img, w=20, h=20, rgb=(7, 8, 9))
+    assert np.array_equal(b, full[:, :, :3])
+    assert np.array_equal(b, N.process(img, w=20, h=20, rgb=(7, 8, 9), to_rgb8=True))

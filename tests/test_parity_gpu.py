@@ -238,21 +238,49 @@ def test_orientation_on_device(fanlin, dev, dev_cuda_cores, dev_exact, exif, h, 
         assert hh[">=2"] == 0 and hh[1] <= 0.002 * want.size + 2, (name, hh)
 
 
-def test_orientation_rejects_bad_value_and_ignores_gif_frames(fanlin, dev):
+def test_orientation_rejects_bad_value_and_composes_with_frame_flags(fanlin, dev):
     img = synth_image(5, 20, 30, 4)
     j = fanlin.make_job(img, fanlin.Query("w=10&h=10"), orientation=9)
     o = np.zeros(10 * 10 * 4, np.uint8)
     j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
     with pytest.raises(fanlin.FanlinError):
         dev.run([j])
-    # process_gif never reads EXIF: a frame job with an orientation is processed as stored
+    # the field is honoured whenever it is set (process_gif simply never sets it): a frame-style job
+    # (Nearest, to_rgba8) with orientation 6 equals the frame job of the image turned on the host
     q = fanlin.Query("w=10&h=10")
-    a = fanlin.process_gif_frames(dev, [img], q)[0]
+    want = fanlin.process_gif_frames(dev, [np.ascontiguousarray(O.apply_orientation(img, 6))], q)[0]
     j2 = fanlin.make_job(img, q, gif=True, orientation=6)
-    o2 = np.zeros(a.size, np.uint8)
+    o2 = np.zeros(want.size, np.uint8)
     j2.dst, j2.dst_capacity = o2.ctypes.data, o2.nbytes
     dev.run([j2])
-    assert np.array_equal(o2.reshape(a.shape), a)
+    assert np.array_equal(o2.reshape(want.shape), want)
+
+
+# ---- encoder layout: RGB8 for the JPEG branch (handler.rs:274-278) ------------
+
+RGB8_CASES = [
+    (90, 120, 3, "w=64&h=64&rgb=3,4,5"),             # letterboxed RGBA canvas -> RGB
+    (90, 120, 4, "w=64&h=40&crop=true"),             # RGBA with real alpha: dropped, not blended
+    (90, 120, 1, "w=50&h=50&crop=true&blur=10"),     # L8 -> (l,l,l) after the blur
+    (60, 80, 2, "inverse=true"),                     # La8, no resize
+    (200, 300, 3, "w=100&h=80&crop=true"),           # already RGB: no pass
+]
+
+
+@pytest.mark.parametrize("h,w,c,qs", RGB8_CASES, ids=[f"{p[0]}x{p[1]}x{p[2]}-{p[3]}" for p in RGB8_CASES])
+def test_to_rgb8_output(fanlin, dev, dev_exact, h, w, c, qs):
+    img = synth_image(610 + c, h, w, c)
+    q = fanlin.Query(qs)
+    kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+    if q.dimensions() is not None:
+        kw["w"], kw["h"] = q.dimensions()
+    want = O.process(img, to_rgb8=True, orientation=8, **kw)
+    assert want.shape[2] == 3
+    exact = fanlin.process_image(dev_exact, img, q, orientation=8, to_rgb8=True)
+    assert exact.shape == want.shape and np.array_equal(exact, want)
+    got = fanlin.process_image(dev, img, q, orientation=8, to_rgb8=True)
+    hh = hist(got, want)
+    assert got.shape == want.shape and hh[">=2"] == 0 and hh[1] <= 0.002 * want.size + 2, hh
 
 
 # ---- same-shaped images in one launch --------------------------------------------------------
