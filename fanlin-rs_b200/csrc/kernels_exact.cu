@@ -89,40 +89,59 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
 }
 
 // Colour op alone (grayscale / inverse), source rows [oy0, oy0 + n_rows) -> dst rows [0, n_rows):
-// the pass in front of the tensor-core resample.  Four pixels per thread through 32-bit words
-// when the rows are word-aligned (HBM-bound: c_mem + c bytes per pixel).
+// the pass in front of the tensor-core resample.  Four pixels of each of CP_ROWS rows per thread
+// through 32-bit words when the rows are word-aligned, all loads issued before the first store
+// (HBM-bound: c_mem + c bytes per pixel; one row per thread was bound by the load latency).
+constexpr uint32_t CP_ROWS = 8;
 __global__ void __launch_bounds__(256) color_pass_kernel(const StageDesc *__restrict__ descs) {
-    const StageDesc d = descs[blockIdx.z];
-    const uint32_t row = blockIdx.y, x = (blockIdx.x * 256 + threadIdx.x) * 4;
-    if (row >= d.n_rows || x >= d.src_w) return;
-    const uint8_t *sp = d.src + size_t(d.oy0 + row) * d.src_pitch + size_t(x) * d.c_mem;
-    uint8_t *dp = d.dst + size_t(row) * d.dst_pitch + size_t(x) * d.c;
-    const bool words = x + 4 <= d.src_w && ((reinterpret_cast<uintptr_t>(sp) | reinterpret_cast<uintptr_t>(dp)) & 3) == 0;
+    const StageDesc &d = descs[blockIdx.z];
+    const uint32_t row0 = blockIdx.y * CP_ROWS, x = (blockIdx.x * 256 + threadIdx.x) * 4;
+    const uint32_t n_rows = d.n_rows, w = d.src_w, c_mem = d.c_mem, c = d.c, op = d.color_op;
+    if (row0 >= n_rows || x >= w) return;
+    const uint8_t *sp0 = d.src + size_t(d.oy0 + row0) * d.src_pitch + size_t(x) * c_mem;
+    uint8_t *dp0 = d.dst + size_t(row0) * d.dst_pitch + size_t(x) * c;
+    const uint32_t sp = d.src_pitch, dpp = d.dst_pitch;
+    const bool words = x + 4 <= w && ((reinterpret_cast<uintptr_t>(sp0) | reinterpret_cast<uintptr_t>(dp0) | sp | dpp) & 3) == 0;
     if (!words) {  // row tail or unaligned rows
-        for (uint32_t q = 0; q < 4 && x + q < d.src_w; q++) {
-            uint32_t v[4] = {0, 0, 0, 0};
-            load_px(d, x + q, d.oy0 + row, v);
-            for (uint32_t k = 0; k < d.c; k++) dp[q * d.c + k] = uint8_t(v[k]);
-        }
+        const StageDesc dd = d;
+        for (uint32_t r = 0; r < CP_ROWS && row0 + r < n_rows; r++)
+            for (uint32_t q = 0; q < 4 && x + q < w; q++) {
+                uint32_t v[4] = {0, 0, 0, 0};
+                load_px(dd, x + q, dd.oy0 + row0 + r, v);
+                for (uint32_t k = 0; k < c; k++) dp0[size_t(r) * dpp + q * c + k] = uint8_t(v[k]);
+            }
         return;
     }
-    const uint32_t *sw = reinterpret_cast<const uint32_t *>(sp);
-    uint32_t *dw = reinterpret_cast<uint32_t *>(dp);
-    if (d.color_op == COLOR_INVERT) {  // c_mem == c words in, c words out; alpha (LA / RGBA) stays
-        const uint32_t mask = d.c == 2 ? 0x00ff00ffu : d.c == 4 ? 0x00ffffffu : 0xffffffffu;
-        for (uint32_t k = 0; k < d.c; k++) dw[k] = __ldg(sw + k) ^ mask;
-    } else if (d.c_mem == 3) {  // RGB -> L: 12 bytes in, 4 out
-        const uint32_t a = __ldg(sw), b = __ldg(sw + 1), c = __ldg(sw + 2);
-        dw[0] = luma_u8(a & 255, (a >> 8) & 255, (a >> 16) & 255) | luma_u8(a >> 24, b & 255, (b >> 8) & 255) << 8 |
-                luma_u8((b >> 16) & 255, b >> 24, c & 255) << 16 | luma_u8((c >> 8) & 255, (c >> 16) & 255, c >> 24) << 24;
-    } else {  // RGBA -> LA: 16 bytes in, 8 out
-        uint32_t o[2] = {0, 0};
+    uint32_t in[CP_ROWS][4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t p = __ldg(sw + q);
-            o[q / 2] |= (luma_u8(p & 255, (p >> 8) & 255, (p >> 16) & 255) | (p >> 24) << 8) << (16 * (q & 1));
+    for (uint32_t r = 0; r < CP_ROWS; r++) {
+        const uint32_t *sw = reinterpret_cast<const uint32_t *>(sp0 + size_t(r) * sp);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) in[r][k] = (row0 + r < n_rows && k < c_mem) ? __ldg(sw + k) : 0u;
+    }
+#pragma unroll
+    for (uint32_t r = 0; r < CP_ROWS; r++) {
+        if (row0 + r >= n_rows) break;
+        uint32_t *dw = reinterpret_cast<uint32_t *>(dp0 + size_t(r) * dpp);
+        const uint32_t *i4 = in[r];
+        if (op == COLOR_INVERT) {  // c_mem == c words in, c words out; alpha (LA / RGBA) stays
+            const uint32_t mask = c == 2 ? 0x00ff00ffu : c == 4 ? 0x00ffffffu : 0xffffffffu;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+                if (k < c) dw[k] = i4[k] ^ mask;
+        } else if (c_mem == 3) {  // RGB -> L: 12 bytes in, 4 out
+            const uint32_t a = i4[0], b = i4[1], cc = i4[2];
+            dw[0] = luma_u8(a & 255, (a >> 8) & 255, (a >> 16) & 255) | luma_u8(a >> 24, b & 255, (b >> 8) & 255) << 8 |
+                    luma_u8((b >> 16) & 255, b >> 24, cc & 255) << 16 | luma_u8((cc >> 8) & 255, (cc >> 16) & 255, cc >> 24) << 24;
+        } else {  // RGBA -> LA: 16 bytes in, 8 out
+            uint32_t o[2] = {0, 0};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t p = i4[q];
+                o[q / 2] |= (luma_u8(p & 255, (p >> 8) & 255, (p >> 16) & 255) | (p >> 24) << 8) << (16 * (q & 1));
+            }
+            dw[0] = o[0]; dw[1] = o[1];
         }
-        dw[0] = o[0]; dw[1] = o[1];
     }
 }
 
@@ -246,7 +265,7 @@ int launch_to_rgb8(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc)
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;
     lc.begin("color_pass_kernel");
-    color_pass_kernel<<<dim3((g.max_canvas_w + 1023) / 1024, g.max_canvas_h, g.n_jobs), 256, 0, lc.st>>>(d_descs);
+    color_pass_kernel<<<dim3((g.max_canvas_w + 1023) / 1024, (g.max_canvas_h + CP_ROWS - 1) / CP_ROWS, g.n_jobs), 256, 0, lc.st>>>(d_descs);
     lc.end();
     return 1;
 }
