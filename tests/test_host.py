@@ -159,3 +159,44 @@ def test_plan_rejects_bad_jobs(fanlin):
     j.src_w, j.src_channels = 10, 5
     with pytest.raises(fanlin.FanlinError):
         fanlin.plan_job(j)
+
+
+def _job(fanlin, w, h, c, qs, gif=False):
+    j = fanlin.Job()
+    q = fanlin.Query(qs)
+    fanlin.lib().fanlin_job_from_query(C.byref(q._q), int(gif), C.byref(j))
+    j.src_w, j.src_h, j.src_channels = w, h, c
+    return j
+
+
+@pytest.mark.parametrize("exif", range(0, 9))
+def test_plan_sees_the_oriented_image(fanlin, exif):
+    """EXIF 5..8 swap width and height before anything else (apply_orientation, handler.rs:221-223):
+    the plan of a stored 400x300 image with orientation e equals the plan of the turned image."""
+    j = _job(fanlin, 400, 300, 3, "w=100&h=100&rgb=1,2,3")
+    j.orientation = exif
+    p = fanlin.plan_job(j)
+    t = _job(fanlin, 300 if exif >= 5 else 400, 400 if exif >= 5 else 300, 3, "w=100&h=100&rgb=1,2,3")
+    q = fanlin.plan_job(t)
+    for f in ("out_w", "out_h", "out_channels", "resized_w", "resized_h", "overlay_x", "overlay_y", "out_bytes", "algorithmic_bytes"):
+        assert getattr(p, f) == getattr(q, f), (exif, f)
+    assert (p.resized_w, p.resized_h) == ((75, 100) if exif >= 5 else (100, 75))
+    j.orientation = 9
+    with pytest.raises(fanlin.FanlinError):
+        fanlin.plan_job(j)
+
+
+def test_plan_output_layouts(fanlin):
+    """FANLIN_TO_RGB8 (JPEG branch, handler.rs:274-278) and FANLIN_TO_RGBA8 (WebP branch :287, GIF frames :355)."""
+    TO_RGBA8, TO_RGB8 = 1 << 4, 1 << 5
+    for c, qs, native in [(1, "w=50&h=50&crop=true", 1), (4, "w=50&h=50&crop=true", 4), (3, "w=50&h=40", 4), (3, "w=50&h=50&crop=true", 3)]:
+        j = _job(fanlin, 200, 200, c, qs)
+        assert fanlin.plan_job(j).out_channels == native
+        j.flags |= TO_RGB8
+        p = fanlin.plan_job(j)
+        assert p.out_channels == 3 and p.out_bytes == p.out_w * p.out_h * 3
+        j.flags |= TO_RGBA8
+        with pytest.raises(fanlin.FanlinError):
+            fanlin.plan_job(j)
+        j.flags &= ~TO_RGB8
+        assert fanlin.plan_job(j).out_channels == 4
