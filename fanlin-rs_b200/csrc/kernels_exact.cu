@@ -70,22 +70,63 @@ __global__ void __launch_bounds__(TX) hpass_exact_kernel(const StageDesc *__rest
     store_px(d, cx, cy, v);
 }
 
-// Compose-only: colour op on load, crop copy, letterbox, to_rgba8.
-__global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs) {
-    const StageDesc d = descs[blockIdx.y];
-    const uint32_t xtiles = (d.canvas_w + TX - 1) / TX;
-    if (blockIdx.x >= d.canvas_h * xtiles) return;
-    const uint32_t cy = blockIdx.x / xtiles;
-    const uint32_t cx = (blockIdx.x % xtiles) * TX + threadIdx.x;
-    if (cx >= d.canvas_w) return;
-    const uint32_t lx = cx - d.dst_x, ly = cy - d.dst_y;
-    if (cx < d.dst_x || cy < d.dst_y || lx >= d.n_cols || ly >= d.n_rows) {
-        store_fill(d, cx, cy);
-        return;
+// One stored pixel of CM channels with the colour op applied, packed one channel per byte.
+template <int CM>
+__device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t color_op) {
+    uint32_t b[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < CM; k++) b[k] = p[k];
+    if (color_op == COLOR_GRAY && CM >= 3) return luma_u8(b[0], b[1], b[2]) | (CM == 4 ? b[3] << 8 : 0u);
+    if (color_op == COLOR_INVERT) {
+        constexpr int NCOL = (CM == 2 || CM == 4) ? CM - 1 : CM;  // alpha stays
+#pragma unroll
+        for (int k = 0; k < NCOL; k++) b[k] = 255u - b[k];
     }
-    uint32_t v[4] = {0, 0, 0, 0};
-    load_px(d, d.ox0 + lx, d.oy0 + ly, v);
-    store_px(d, cx, cy, v);
+    return b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
+}
+
+// Compose-only: colour op on load, crop copy, letterbox, to_rgba8.  Four consecutive canvas pixels
+// of a row per thread; RGBA output leaves as one 16-byte store when the row allows.
+__global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs) {
+    const StageDesc &d = descs[blockIdx.y];
+    const uint32_t cw = d.canvas_w, ch = d.canvas_h;
+    const uint32_t xtiles = (cw + 4 * TX - 1) / (4 * TX);
+    if (blockIdx.x >= ch * xtiles) return;
+    const uint32_t cy = blockIdx.x / xtiles;
+    const uint32_t cx0 = ((blockIdx.x % xtiles) * TX + threadIdx.x) * 4;
+    if (cx0 >= cw) return;
+    const uint32_t c_mem = d.c_mem, C = d.c, c_out = d.c_out, epi = d.epi, fill = d.fill, color_op = d.color_op;
+    const uint32_t dst_x = d.dst_x, dst_y = d.dst_y, n_cols = d.n_cols, n_rows = d.n_rows;
+    const uint8_t *srow = d.src + size_t(d.oy0 + (cy - dst_y)) * d.src_pitch + size_t(d.ox0) * c_mem;
+    uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx0) * c_out;
+    const bool row_in = cy >= dst_y && cy - dst_y < n_rows;
+    uint32_t out[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+        const uint32_t cx = cx0 + k, lx = cx - dst_x;
+        out[k] = fill;  // letterbox bar (only EPI_BLEND_FILL stages have pixels outside the placed rect)
+        if (cx < cw && row_in && cx >= dst_x && lx < n_cols) {
+            const uint8_t *p = srow + size_t(lx) * c_mem;
+            const uint32_t v = c_mem == 4 ? fetch_packed<4>(p, color_op) : c_mem == 3 ? fetch_packed<3>(p, color_op)
+                             : c_mem == 1 ? fetch_packed<1>(p, color_op) : fetch_packed<2>(p, color_op);
+            if (epi == EPI_PLAIN) {
+                out[k] = v;
+            } else {  // the pixel viewed as Rgba<u8> (to_rgba): L -> (l,l,l,255), La -> (l,l,l,a), Rgb -> (r,g,b,255)
+                const uint32_t l = v & 255u;
+                uint32_t px = C == 1 ? (l * 0x010101u | 0xff000000u) : C == 2 ? (l * 0x010101u | ((v >> 8) & 255u) << 24)
+                            : C == 3 ? (v | 0xff000000u) : v;
+                if (epi == EPI_BLEND_FILL) px = blend_rgba(fill, px);
+                out[k] = px;
+            }
+        }
+    }
+    const uint32_t n = min(4u, cw - cx0);
+    if (c_out == 4 && n == 4 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+        *reinterpret_cast<uint4 *>(q) = make_uint4(out[0], out[1], out[2], out[3]);
+    } else {
+        for (uint32_t k = 0; k < n; k++)
+            for (uint32_t b = 0; b < c_out; b++) q[k * c_out + b] = uint8_t(out[k] >> (8 * b));
+    }
 }
 
 // Colour op alone (grayscale / inverse), source rows [oy0, oy0 + n_rows) -> dst rows [0, n_rows):
@@ -164,21 +205,6 @@ __global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restric
 //   6 rotate 90 clockwise, 7 transverse (rotate270 + flip_horizontal), 8 rotate 270.
 // A block moves a 32 x 32 pixel tile; the transposing cases go through shared memory so that both
 // the reads (along stored rows) and the writes (along oriented rows) are coalesced.
-// One stored pixel of CM channels with the colour op applied, packed one channel per byte.
-template <int CM>
-__device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t color_op) {
-    uint32_t b[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < CM; k++) b[k] = p[k];
-    if (color_op == COLOR_GRAY && CM >= 3) return luma_u8(b[0], b[1], b[2]) | (CM == 4 ? b[3] << 8 : 0u);
-    if (color_op == COLOR_INVERT) {
-        constexpr int NCOL = (CM == 2 || CM == 4) ? CM - 1 : CM;  // alpha stays
-#pragma unroll
-        for (int k = 0; k < NCOL; k++) b[k] = 255u - b[k];
-    }
-    return b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
-}
-
 __global__ void __launch_bounds__(256) orient_pass_kernel(const StageDesc *__restrict__ descs) {
     constexpr uint32_t TK = 64;  // tile extent across the stored rows: 8 pixels per thread in flight
     __shared__ uint32_t tile[TK][33];  // [k][tx]: k counts stored rows (oriented rows, or oriented columns when the axes swap)
@@ -293,7 +319,7 @@ int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const floa
 
 int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0) return 0;
-    const uint32_t hx = g.max_canvas_h * ((g.max_canvas_w + TX - 1) / TX);
+    const uint32_t hx = g.max_canvas_h * ((g.max_canvas_w + 4 * TX - 1) / (4 * TX));  // four pixels per thread
     if (!hx) return 0;
     lc.begin("compose_kernel");
     compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs);
