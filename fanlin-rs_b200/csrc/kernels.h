@@ -56,8 +56,8 @@ bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t r
 struct BlurItem;
 int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
                 uint32_t taps_pad, const float *d_w, bool skip_v, LaunchCtx &lc);
-// Compose-only stages: colour op / crop copy / letterbox / to_rgba8.
-int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+// Compose-only stages: colour op / crop copy / letterbox / to_rgba8, and Nearest resamples (a gather through the tap tables).
+int launch_compose(const StageDesc *d_descs, const TapEntry *d_tab, const LaunchGeom &g, LaunchCtx &lc);
 // Vertical blur pass on the tensor cores (kernels_fused_tc.cu); writes the f32 intermediate the horizontal blur kernel reads.
 struct BlurVTcItem;
 int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,

@@ -85,9 +85,11 @@ __device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t colo
     return b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
 }
 
-// Compose-only: colour op on load, crop copy, letterbox, to_rgba8.  Four consecutive canvas pixels
-// of a row per thread; RGBA output leaves as one 16-byte store when the row allows.
-__global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs) {
+// Compose-only: colour op on load, crop copy, letterbox, to_rgba8 -- and the Nearest resample of
+// GIF frames (handler.rs:338,340), which is a gather: with tables (v_tab != NO_TABLE) the source
+// pixel of an output is (h_tab[x].left, v_tab[y].left), its single tap.  Four consecutive canvas
+// pixels of a row per thread; RGBA output leaves as one 16-byte store when the row allows.
+__global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs, const TapEntry *__restrict__ tab) {
     const StageDesc &d = descs[blockIdx.y];
     const uint32_t cw = d.canvas_w, ch = d.canvas_h;
     const uint32_t xtiles = (cw + 4 * TX - 1) / (4 * TX);
@@ -97,16 +99,20 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
     if (cx0 >= cw) return;
     const uint32_t c_mem = d.c_mem, C = d.c, c_out = d.c_out, epi = d.epi, fill = d.fill, color_op = d.color_op;
     const uint32_t dst_x = d.dst_x, dst_y = d.dst_y, n_cols = d.n_cols, n_rows = d.n_rows;
-    const uint8_t *srow = d.src + size_t(d.oy0 + (cy - dst_y)) * d.src_pitch + size_t(d.ox0) * c_mem;
-    uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx0) * c_out;
     const bool row_in = cy >= dst_y && cy - dst_y < n_rows;
+    const bool gather = d.v_tab != NO_TABLE;
+    const uint32_t sy = !row_in ? 0u : gather ? tab[d.v_tab + d.oy0 + (cy - dst_y)].left : d.oy0 + (cy - dst_y);
+    const uint8_t *srow = d.src + size_t(sy) * d.src_pitch;
+    const uint32_t ox0 = d.ox0, h_tab = d.h_tab;
+    uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx0) * c_out;
     uint32_t out[4];
 #pragma unroll
     for (uint32_t k = 0; k < 4; k++) {
         const uint32_t cx = cx0 + k, lx = cx - dst_x;
         out[k] = fill;  // letterbox bar (only EPI_BLEND_FILL stages have pixels outside the placed rect)
         if (cx < cw && row_in && cx >= dst_x && lx < n_cols) {
-            const uint8_t *p = srow + size_t(lx) * c_mem;
+            const uint32_t sx = gather ? tab[h_tab + ox0 + lx].left : ox0 + lx;
+            const uint8_t *p = srow + size_t(sx) * c_mem;
             const uint32_t v = c_mem == 4 ? fetch_packed<4>(p, color_op) : c_mem == 3 ? fetch_packed<3>(p, color_op)
                              : c_mem == 1 ? fetch_packed<1>(p, color_op) : fetch_packed<2>(p, color_op);
             if (epi == EPI_PLAIN) {
@@ -317,12 +323,12 @@ int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const floa
     return n;
 }
 
-int launch_compose(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
+int launch_compose(const StageDesc *d_descs, const TapEntry *d_tab, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0) return 0;
     const uint32_t hx = g.max_canvas_h * ((g.max_canvas_w + 4 * TX - 1) / (4 * TX));  // four pixels per thread
     if (!hx) return 0;
     lc.begin("compose_kernel");
-    compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs);
+    compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs, d_tab);
     lc.end();
     return 1;
 }

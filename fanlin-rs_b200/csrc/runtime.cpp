@@ -283,6 +283,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     std::unique_ptr<FusedCache, void (*)(FusedCache *)> fcache(fused_cache_new(), fused_cache_free);
     FusedTables ftabs;
     std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
+    std::vector<uint8_t> gather_a(n_jobs, 0); // stage A is a Nearest resample: the compose kernel gathers through the tap tables
     std::vector<StagePlan> a_pre(n_jobs);     // present: stage A as the tensor-core kernel sees it behind a colour-op pass
     std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(), fused_tc_cache_free);
     FusedTcTables tctabs;
@@ -320,7 +321,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         if (plans_out) plans_out[i] = b->plans[i].pub;
         const JobPlan &p = b->plans[i];
         fused_a[i] = 0;
-        if (!exact && use_tc) {
+        gather_a[i] = p.a.present && p.a.separable && p.a.v_kind == KIND_NEAREST && p.a.h_kind == KIND_NEAREST;  // one tap per output: a gather
+        if (!exact && use_tc && !gather_a[i]) {
             if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) {
                 fused_a[i] = 2;
             } else if (p.a.present && p.a.separable && p.a.color_op != COLOR_NONE && p.a.src_is_input) {
@@ -337,7 +339,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 }
             }
         }
-        if (!fused_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
+        if (!fused_a[i] && !gather_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         fast_b[i] = !exact && blur_eligible(p.b);
         if (!fast_b[i]) { add_table(p.b.vtab); add_table(p.b.htab); }
@@ -355,7 +357,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (p.pre.present) js[i].pre = align_up(size_t(p.pre.job.src_pitch) * p.pre.job.src_h, 256);
             if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_pitch) * p.a.canvas_h, 256);
             size_t ta = 0, tb = 0;
-            if (p.a.present && p.a.separable && !fused_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
+            if (p.a.present && p.a.separable && !fused_a[i] && !gather_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
             if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of either blur path
             js[i].tmp = align_up(std::max(ta, tb), 256);
             if (p.post_c_in) js[i].fin = align_up(size_t(p.pub.out_w) * p.pub.out_h * p.post_c_in, 256);  // the final image before to_rgb8
@@ -471,8 +473,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const JobPlan &p = b->plans[i];
                 const StagePlan &s = pass == 2 ? p.b : p.a;
                 if (!s.present) continue;
-                if (pass == 0 && (!s.separable || fused_a[i])) continue;
-                if (pass == 1 && s.separable) continue;
+                if (pass == 0 && (!s.separable || fused_a[i] || gather_a[i])) continue;
+                if (pass == 1 && s.separable && !gather_a[i]) continue;
                 if (pass == 2 && fast_b[i]) continue;
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 float *tmp = js[i].tmp ? reinterpret_cast<float *>(static_cast<uint8_t *>(b->d_scratch) + js[i].tmp_off) : nullptr;
@@ -693,7 +695,7 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
         } else if (s.kind == 8) n += launch_to_rgb8(s.descs, s.geom, lc);
         else if (s.kind == 6) n += launch_orient_pass(s.descs, s.geom, lc);
         else if (s.kind == 5) n += launch_color_pass(s.descs, s.geom, lc);
-        else if (s.kind == 1) n += launch_compose(s.descs, s.geom, lc);
+        else if (s.kind == 1) n += launch_compose(s.descs, b->d_tab, s.geom, lc);
         else n += launch_sep_exact(s.descs, b->d_tab, b->d_w, s.geom, lc);
     }
     if (b->timing) b->ev_used = lc.used;
