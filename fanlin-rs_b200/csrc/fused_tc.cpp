@@ -2,6 +2,8 @@
 // s8 digit tiles of the vertical weights and the horizontal scatter table.
 #include "fused_tc.h"
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <map>
@@ -16,6 +18,8 @@ struct TcBand {
 };
 struct TcGeom {
     bool ok = false;
+    bool hm = false;        // horizontal stage on the tensor cores
+    uint32_t hrec_off = 0;  // its per-chunk records
     uint32_t b0 = 0, n_chunks = 0, chunk_off = 0, hw_off = 0, hinfo_off = 0, cpre_off = 0, out_stride = 1;
     float scale = 1.f;
     std::vector<TcBand> bands;
@@ -95,8 +99,26 @@ uint32_t fused_tc_max_band(uint32_t c, uint32_t out_stride) {
 
 struct FusedTcCache {
     std::map<TcKey, TcGeom> geoms;
+    bool allow_hmma = true;
 };
-FusedTcCache *fused_tc_cache_new() { return new FusedTcCache(); }
+FusedTcCache *fused_tc_cache_new(bool allow_hmma) {
+    FusedTcCache *c = new FusedTcCache();
+    c->allow_hmma = allow_hmma;
+    return c;
+}
+
+// ---- tensor-core horizontal stage ---------------------------------------------------------------
+size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh) {
+    const size_t a = size_t(n_a) * kg_max * TC_M, b = 2 * size_t(TC_N) * kg_max;  // source slots, two vertical weight-tile slots
+    const size_t wh = size_t(n_wh) * fused_tc2_n(c) * 512;                        // hi + lo tiles [N2][128] f16
+    const size_t t = 2 * size_t(n_groups) * 32 * 256;                             // T hi + lo: [32 rows per group][128] f16
+    return a + b + wh + t + 1024;
+}
+
+size_t fused_tc_item_smem(const FusedTcItem &it) {
+    return it.hmma ? fused_tc2_smem_bytes(it.c, it.n_groups, it.kg_max, it.n_a, it.n_wh)
+                   : fused_tc_smem_bytes(it.c, it.band_rows, it.kg_max, it.out_stride, it.n_a);
+}
 void fused_tc_cache_free(FusedTcCache *c) { delete c; }
 
 bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
@@ -191,6 +213,79 @@ static int weight_shift(const AxisTable &vt) {
     return sh;
 }
 
+// Group size and K extent build_band would choose for a band, without building anything.
+static bool plan_band(const AxisTable &vt, uint32_t oy0, uint32_t r0, uint32_t rows, uint32_t min_grp, uint32_t *n_groups, uint32_t *kg_max) {
+    uint32_t best_r = 0, best_cost = ~0u, best_kg = 0;
+    for (uint32_t gr = TC_GROUP_ROWS; gr >= min_grp; gr--) {
+        uint32_t cost = 0, kgm = 0;
+        bool fits = true;
+        for (uint32_t ra = 0; ra < rows && fits; ra += gr) {
+            const uint32_t rb = std::min(rows, ra + gr), k0 = vt.entries[oy0 + r0 + ra].left;
+            uint32_t k1 = 0;
+            for (uint32_t r = ra; r < rb; r++) k1 = std::max(k1, vt.entries[oy0 + r0 + r].left + vt.entries[oy0 + r0 + r].count);
+            fits = k1 - k0 <= TC_KG_MAX;
+            cost += (k1 - k0 + 31) / 32;
+            kgm = std::max(kgm, (k1 - k0 + 31) / 32 * 32);
+        }
+        if (fits && cost < best_cost) { best_cost = cost; best_r = gr; best_kg = kgm; }
+    }
+    if (!best_r) return false;
+    *n_groups = (rows + best_r - 1) / best_r;
+    *kg_max = best_kg;
+    return true;
+}
+
+// Horizontal stage on the tensor cores: per chunk one f16 weight tile pair (hi, lo; K-major core-matrix
+// layout, [N2][128 tile columns]) that maps the chunk's 128 tile columns (byte b = pixel b / c, channel
+// b % c) to the accumulator columns (ring position of the output) * c + channel, ring = N2 / c outputs:
+// the outputs a chunk touches and those still unfinished from earlier chunks must fit the ring.
+// Records per chunk: {tile byte offset, first output it finishes (relative to ox0), outputs finished}.
+static bool build_hmma(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTables *tct) {
+    const AxisTable &t = *s.htab;
+    const uint32_t C = s.c, N2 = fused_tc2_n(C), RP = N2 / C;
+    const uint32_t o0 = s.ox0, o_end = s.ox0 + s.n_cols;
+    {  // dry run: the ring condition
+        uint32_t fin = o0, touch = o0;
+        for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+            const uint32_t b1 = g.b0 + TC_M * (ch + 1), x_hi = (b1 - 1) / C;
+            while (touch < o_end && t.entries[touch].left <= x_hi) touch++;
+            if (touch - fin > RP) return false;
+            while (fin < touch && (t.entries[fin].left + t.entries[fin].count) * C <= b1) fin++;
+        }
+        if (fin != o_end) return false;
+    }
+    std::vector<uint32_t> rec(size_t(3) * g.n_chunks);
+    uint32_t fin = o0, touch = o0;
+    for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+        const uint32_t b0 = g.b0 + TC_M * ch, b1 = b0 + TC_M, x_hi = (b1 - 1) / C;
+        while (touch < o_end && t.entries[touch].left <= x_hi) touch++;
+        const size_t off = (tct->b.size() + 127) & ~size_t(127);
+        tct->b.resize(off + size_t(N2) * 512, 0);
+        uint16_t *hi = reinterpret_cast<uint16_t *>(&tct->b[off]), *lo = hi + size_t(N2) * 128;
+        for (uint32_t o = fin; o < touch; o++) {
+            const TapEntry &e = t.entries[o];
+            for (uint32_t tt = 0; tt < e.count; tt++) {
+                const float w = t.weights[e.woff + tt] * TC2_WSCALE;
+                const __half wh = __float2half_rn(w), wl = __float2half_rn(w - __half2float(wh));
+                for (uint32_t chn = 0; chn < C; chn++) {
+                    const uint32_t byte = (e.left + tt) * C + chn;
+                    if (byte < b0 || byte >= b1) continue;
+                    const uint32_t k = byte - b0, n = ((o - o0) % RP) * C + chn;
+                    const size_t at = (size_t(n / 8) * 16 + k / 8) * 64 + (n % 8) * 8 + k % 8;  // in f16 elements
+                    hi[at] = __half_as_ushort(wh);
+                    lo[at] = __half_as_ushort(wl);
+                }
+            }
+        }
+        const uint32_t first = fin;
+        while (fin < touch && (t.entries[fin].left + t.entries[fin].count) * C <= b1) fin++;
+        rec[3 * ch] = uint32_t(off); rec[3 * ch + 1] = first - o0; rec[3 * ch + 2] = fin - first;
+    }
+    g.hrec_off = uint32_t(tabs->info.size());
+    tabs->info.insert(tabs->info.end(), rec.begin(), rec.end());
+    return true;
+}
+
 static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
     const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c | (s.c_out << 8));
     auto it = cache->geoms.find(key);
@@ -204,6 +299,38 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
     const uint32_t C = s.c, xa = s.sx0, xe = s.sx0 + s.n_sx;
     g.b0 = (xa * C) & ~15u;
     g.n_chunks = (xe * C - g.b0 + TC_M - 1) / TC_M;
+    // Horizontal stage on the tensor cores where the output ring and the shared-memory budget allow it: the band
+    // keeps its rows as f16 hi / lo tiles (32 rows per group, <= 8 groups = two M = 128 tiles) next to >= 2 source slots.
+    if (cache->allow_hmma) {
+        const int sh = weight_shift(*s.vtab);
+        bool fits = false;
+        uint32_t n_bands = 1, band_rows = s.n_rows;
+        for (; n_bands <= 8 && !fits; n_bands++) {
+            band_rows = (s.n_rows + n_bands - 1) / n_bands;
+            fits = true;
+            for (uint32_t r0 = 0; r0 < s.n_rows && fits; r0 += band_rows) {
+                uint32_t ng = 0, kgm = 0;
+                fits = plan_band(*s.vtab, s.oy0, r0, std::min(band_rows, s.n_rows - r0), 8, &ng, &kgm) && ng <= 8 &&
+                       fused_tc2_smem_bytes(C, ng, kgm, 2, 1) <= TC_SMEM_LIMIT;
+            }
+            if (fits) break;
+        }
+        if (fits && build_hmma(s, g, tabs, tct)) {
+            g.scale = std::ldexp(1.0f, -sh);
+            bool okb = true;
+            for (uint32_t r0 = 0; r0 < s.n_rows && okb; r0 += band_rows) {
+                TcBand bt{};
+                okb = build_band(*s.vtab, s.oy0, r0, std::min(band_rows, s.n_rows - r0), sh, 8, tabs, tct, &bt);
+                g.bands.push_back(bt);
+            }
+            if (okb) {
+                g.hm = true;
+                g.ok = true;
+                return cache->geoms.emplace(key, std::move(g)).first->second;
+            }
+            g.bands.clear();
+        }
+    }
     std::vector<PxPair> pairs;
     std::vector<uint32_t> recs;
     {
@@ -276,6 +403,11 @@ bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *
     return geom_of(s, cache, tabs, tct).ok;
 }
 
+bool fused_tc_uses_hmma(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
+    const TcGeom &g = geom_of(s, cache, tabs, tct);
+    return g.ok && g.hm;
+}
+
 int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
                    FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct, std::vector<FusedTcItem> *items) {
     (void)job;
@@ -296,6 +428,12 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         f.dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
         f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;
         f.first_band = b == 0; f.last_band = b + 1 == g.bands.size();
+        if (g.hm) {
+            f.hmma = 1; f.hrec_off = g.hrec_off;
+            f.n_a = 4; f.n_wh = 1;
+            while (f.n_a > 2 && fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 1) > TC_SMEM_LIMIT) f.n_a--;
+            if (fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 2) <= TC_SMEM_LIMIT) f.n_wh = 2;
+        }
         items->push_back(f);
     }
     return FANLIN_OK;

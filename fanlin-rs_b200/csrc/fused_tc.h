@@ -45,7 +45,17 @@ struct FusedTcItem {
     uint32_t n_cols;
     uint32_t dst_pitch, c_out, canvas_w, canvas_h, dst_x, dst_y, epi, fill;
     uint32_t first_band, last_band;
+    // tensor-core horizontal stage (fused_resample_tc2_kernel): per-chunk records {byte offset of the chunk's f16
+    // weight tiles, first output finished by the chunk (relative to the first produced column), outputs finished}
+    uint32_t hmma, hrec_off, n_wh;
 };
+
+// Tensor-core horizontal stage: the chunk's 128 tile columns (K) are contracted with an f16 weight
+// tile [N2][128] into N2 = ring positions x channels accumulator columns (ring of N2 / c outputs).
+inline uint32_t fused_tc2_n(uint32_t c) { return c == 3 ? 48u : 64u; }
+constexpr float TC2_WSCALE = 16.0f;  // horizontal weights are stored x16: their low halves stay f16 normals
+size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh);
+size_t fused_tc_item_smem(const FusedTcItem &it);
 
 // Vertical Gaussian pass of the blur on the tensor cores (kernels_fused_tc.cu blur_v_tc_kernel):
 // the same banded integer contraction, output rows = input rows, written as the f32 intermediate
@@ -67,9 +77,10 @@ struct FusedTcTables {
 
 bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job);
 struct FusedTcCache;
-FusedTcCache *fused_tc_cache_new();
+FusedTcCache *fused_tc_cache_new(bool allow_hmma = true);
 void fused_tc_cache_free(FusedTcCache *);
 bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs);
+bool fused_tc_uses_hmma(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs);
 int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
                    FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs, std::vector<FusedTcItem> *items);
 

@@ -59,6 +59,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // A is MN-major (bit 15), B is K-major, N >> 3 @ bit 17, M >> 4 @ bit 24.
 constexpr uint32_t UMMA_IDESC = (2u << 4) | (0u << 7) | (1u << 10) | (1u << 15) | ((TC_N >> 3) << 17) | ((TC_M >> 4) << 24);
 
+// One lane of a converged warp.  Unlike `lane == 0`, elect.sync tells ptxas that a single thread runs
+// the branch, so tcgen05.mma / TMA operands stay in uniform registers: with `lane == 0` every
+// UTCIMMA sat in an ELECT / BRA.U.ANY loop and issued every ~110 clk whatever its shape
+// (profiles/microbench/umma_rate_elect.cu: 71 clk for the same loop, N / 2 clk from N = 192 up).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -113,11 +123,12 @@ struct TcPipe {
 };
 
 // source TMA thread: one tensor copy per group (kg_max rows x 128 B), n_a groups deep
+template <uint32_t NRT = NR>
 __device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMap *tmap) {
     const uint32_t total = p.n_chunks * p.n_groups;
     uint32_t g = 0, chunk = 0, slot = 0;
     for (uint32_t gg = 0; gg < total; gg++) {
-        if (gg >= p.n_a) mbar_wait(p.mbar + 8 * ((gg - p.n_a) % NR), ((gg - p.n_a) / NR) & 1);  // the slot was read by the MMAs of group gg - n_a
+        if (gg >= p.n_a) mbar_wait(p.mbar + 8 * ((gg - p.n_a) % NRT), ((gg - p.n_a) / NRT) & 1);  // the slot was read by the MMAs of group gg - n_a
         const uint32_t bar = p.a_full + 8 * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.kg_max * TC_M) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -130,11 +141,12 @@ __device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMa
 }
 
 // weight TMA thread: one bulk copy per group into slot gg % NB
+template <uint32_t NRT = NR>
 __device__ __forceinline__ void tc_weight_role(const TcPipe &p, const uint8_t *tb) {
     const uint32_t total = p.n_chunks * p.n_groups;
     uint32_t g = 0;
     for (uint32_t gg = 0; gg < total; gg++) {
-        if (gg >= NB) mbar_wait(p.mbar + 8 * ((gg - NB) % NR), ((gg - NB) / NR) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
+        if (gg >= NB) mbar_wait(p.mbar + 8 * ((gg - NB) % NRT), ((gg - NB) / NRT) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
         const uint32_t kg = p.grp[4 * g + 1], b_off = p.grp[4 * g + 2];
         const uint32_t bar = p.b_full + 8 * (gg % NB);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
@@ -271,11 +283,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp;
 
     if (warp == NT / 32 + 1) {
-        if (lane == 0) tc_source_role(pipe, tmap);
+        if (elect_one()) tc_source_role(pipe, tmap);
     } else if (warp == NT / 32 + 2) {
-        if (lane == 0) tc_weight_role(pipe, tb);
+        if (elect_one()) tc_weight_role(pipe, tb);
     } else if (warp == NT / 32) {
-        if (lane == 0) tc_mma_role(pipe);
+        if (elect_one()) tc_mma_role(pipe);
     } else {
     // ================= consumer warps =================
     auto stage_htab = [&](uint32_t chunk) {  // the chunk's slice of the horizontal table -> its shared-memory copy
@@ -513,11 +525,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) blur_v_tc_kernel(const BlurVTcItem 
     pipe.kg_max = it.kg_max; pipe.n_a = it.n_a; pipe.n_chunks = it.n_chunks; pipe.n_groups = it.n_groups;
     pipe.x0 = 0; pipe.tmem_base = tmem_base_s; pipe.grp = grp;
     if (warp == NT / 32 + 1) {
-        if (lane == 0) tc_source_role(pipe, tmaps + blockIdx.x);
+        if (elect_one()) tc_source_role(pipe, tmaps + blockIdx.x);
     } else if (warp == NT / 32 + 2) {
-        if (lane == 0) tc_weight_role(pipe, tb);
+        if (elect_one()) tc_weight_role(pipe, tb);
     } else if (warp == NT / 32) {
-        if (lane == 0) tc_mma_role(pipe);
+        if (elect_one()) tc_mma_role(pipe);
     } else {
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
         const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane, n_e = it.n_e;
@@ -554,6 +566,322 @@ __global__ void __launch_bounds__(NT_ALL, 1) blur_v_tc_kernel(const BlurVTcItem 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "r"(TMEM_COLS));
 }
 
+
+// ================= both passes on the tensor cores (fused_resample_tc2_kernel) =================
+// The vertical pass is the banded integer contraction above.  Its results no longer go through a
+// scatter loop on the CUDA cores: the consumers write them as f16 hi / lo halves (v = hi + lo to
+// 2^-14) into the MN-major operand tile T[group row][tile column], and the horizontal pass is a
+// second contraction per chunk and per tile of 128 band rows (four groups of 32):
+//
+//   D2[128 rows x N2] (f32, TMEM) = T_hi . W_hi + T_lo . W_hi + T_hi . W_lo     (kind::f16, K = 128 columns)
+//
+// W[N2][128] maps the chunk's tile columns (byte b of the row = channel b % c of pixel b / c) to
+// accumulator columns (ring position of the output pixel) * c + channel; the host builds it per
+// chunk with the crate's weights x 16 split into f16 halves.  A chunk's D2 holds the partial sums
+// of the <= N2 / c outputs whose windows meet the chunk; each consumer thread owns one band row
+// and half of the ring in registers, adds the partial sums and, when a pixel's window has ended,
+// rounds and stores it.  The CUDA cores only drain, convert and store.
+constexpr int NT_ALL2 = NT + 128;   // + the MMA warp, the source / vertical-weight / horizontal-weight TMA warps
+constexpr uint32_t NR2 = 4;          // TMEM regions of the vertical pass (96 columns each, from column 128)
+constexpr uint32_t TMEM_V0 = 128;    // columns [0, 128): D2 of the two row tiles
+constexpr uint32_t H_LAG = 2;        // vertical groups issued between a row tile's last group and its horizontal MMAs
+
+struct Tc2Pipe {
+    uint32_t t_ready, d2_full, d2_free, wh_full, wh_free;  // mbarrier arrays (8 bytes per entry)
+    uint32_t sT_u, t_bytes;                       // T hi tile; the lo tile follows t_bytes later
+    uint32_t sWh_u, n_wh;                         // horizontal weight slots [n_wh][hi N2 x 128 | lo N2 x 128] f16
+    uint32_t n_mt;                                // row tiles (1 or 2)
+};
+
+// horizontal-weight TMA thread: one bulk copy per chunk into slot chunk % n_wh, after the horizontal MMAs of the chunk that used it
+template <uint32_t N2>
+__device__ __forceinline__ void tc2_wh_role(const TcPipe &p, const Tc2Pipe &h, const uint8_t *tb, const uint32_t *hrec) {
+    for (uint32_t ch = 0; ch < p.n_chunks; ch++) {
+        if (ch >= h.n_wh) mbar_wait(h.wh_free + 8 * (ch % h.n_wh), (ch / h.n_wh - 1) & 1);  // the slot's previous tiles were read
+        const uint32_t bar = h.wh_full + 8 * (ch % h.n_wh);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(N2 * 512u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(h.sWh_u + (ch % h.n_wh) * N2 * 512u),
+                     "l"(tb + __ldg(hrec + 3 * ch)), "r"(N2 * 512u), "r"(bar)
+                     : "memory");
+    }
+}
+
+// MMA thread: the vertical groups as in tc_mma_role (regions of NR2), and H_LAG groups after the last
+// group of a row tile, that tile's 24 horizontal MMAs
+template <uint32_t N2>
+__device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) {
+    constexpr uint32_t IDESC_H = (1u << 4) | (1u << 15) | ((N2 >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
+    const uint32_t total = p.n_chunks * p.n_groups;
+    uint32_t h_ch = 0, h_mt = 0;  // next horizontal MMA batch: chunk, row tile
+    uint32_t h_trigger = min(3u, p.n_groups - 1) + H_LAG;
+    auto issue_h = [&]() {
+        const uint32_t slot = h_ch % h.n_wh;
+        if (h_mt == 0) mbar_wait(h.wh_full + 8 * slot, (h_ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
+        mbar_wait(h.t_ready + 8 * h_mt, h_ch & 1);                            // the consumers have written the tile's rows
+        if (h_ch > 0) mbar_wait(h.d2_free + 8 * h_mt, (h_ch - 1) & 1);        // ... and read the previous chunk's D2
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = h.sT_u + h_mt * 32768u, a_lo = a_hi + h.t_bytes;
+        const uint32_t b_hi = h.sWh_u + slot * N2 * 512u, b_lo = b_hi + N2 * 256u;
+        const uint32_t d_tmem = p.tmem_base + h_mt * N2;
+#pragma unroll
+        for (int combo = 0; combo < 3; combo++) {
+            uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);  // LBO: next 8 columns (K), SBO: next 8 rows (M)
+            uint64_t db = umma_desc(combo == 2 ? b_lo : b_hi, 128, 2048);  // LBO: next 8 columns (K), SBO: next 8 accumulator columns (N)
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                if (combo == 0 && ks == 0)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
+                                 "l"(db), "r"(IDESC_H)
+                                 : "memory");
+                else
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
+                                 "l"(db), "r"(IDESC_H)
+                                 : "memory");
+                da += 256 >> 4;  // 16 columns = two core matrices along K
+                db += 256 >> 4;
+            }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(h.d2_full + 8 * h_mt) : "memory");
+        if (h_mt + 1 == h.n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(h.wh_free + 8 * slot) : "memory");
+        if (++h_mt == h.n_mt) { h_mt = 0; h_ch++; }
+        h_trigger = h_ch * p.n_groups + min(4 * h_mt + 3, p.n_groups - 1) + H_LAG;
+    };
+    uint32_t g = 0, slot = 0, suse = 0;
+    for (uint32_t gg = 0; gg < total; gg++) {
+        const uint32_t region = gg % NR2, ruse = gg / NR2, bslot = gg % NB;
+        const uint32_t kg = p.grp[4 * g + 1];
+        mbar_wait(p.b_full + 8 * bslot, (gg / NB) & 1);
+        mbar_wait(p.a_full + 8 * slot, suse & 1);
+        if (ruse > 0) mbar_wait(p.tmem_free + 8 * region, (ruse - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint64_t da = umma_desc(p.sA_u + slot * p.kg_max * TC_M, 16, 1024, 2);
+        uint64_t db = umma_desc(p.sB_u + bslot * TC_N * p.kg_max, 128, (kg / 16) * 128);
+        const uint32_t d_tmem = p.tmem_base + TMEM_V0 + region * TC_N;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                     "l"(da), "l"(db), "r"(UMMA_IDESC)
+                     : "memory");
+        for (uint32_t ks = 1; ks < kg / 32; ks++) {
+            da += SLAB >> 4;
+            db += (2 * 128) >> 4;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                         "l"(da), "l"(db), "r"(UMMA_IDESC)
+                         : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(p.mbar + 8 * region) : "memory");
+        if (++slot == p.n_a) { slot = 0; suse++; }
+        if (++g == p.n_groups) g = 0;
+        while (h_ch < p.n_chunks && h_trigger <= gg) issue_h();
+    }
+    while (h_ch < p.n_chunks) issue_h();
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {  // {lo, hi} -> f16x2, round to nearest even
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+    float2 r;
+    asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}\n" : "=f"(r.x), "=f"(r.y) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const FusedTcItem *__restrict__ items, const CUtensorMap *__restrict__ tmaps,
+                                                                    const uint8_t *__restrict__ tb, const uint32_t *__restrict__ tinfo) {
+    constexpr uint32_t N2 = C == 3 ? 48 : 64, RP = N2 / C, HP = RP / 2;  // accumulator columns, ring of outputs, ring positions per thread
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ FusedTcItem it_s;
+    __shared__ __align__(8) uint64_t mbar[NR2], tmem_free[NR2], a_full[NA_MAX], b_full[NB];
+    __shared__ __align__(8) uint64_t t_ready[2], d2_full[2], d2_free[2], wh_full[2], wh_free[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t grp[4 * 8];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    if (tid == 0) {
+        it_s = items[blockIdx.x];
+        for (uint32_t r = 0; r < NR2; r++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&tmem_free[r])));
+        }
+        for (uint32_t r = 0; r < NA_MAX; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&a_full[r])));
+        for (uint32_t r = 0; r < NB; r++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&b_full[r])));
+        for (uint32_t r = 0; r < 2; r++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&t_ready[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&d2_full[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem_u32(&d2_free[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wh_full[r])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&wh_free[r])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const FusedTcItem &it = it_s;
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < NT / 32) fill_bars(it, warp, lane, NT / 32);
+
+    // ---- shared-memory carve-up: T hi | T lo | source slots | vertical weight slots | horizontal weight slots.
+    // The horizontal MMAs always read 128 rows per tile: behind a tile of fewer groups they read into
+    // whatever follows (T lo, the source slots) -- rows nobody drains.
+    const uint32_t kg_max = it.kg_max, n_a = it.n_a, n_groups = it.n_groups, n_chunks = it.n_chunks;
+    const uint32_t t_bytes = n_groups * 32u * 256u;
+    uint8_t *sT = smem;
+    uint8_t *sA = sT + 2 * size_t(t_bytes);
+    uint8_t *sB = sA + size_t(n_a) * kg_max * TC_M;
+    uint8_t *sWh = sB + NB * size_t(TC_N) * kg_max;
+    for (uint32_t k = tid; k < 4 * n_groups; k += NT_ALL2) grp[k] = tinfo[it.grp_off + k];
+    __syncthreads();
+
+    TcPipe pipe;
+    pipe.mbar = smem_u32(&mbar[0]); pipe.tmem_free = smem_u32(&tmem_free[0]); pipe.a_full = smem_u32(&a_full[0]); pipe.b_full = smem_u32(&b_full[0]);
+    pipe.sA_u = smem_u32(sA); pipe.sB_u = smem_u32(sB); pipe.kg_max = kg_max; pipe.n_a = n_a; pipe.n_chunks = n_chunks; pipe.n_groups = n_groups;
+    pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp;
+    Tc2Pipe hp;
+    hp.t_ready = smem_u32(&t_ready[0]); hp.d2_full = smem_u32(&d2_full[0]); hp.d2_free = smem_u32(&d2_free[0]); hp.wh_full = smem_u32(&wh_full[0]); hp.wh_free = smem_u32(&wh_free[0]);
+    hp.sT_u = smem_u32(sT); hp.t_bytes = t_bytes; hp.sWh_u = smem_u32(sWh); hp.n_wh = it.n_wh; hp.n_mt = (n_groups + 3) / 4;
+    const uint32_t *hrec = tinfo + it.hrec_off;
+
+    if (warp == NT / 32 + 1) {
+        if (elect_one()) tc_source_role<NR2>(pipe, tmaps + blockIdx.x);
+    } else if (warp == NT / 32 + 2) {
+        if (elect_one()) tc_weight_role<NR2>(pipe, tb);
+    } else if (warp == NT / 32 + 3) {
+        if (elect_one()) tc2_wh_role<N2>(pipe, hp, tb, hrec);
+    } else if (warp == NT / 32) {
+        if (elect_one()) tc2_mma_role<N2>(pipe, hp);
+    } else {
+        // ================= consumer warps =================
+        const float scale = it.scale, scale_hi = it.scale * 16384.0f;
+        const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        const uint32_t grp_rows = it.grp_rows, n_mt = hp.n_mt;
+        float acc[2][HP][C];  // partial sums of this thread's band row (one per row tile) for its half of the output ring
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int k = 0; k < int(HP); k++)
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[t][k][c] = 0.f;
+
+        // D2 of (chunk, row tile) -> registers; pixels whose window ended in the chunk are rounded and stored
+        auto drain_d2 = [&](uint32_t chunk, uint32_t mt, float (&a)[HP][C]) {
+            mbar_wait(hp.d2_full + 8 * mt, chunk & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[N2 / 2];
+            const uint32_t taddr = tmem_base + mt * N2 + ((q * 32u) << 16) + half * (N2 / 2);
+            if constexpr (N2 == 48) {
+                tmem_ld16(taddr, v);
+                tmem_ld8(taddr + 16, v + 16);
+            } else {
+                tmem_ld16(taddr, v);
+                tmem_ld16(taddr + 16, v + 16);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hp.d2_free + 8 * mt) : "memory");
+            const uint32_t g = mt * 4 + q;
+            const bool row_ok = g < n_groups && lane < grp[4 * min(g, n_groups - 1) + 3];
+            const uint32_t cy = it.dst_y + it.band_r0 + g * grp_rows + lane;
+            const uint32_t fin_first = __ldg(hrec + 3 * chunk + 1), n_fin = __ldg(hrec + 3 * chunk + 2);
+#pragma unroll
+            for (int k = 0; k < int(HP); k++) {
+#pragma unroll
+                for (int c = 0; c < C; c++) a[k][c] += __uint_as_float(v[k * C + c]);
+                const uint32_t d = (half * HP + k - fin_first) & (RP - 1);  // ring distance from the first output finished here
+                if (d < n_fin) {  // uniform over the warp
+                    if (row_ok) {
+                        uint32_t u[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int c = 0; c < C; c++) u[c] = round_u8(a[k][c] * (1.0f / TC2_WSCALE));
+                        emit_px<C>(it, it.dst_x + fin_first + d, cy, u);
+                    }
+#pragma unroll
+                    for (int c = 0; c < C; c++) a[k][c] = 0.f;
+                }
+            }
+        };
+
+        uint32_t gg = 0;
+        for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+            for (uint32_t g = 0; g < n_groups; g++, gg++) {
+                // the tile's rows are about to be overwritten: its horizontal MMAs of the previous chunk must have
+                // finished -- which is also when their D2 can be drained
+                if ((g & 3) == 0 && chunk > 0) {
+                    if ((g >> 2) == 0) drain_d2(chunk - 1, 0, acc[0]);
+                    else drain_d2(chunk - 1, 1, acc[1]);
+                }
+                const uint32_t region = gg % NR2;
+                mbar_wait(smem_u32(&mbar[region]), (gg / NR2) & 1);  // the vertical MMAs of group gg have retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + TMEM_V0 + region * TC_N + ((q * 32u) << 16) + half * 16;
+                uint32_t hi[16], mid[16], lo[16];
+                tmem_ld16(taddr, hi);
+                tmem_ld16(taddr + 32, mid);
+                tmem_ld16(taddr + 64, lo);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_free[region])) : "memory");
+                uint32_t ph[8], pl[8];  // rows 2e, 2e + 1 of this half: f16x2 of the high and of the low halves
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {  // value = (hi 2^14 + mid 2^7 + lo) 2^-s, two rows per f32x2 op
+                    const float2 fh = make_float2(float(int(hi[e])), float(int(hi[e + 1])));
+                    const float2 fl = make_float2(float(int(mid[e]) * 128 + int(lo[e])), float(int(mid[e + 1]) * 128 + int(lo[e + 1])));
+                    float2 r = make_float2(0.f, 0.f);
+                    ffma2(r, fl, scale);
+                    ffma2(r, fh, scale_hi);
+                    const uint32_t h2 = pack_f16x2(r.x, r.y);
+                    const float2 back = unpack_f16x2(h2);
+                    ph[e / 2] = h2;
+                    pl[e / 2] = pack_f16x2(r.x - back.x, r.y - back.y);
+                }
+                // T[row][column m]: core matrices of 8 rows x 8 columns, 16 bytes = 8 rows of one column; a warp's
+                // 32 columns are 512 contiguous bytes per block of 8 rows
+                const uint32_t t0 = hp.sT_u + (g * 4 + half * 2) * 2048u + m * 16u;
+                sts128(t0, ph[0], ph[1], ph[2], ph[3]);
+                sts128(t0 + 2048, ph[4], ph[5], ph[6], ph[7]);
+                sts128(t0 + t_bytes, pl[0], pl[1], pl[2], pl[3]);
+                sts128(t0 + t_bytes + 2048, pl[4], pl[5], pl[6], pl[7]);
+                if ((g & 3) == 3 || g + 1 == n_groups) {  // the row tile is complete: hand it to the tensor core
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hp.t_ready + 8 * (g >> 2)) : "memory");
+                }
+            }
+        }
+        drain_d2(n_chunks - 1, 0, acc[0]);
+        if (n_mt > 1) drain_d2(n_chunks - 1, 1, acc[1]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+template <int C>
+void launch_tc2_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b, const uint32_t *d_info,
+                        LaunchCtx &lc) {
+    auto kern = fused_resample_tc2_kernel<C>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    lc.begin("fused_resample_tc2_kernel");
+    kern<<<n_items, NT_ALL2, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
+    lc.end();
+}
+
 template <int C>
 void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
                        const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
@@ -569,6 +897,15 @@ void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t
 int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
     if (n_items == 0) return 0;
+    if (c & 8) {  // both passes on the tensor cores
+        switch (c & 7) {
+        case 1: launch_tc2_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 2: launch_tc2_variant<2>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 3: launch_tc2_variant<3>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 4: launch_tc2_variant<4>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        }
+        return -1;
+    }
     switch (c) {
     case 1: launch_tc_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
     case 2: launch_tc_variant<2>(d_items, d_tmaps, n_items, smem, d_b, d_w, d_info, lc); return 1;
@@ -601,8 +938,10 @@ size_t fused_tc_smem_limit() {
     static size_t limit = 0;
     if (!limit) {
         size_t stat = 0;
-        const void *kerns[4] = {reinterpret_cast<const void *>(fused_resample_tc_kernel<1>), reinterpret_cast<const void *>(fused_resample_tc_kernel<2>),
-                                reinterpret_cast<const void *>(fused_resample_tc_kernel<3>), reinterpret_cast<const void *>(fused_resample_tc_kernel<4>)};
+        const void *kerns[8] = {reinterpret_cast<const void *>(fused_resample_tc_kernel<1>), reinterpret_cast<const void *>(fused_resample_tc_kernel<2>),
+                                reinterpret_cast<const void *>(fused_resample_tc_kernel<3>), reinterpret_cast<const void *>(fused_resample_tc_kernel<4>),
+                                reinterpret_cast<const void *>(fused_resample_tc2_kernel<1>), reinterpret_cast<const void *>(fused_resample_tc2_kernel<2>),
+                                reinterpret_cast<const void *>(fused_resample_tc2_kernel<3>), reinterpret_cast<const void *>(fused_resample_tc2_kernel<4>)};
         bool ok = true;
         for (const void *k : kerns) {
             cudaFuncAttributes fa{};

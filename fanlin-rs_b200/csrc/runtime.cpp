@@ -285,9 +285,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
     std::vector<uint8_t> gather_a(n_jobs, 0); // stage A is a Nearest resample: the compose kernel gathers through the tap tables
     std::vector<StagePlan> a_pre(n_jobs);     // present: stage A as the tensor-core kernel sees it behind a colour-op pass
-    std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(), fused_tc_cache_free);
+    std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(ctx->cfg.vertical_path == 0), fused_tc_cache_free);
     FusedTcTables tctabs;
-    const bool use_tc = ctx->cfg.vertical_path == 0;
+    const bool use_tc = ctx->cfg.vertical_path == 0 || ctx->cfg.vertical_path == 2;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
     std::vector<uint8_t> fast_b(n_jobs, 0);  // stage B takes the fast blur kernels
     BlurTables btabs;
     std::vector<BlurItem> bitems;
@@ -396,7 +396,10 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         std::map<uint32_t, std::vector<uint32_t>> tc_by_c;
         for (uint32_t i = begin; i < end; i++) {
             if (fused_a[i] == 1) by_variant[fused_variant(b->plans[i].a)].push_back(i);
-            if (fused_a[i] == 2) tc_by_c[b->plans[i].a.c].push_back(i);
+            if (fused_a[i] == 2) {  // key: channels | 8 when the horizontal stage runs on the tensor cores too (another kernel)
+                const StagePlan &ta = a_pre[i].present ? a_pre[i] : b->plans[i].a;
+                tc_by_c[ta.c | (fused_tc_uses_hmma(ta, tcache.get(), &ftabs, &tctabs) ? 8u : 0u)].push_back(i);
+            }
         }
         {  // orientation passes: the stored image turned (and its colour op applied) into scratch, in front of everything
             HostStep hs{6, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
@@ -451,7 +454,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             }
             hs.n_items = uint32_t(tcitems.size() - hs.first);
             for (size_t k = hs.first; k < tcitems.size(); k++)
-                hs.smem = std::max(hs.smem, fused_tc_smem_bytes(kv.first, tcitems[k].band_rows, tcitems[k].kg_max, tcitems[k].out_stride, tcitems[k].n_a));
+                hs.smem = std::max(hs.smem, fused_tc_item_smem(tcitems[k]));
             if (hs.n_items) hsteps.push_back(hs);
         }
         for (auto &kv : by_variant) {

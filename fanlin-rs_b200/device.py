@@ -178,9 +178,11 @@ class Device:
     """fanlin_ctx: created once at start-up, shared by all request threads."""
 
     def __init__(self, device_ids=None, *, exact=False, device_scratch_bytes=0, pinned_bytes=0,
-                 batch_window_us=0, max_batch_jobs=0, tensor_cores=True):
+                 batch_window_us=0, max_batch_jobs=0, tensor_cores=True, vertical_path=None):
+        """vertical_path: None = from tensor_cores (0 / 1); 2 = tensor cores for the vertical pass only
+        (the horizontal stage stays on the CUDA cores)."""
         cfg = Config(C.sizeof(Config), int(exact), device_scratch_bytes, pinned_bytes, batch_window_us, max_batch_jobs,
-                     0 if tensor_cores else 1, 0)
+                     (0 if tensor_cores else 1) if vertical_path is None else int(vertical_path), 0)
         h = C.c_void_p()
         if device_ids:
             arr = (C.c_int * len(device_ids))(*device_ids)
