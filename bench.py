@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check (kernel ablation runs only)")
     ap.add_argument("--exact", action="store_true", help="bit-exact kernels (crate operation order)")
+    ap.add_argument("--vertical-path", type=int, default=0, help="0: tensor cores (default), 1: CUDA cores, 2: tensor cores for the vertical pass only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))
@@ -207,7 +208,7 @@ def main():
     peak, peak_src = load_peaks()
     warm = max(args.warmup, 3)
 
-    dev = pkg.Device([local_rank], exact=args.exact)
+    dev = pkg.Device([local_rank], exact=args.exact, vertical_path=args.vertical_path)
     n = args.batch
     src = synth_batch_on_device(torch, n, 2000 + rank, device)
     dst = torch.zeros((n, OUT_H, OUT_W, OUT_C), dtype=torch.uint8, device=device)

@@ -63,18 +63,30 @@ __device__ __forceinline__ void emit_px(const ITEM &it, uint32_t cx, uint32_t cy
 
 
 // Letterbox bars of a band: canvas pixels outside the placed rect (and the rows above /
-// below the image for the first / last band) get the fill colour.
+// below the image for the first / last band) get the fill colour.  Only the bar pixels are
+// visited, and every field of the item is read once: the item lives in shared memory and the
+// stores go through generic pointers, so the compiler would re-read it around every store
+// (measured: 58 k clk per 300 x 200 canvas for the pixel-by-pixel test of the whole canvas,
+// 12 % of a C2 image's time on the SM).
 template <typename ITEM>
 __device__ __forceinline__ void fill_bars(const ITEM &it, uint32_t warp, uint32_t lane, uint32_t n_warps) {
     if (it.epi != EPI_BLEND_FILL) return;
-    const uint32_t ya = it.first_band ? 0u : it.dst_y + it.band_r0;
-    const uint32_t yb = it.last_band ? it.canvas_h : it.dst_y + it.band_r0 + it.band_rows;
+    uint8_t *const dst = it.dst;
+    const uint32_t pitch = it.dst_pitch, cw = it.canvas_w, fill = it.fill;
     const uint32_t iy0 = it.dst_y + it.band_r0, iy1 = iy0 + it.band_rows;
-    for (uint32_t y = ya + warp; y < yb; y += n_warps) {
-        const bool inside_rows = y >= iy0 && y < iy1;
-        for (uint32_t x = lane; x < it.canvas_w; x += 32)
-            if (!inside_rows || x < it.dst_x || x >= it.dst_x + it.n_cols)
-                store_rgba(it.dst + size_t(y) * it.dst_pitch + size_t(x) * 4, it.fill);
+    const uint32_t ya = it.first_band ? 0u : iy0, yb = it.last_band ? it.canvas_h : iy1;
+    const uint32_t x0 = it.dst_x, x1 = it.dst_x + it.n_cols;
+    const uint32_t n_top = iy0 - ya, n_full = n_top + (yb - iy1);  // whole rows above and below the image rows
+    for (uint32_t k = warp; k < n_full; k += n_warps) {
+        uint8_t *row = dst + size_t(k < n_top ? ya + k : iy1 + (k - n_top)) * pitch;
+        for (uint32_t x = lane; x < cw; x += 32) store_rgba(row + size_t(x) * 4, fill);
+    }
+    const uint32_t n_side = x0 + (cw - x1);  // bar pixels left and right of the image in its rows
+    if (n_side) {
+        for (uint32_t y = iy0 + warp; y < iy1; y += n_warps) {
+            uint8_t *row = dst + size_t(y) * pitch;
+            for (uint32_t k = lane; k < n_side; k += 32) store_rgba(row + size_t(k < x0 ? k : x1 + (k - x0)) * 4, fill);
+        }
     }
 }
 

@@ -108,15 +108,16 @@ FusedTcCache *fused_tc_cache_new(bool allow_hmma) {
 }
 
 // ---- tensor-core horizontal stage ---------------------------------------------------------------
-size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh) {
+size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t band_rows, uint32_t out_stride) {
+    const size_t out = size_t(band_rows) * out_stride * 4;  // output pixels finished in a chunk
     const size_t a = size_t(n_a) * kg_max * TC_M, b = 2 * size_t(TC_N) * kg_max;  // source slots, two vertical weight-tile slots
     const size_t wh = size_t(n_wh) * fused_tc2_n(c) * 512;                        // hi + lo tiles [N2][128] f16
     const size_t t = 2 * size_t(n_groups) * 32 * 256;                             // T hi + lo: [32 rows per group][128] f16
-    return a + b + wh + t + 1024;
+    return a + b + wh + t + out;  // the kernel's static shared memory is a multiple of 1024 bytes: the dynamic part starts aligned
 }
 
 size_t fused_tc_item_smem(const FusedTcItem &it) {
-    return it.hmma ? fused_tc2_smem_bytes(it.c, it.n_groups, it.kg_max, it.n_a, it.n_wh)
+    return it.hmma ? fused_tc2_smem_bytes(it.c, it.n_groups, it.kg_max, it.n_a, it.n_wh, it.band_rows, it.out_stride)
                    : fused_tc_smem_bytes(it.c, it.band_rows, it.kg_max, it.out_stride, it.n_a);
 }
 void fused_tc_cache_free(FusedTcCache *c) { delete c; }
@@ -303,6 +304,17 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
     // keeps its rows as f16 hi / lo tiles (32 rows per group, <= 8 groups = two M = 128 tiles) next to >= 2 source slots.
     if (cache->allow_hmma) {
         const int sh = weight_shift(*s.vtab);
+        uint32_t hm_out_stride = 1;
+        {  // most outputs a chunk finishes -> words per row of the output staging buffer (odd: rows on distinct banks)
+            uint32_t fin = s.ox0, widest = 0;
+            for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+                const uint32_t b1 = g.b0 + TC_M * (ch + 1), first = fin;
+                while (fin < s.ox0 + s.n_cols && (s.htab->entries[fin].left + s.htab->entries[fin].count) * C <= b1) fin++;
+                widest = std::max(widest, fin - first);
+            }
+            widest = std::max(widest, s.ox0 + s.n_cols - fin + 1);
+            hm_out_stride = ((widest * s.c_out + 6) / 4) | 1u;
+        }
         bool fits = false;
         uint32_t n_bands = 1, band_rows = s.n_rows;
         for (; n_bands <= 8 && !fits; n_bands++) {
@@ -311,12 +323,13 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
             for (uint32_t r0 = 0; r0 < s.n_rows && fits; r0 += band_rows) {
                 uint32_t ng = 0, kgm = 0;
                 fits = plan_band(*s.vtab, s.oy0, r0, std::min(band_rows, s.n_rows - r0), 8, &ng, &kgm) && ng <= 8 &&
-                       fused_tc2_smem_bytes(C, ng, kgm, 2, 1) <= TC_SMEM_LIMIT;
+                       fused_tc2_smem_bytes(C, ng, kgm, 2, 1, std::min(band_rows, s.n_rows - r0), hm_out_stride) <= TC_SMEM_LIMIT;
             }
             if (fits) break;
         }
         if (fits && build_hmma(s, g, tabs, tct)) {
             g.scale = std::ldexp(1.0f, -sh);
+            g.out_stride = hm_out_stride;
             bool okb = true;
             for (uint32_t r0 = 0; r0 < s.n_rows && okb; r0 += band_rows) {
                 TcBand bt{};
@@ -431,8 +444,8 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         if (g.hm) {
             f.hmma = 1; f.hrec_off = g.hrec_off;
             f.n_a = 4; f.n_wh = 1;
-            while (f.n_a > 2 && fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 1) > TC_SMEM_LIMIT) f.n_a--;
-            if (fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 2) <= TC_SMEM_LIMIT) f.n_wh = 2;
+            while (f.n_a > 2 && fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 1, bt.rows, g.out_stride) > TC_SMEM_LIMIT) f.n_a--;
+            if (fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 2, bt.rows, g.out_stride) <= TC_SMEM_LIMIT) f.n_wh = 2;
         }
         items->push_back(f);
     }

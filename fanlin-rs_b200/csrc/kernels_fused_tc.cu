@@ -42,6 +42,9 @@ constexpr uint32_t SLAB = 32 * TC_M;  // one K step of A: 32 source rows x 128 b
 constexpr uint32_t NA_MAX = 4;    // most shared-memory slots for a group's source rows
 constexpr uint32_t NR = 5;        // TMEM accumulator regions of 96 columns
 constexpr int S = FUSED_SLOTS;
+#ifndef TC_PF_AHEAD
+#define TC_PF_AHEAD 6
+#endif
 constexpr uint32_t TMEM_COLS = 512;  // NR regions of 96 columns
 
 // Shared-memory matrix descriptor, no swizzle.  Measured on B200
@@ -76,6 +79,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     }
 }
+
+#ifdef TC2_PROF
+#define PW(acc, ...) do { const long long t0_ = clock64(); mbar_wait(__VA_ARGS__); (acc) += clock64() - t0_; } while (0)
+#else
+#define PW(acc, ...) mbar_wait(__VA_ARGS__)
+#endif
 
 __device__ __forceinline__ void ffma2(float2 &acc, float2 a, float w) {
     const float2 b = make_float2(w, w);
@@ -119,6 +128,7 @@ struct TcPipe {
     uint32_t kg_max, n_a, n_chunks, n_groups;
     uint32_t x0;                                // byte offset of chunk 0 in a row (16-byte aligned)
     uint32_t tmem_base;
+    uint32_t pf_ahead;                          // groups the L2 prefetch runs ahead of the copies (0 = off)
     const uint32_t *grp;                        // {k0, kg, b_off, rows} x n_groups, in shared memory
 };
 
@@ -127,7 +137,17 @@ template <uint32_t NRT = NR>
 __device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMap *tmap) {
     const uint32_t total = p.n_chunks * p.n_groups;
     uint32_t g = 0, chunk = 0, slot = 0;
+    // L2 prefetch cursor: the box of group gg + pf_ahead is requested into L2 when group gg's copy is issued, so that
+    // the copy itself (issued when a slot frees up) finds its lines in L2
+    uint32_t pg = 0, pchunk = 0;
+    const uint32_t pf_ahead = p.pf_ahead;
+    for (uint32_t k = 0; k < pf_ahead && pchunk < p.n_chunks; k++)
+        if (++pg == p.n_groups) { pg = 0; pchunk++; }
     for (uint32_t gg = 0; gg < total; gg++) {
+        if (pf_ahead && pchunk < p.n_chunks) {
+            asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(p.x0 + TC_M * pchunk), "r"(p.grp[4 * pg]) : "memory");
+            if (++pg == p.n_groups) { pg = 0; pchunk++; }
+        }
         if (gg >= p.n_a) mbar_wait(p.mbar + 8 * ((gg - p.n_a) % NRT), ((gg - p.n_a) / NRT) & 1);  // the slot was read by the MMAs of group gg - n_a
         const uint32_t bar = p.a_full + 8 * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.kg_max * TC_M) : "memory");
@@ -280,7 +300,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
     TcPipe pipe;
     pipe.mbar = smem_u32(&mbar[0]); pipe.tmem_free = smem_u32(&tmem_free[0]); pipe.a_full = smem_u32(&a_full[0]); pipe.b_full = smem_u32(&b_full[0]);
     pipe.sA_u = sA_u; pipe.sB_u = sB_u; pipe.kg_max = kg_max; pipe.n_a = n_a; pipe.n_chunks = n_chunks; pipe.n_groups = n_groups;
-    pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp;
+    pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp; pipe.pf_ahead = TC_PF_AHEAD;
 
     if (warp == NT / 32 + 1) {
         if (elect_one()) tc_source_role(pipe, tmap);
@@ -523,7 +543,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) blur_v_tc_kernel(const BlurVTcItem 
     pipe.mbar = smem_u32(&mbar[0]); pipe.tmem_free = smem_u32(&tmem_free[0]); pipe.a_full = smem_u32(&a_full[0]); pipe.b_full = smem_u32(&b_full[0]);
     pipe.sA_u = smem_u32(smem); pipe.sB_u = pipe.sA_u + it.n_a * it.kg_max * TC_M;
     pipe.kg_max = it.kg_max; pipe.n_a = it.n_a; pipe.n_chunks = it.n_chunks; pipe.n_groups = it.n_groups;
-    pipe.x0 = 0; pipe.tmem_base = tmem_base_s; pipe.grp = grp;
+    pipe.x0 = 0; pipe.tmem_base = tmem_base_s; pipe.grp = grp; pipe.pf_ahead = 0;
     if (warp == NT / 32 + 1) {
         if (elect_one()) tc_source_role(pipe, tmaps + blockIdx.x);
     } else if (warp == NT / 32 + 2) {
@@ -612,13 +632,15 @@ template <uint32_t N2>
 __device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) {
     constexpr uint32_t IDESC_H = (1u << 4) | (1u << 15) | ((N2 >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
     const uint32_t total = p.n_chunks * p.n_groups;
+    long long w_b = 0, w_a = 0, w_tf = 0, w_wh = 0, w_tr = 0, w_df = 0;
+    const long long t_start = clock64();
     uint32_t h_ch = 0, h_mt = 0;  // next horizontal MMA batch: chunk, row tile
     uint32_t h_trigger = min(3u, p.n_groups - 1) + H_LAG;
     auto issue_h = [&]() {
         const uint32_t slot = h_ch % h.n_wh;
-        if (h_mt == 0) mbar_wait(h.wh_full + 8 * slot, (h_ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
-        mbar_wait(h.t_ready + 8 * h_mt, h_ch & 1);                            // the consumers have written the tile's rows
-        if (h_ch > 0) mbar_wait(h.d2_free + 8 * h_mt, (h_ch - 1) & 1);        // ... and read the previous chunk's D2
+        if (h_mt == 0) PW(w_wh, h.wh_full + 8 * slot, (h_ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
+        PW(w_tr, h.t_ready + 8 * h_mt, h_ch & 1);                            // the consumers have written the tile's rows
+        if (h_ch > 0) PW(w_df, h.d2_free + 8 * h_mt, (h_ch - 1) & 1);        // ... and read the previous chunk's D2
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_hi = h.sT_u + h_mt * 32768u, a_lo = a_hi + h.t_bytes;
         const uint32_t b_hi = h.sWh_u + slot * N2 * 512u, b_lo = b_hi + N2 * 256u;
@@ -650,9 +672,9 @@ __device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) 
     for (uint32_t gg = 0; gg < total; gg++) {
         const uint32_t region = gg % NR2, ruse = gg / NR2, bslot = gg % NB;
         const uint32_t kg = p.grp[4 * g + 1];
-        mbar_wait(p.b_full + 8 * bslot, (gg / NB) & 1);
-        mbar_wait(p.a_full + 8 * slot, suse & 1);
-        if (ruse > 0) mbar_wait(p.tmem_free + 8 * region, (ruse - 1) & 1);
+        PW(w_b, p.b_full + 8 * bslot, (gg / NB) & 1);
+        PW(w_a, p.a_full + 8 * slot, suse & 1);
+        if (ruse > 0) PW(w_tf, p.tmem_free + 8 * region, (ruse - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t da = umma_desc(p.sA_u + slot * p.kg_max * TC_M, 16, 1024, 2);
         uint64_t db = umma_desc(p.sB_u + bslot * TC_N * p.kg_max, 128, (kg / 16) * 128);
@@ -673,6 +695,13 @@ __device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) 
         while (h_ch < p.n_chunks && h_trigger <= gg) issue_h();
     }
     while (h_ch < p.n_chunks) issue_h();
+#ifdef TC2_PROF
+    if (blockIdx.x == 300)
+        printf("MMA thread: total %lld clk; waits: vertical weights %lld, source rows %lld, TMEM region %lld, horizontal weights %lld, T tile %lld, D2 drained %lld\n",
+               clock64() - t_start, w_b, w_a, w_tf, w_wh, w_tr, w_df);
+#else
+    (void)t_start; (void)w_b; (void)w_a; (void)w_tf; (void)w_wh; (void)w_tr; (void)w_df;
+#endif
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t r[8]) {
@@ -707,6 +736,12 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
     __shared__ uint32_t grp[4 * 8];
     const uint32_t tid = threadIdx.x;
     const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+#ifdef TC2_PROF
+    const long long t_entry = clock64();
+    unsigned long long g_entry;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+    long long t_roles = 0, t_p1 = 0, t_p2 = 0;
+#endif
     if (tid == 0) {
         it_s = items[blockIdx.x];
         for (uint32_t r = 0; r < NR2; r++) {
@@ -734,8 +769,13 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const FusedTcItem &it = it_s;
     const uint32_t tmem_base = tmem_base_s;
-
+#ifdef TC2_PROF
+    t_p1 = clock64();
+#endif
     if (warp < NT / 32) fill_bars(it, warp, lane, NT / 32);
+#ifdef TC2_PROF
+    t_p2 = clock64();
+#endif
 
     // ---- shared-memory carve-up: T hi | T lo | source slots | vertical weight slots | horizontal weight slots.
     // The horizontal MMAs always read 128 rows per tile: behind a tile of fewer groups they read into
@@ -746,18 +786,23 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
     uint8_t *sA = sT + 2 * size_t(t_bytes);
     uint8_t *sB = sA + size_t(n_a) * kg_max * TC_M;
     uint8_t *sWh = sB + NB * size_t(TC_N) * kg_max;
+    // pixels finished by a chunk wait here, [band row][out_stride words], and leave as whole words per row segment
+    uint32_t *out_s = reinterpret_cast<uint32_t *>(sWh + size_t(it.n_wh) * N2 * 512u);
     for (uint32_t k = tid; k < 4 * n_groups; k += NT_ALL2) grp[k] = tinfo[it.grp_off + k];
     __syncthreads();
 
     TcPipe pipe;
     pipe.mbar = smem_u32(&mbar[0]); pipe.tmem_free = smem_u32(&tmem_free[0]); pipe.a_full = smem_u32(&a_full[0]); pipe.b_full = smem_u32(&b_full[0]);
     pipe.sA_u = smem_u32(sA); pipe.sB_u = smem_u32(sB); pipe.kg_max = kg_max; pipe.n_a = n_a; pipe.n_chunks = n_chunks; pipe.n_groups = n_groups;
-    pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp;
+    pipe.x0 = it.b0; pipe.tmem_base = tmem_base; pipe.grp = grp; pipe.pf_ahead = TC_PF_AHEAD;
     Tc2Pipe hp;
     hp.t_ready = smem_u32(&t_ready[0]); hp.d2_full = smem_u32(&d2_full[0]); hp.d2_free = smem_u32(&d2_free[0]); hp.wh_full = smem_u32(&wh_full[0]); hp.wh_free = smem_u32(&wh_free[0]);
     hp.sT_u = smem_u32(sT); hp.t_bytes = t_bytes; hp.sWh_u = smem_u32(sWh); hp.n_wh = it.n_wh; hp.n_mt = (n_groups + 3) / 4;
     const uint32_t *hrec = tinfo + it.hrec_off;
 
+#ifdef TC2_PROF
+    t_roles = clock64();
+#endif
     if (warp == NT / 32 + 1) {
         if (elect_one()) tc_source_role<NR2>(pipe, tmaps + blockIdx.x);
     } else if (warp == NT / 32 + 2) {
@@ -771,6 +816,42 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
         const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
         const uint32_t grp_rows = it.grp_rows, n_mt = hp.n_mt;
+        const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows, h_epi = it.epi, h_fill = it.fill;
+        const uint32_t out_stride = it.out_stride, out_u = smem_u32(out_s);
+        uint8_t *const h_row0 = it.dst + size_t(it.dst_y + it.band_r0) * it.dst_pitch + size_t(it.dst_x) * h_cout;  // first canvas byte of the band
+        const uint32_t h_ph0 = uint32_t(reinterpret_cast<uintptr_t>(h_row0));
+        const bool h_words = h_cout == 4 && ((reinterpret_cast<uintptr_t>(h_row0) | h_pitch) & 3) == 0;
+        // the pixels a chunk finished, staged by drain_d2, leave as whole words per row segment
+        auto write_out = [&](uint32_t chunk) {
+            const uint32_t o_first = __ldg(hrec + 3 * chunk + 1), o_count = __ldg(hrec + 3 * chunk + 2);
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // every row's pixels are staged
+            if (const uint32_t nb = o_count * h_cout; nb && h_words) {
+                uint32_t *gq = reinterpret_cast<uint32_t *>(h_row0) + o_first + (tid >> 3) * (h_pitch >> 2) + (tid & 7);
+                const uint32_t *sq = out_s + (tid >> 3) * out_stride + (tid & 7);
+                const uint32_t g_step = (NT / 8) * (h_pitch >> 2), s_step = (NT / 8) * out_stride;
+                for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8, gq += g_step, sq += s_step)
+                    for (uint32_t k = tid & 7; k < o_count; k += 8) gq[k - (tid & 7)] = sq[k - (tid & 7)];
+            } else if (nb) {
+                for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8) {  // 8 lanes per row segment
+                    uint8_t *g0 = h_row0 + size_t(r) * h_pitch + size_t(o_first) * h_cout;
+                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(g0)) & 3u;
+                    const uint32_t nw = (ph + nb + 3) >> 2;
+                    for (uint32_t k = tid & 7; k < nw; k += 8) {
+                        const uint32_t wv = out_s[r * out_stride + k];
+                        uint8_t *gw = g0 - ph + 4 * k;
+                        const int lo = int(ph) - int(4 * k), hi = int(ph + nb) - int(4 * k);  // the word's valid bytes: [lo, hi)
+                        if (lo <= 0 && hi >= 4) {
+                            *reinterpret_cast<uint32_t *>(gw) = wv;
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < 4; b++)
+                                if (b >= lo && b < hi) gw[b] = uint8_t(wv >> (8 * b));
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the staging buffer may be overwritten
+        };
         float acc[2][HP][C];  // partial sums of this thread's band row (one per row tile) for its half of the output ring
 #pragma unroll
         for (int t = 0; t < 2; t++)
@@ -780,8 +861,13 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
                 for (int c = 0; c < C; c++) acc[t][k][c] = 0.f;
 
         // D2 of (chunk, row tile) -> registers; pixels whose window ended in the chunk are rounded and stored
+        long long w_v = 0, w_d2 = 0, t_d2 = 0;
+        const long long t_start = clock64();
         auto drain_d2 = [&](uint32_t chunk, uint32_t mt, float (&a)[HP][C]) {
-            mbar_wait(hp.d2_full + 8 * mt, chunk & 1);
+#ifdef TC2_PROF
+            const long long td0 = clock64();
+#endif
+            PW(w_d2, hp.d2_full + 8 * mt, chunk & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t v[N2 / 2];
             const uint32_t taddr = tmem_base + mt * N2 + ((q * 32u) << 16) + half * (N2 / 2);
@@ -797,8 +883,11 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hp.d2_free + 8 * mt) : "memory");
             const uint32_t g = mt * 4 + q;
             const bool row_ok = g < n_groups && lane < grp[4 * min(g, n_groups - 1) + 3];
-            const uint32_t cy = it.dst_y + it.band_r0 + g * grp_rows + lane;
+            const uint32_t row = min(g * grp_rows + lane, h_rows - 1);
             const uint32_t fin_first = __ldg(hrec + 3 * chunk + 1), n_fin = __ldg(hrec + 3 * chunk + 2);
+            // staging byte address of this row's first finished pixel: the row segment keeps the alignment phase
+            // of its canvas address so that staged words are canvas words
+            const uint32_t sp = out_u + row * out_stride * 4 + ((h_ph0 + row * h_pitch + fin_first * h_cout) & 3u);
 #pragma unroll
             for (int k = 0; k < int(HP); k++) {
 #pragma unroll
@@ -809,12 +898,28 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
                         uint32_t u[4] = {0, 0, 0, 0};
 #pragma unroll
                         for (int c = 0; c < C; c++) u[c] = round_u8(a[k][c] * (1.0f / TC2_WSCALE));
-                        emit_px<C>(it, it.dst_x + fin_first + d, cy, u);
+                        const uint32_t sq = sp + d * h_cout;
+                        if (h_epi == EPI_PLAIN) {
+#pragma unroll
+                            for (int c = 0; c < C; c++) sts8(sq + c, u[c]);
+                        } else {
+                            uint32_t px = to_rgba_packed(u, C);
+                            if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
+                            if (h_words) {
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sq), "r"(px) : "memory");
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; c++) sts8(sq + c, px >> (8 * c));
+                            }
+                        }
                     }
 #pragma unroll
                     for (int c = 0; c < C; c++) a[k][c] = 0.f;
                 }
             }
+#ifdef TC2_PROF
+            t_d2 += clock64() - td0;
+#endif
         };
 
         uint32_t gg = 0;
@@ -825,9 +930,10 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
                 if ((g & 3) == 0 && chunk > 0) {
                     if ((g >> 2) == 0) drain_d2(chunk - 1, 0, acc[0]);
                     else drain_d2(chunk - 1, 1, acc[1]);
+                    if ((g >> 2) + 1 == n_mt) write_out(chunk - 1);
                 }
                 const uint32_t region = gg % NR2;
-                mbar_wait(smem_u32(&mbar[region]), (gg / NR2) & 1);  // the vertical MMAs of group gg have retired
+                PW(w_v, smem_u32(&mbar[region]), (gg / NR2) & 1);  // the vertical MMAs of group gg have retired
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + TMEM_V0 + region * TC_N + ((q * 32u) << 16) + half * 16;
                 uint32_t hi[16], mid[16], lo[16];
@@ -866,10 +972,24 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
         }
         drain_d2(n_chunks - 1, 0, acc[0]);
         if (n_mt > 1) drain_d2(n_chunks - 1, 1, acc[1]);
+        write_out(n_chunks - 1);
+#ifdef TC2_PROF
+        if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 5))
+            printf("consumer warp %u: total %lld clk; waits: vertical results %lld, D2 %lld; D2 drain + emit (incl. wait) %lld\n", warp, clock64() - t_start, w_v, w_d2, t_d2);
+#else
+        (void)t_start; (void)w_v; (void)w_d2; (void)t_d2;
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+#ifdef TC2_PROF
+    if (tid == 0 && (blockIdx.x == 300 || blockIdx.x == 301 || blockIdx.x == 450 || blockIdx.x == 10)) {
+        unsigned long long g_exit;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+        printf("CTA %u: entry at %llu ns, lifetime %llu ns = %lld clk, prologue %lld clk (init %lld, bars %lld, tables %lld)\n", blockIdx.x, g_entry, g_exit - g_entry, clock64() - t_entry, t_roles - t_entry, t_p1 - t_entry, t_p2 - t_p1, t_roles - t_p2);
+    }
+#endif
 }
 
 template <int C>
