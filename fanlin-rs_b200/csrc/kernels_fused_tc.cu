@@ -601,10 +601,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) blur_v_tc_kernel(const BlurVTcItem 
 // of the <= N2 / c outputs whose windows meet the chunk; each consumer thread owns one band row
 // and half of the ring in registers, adds the partial sums and, when a pixel's window has ended,
 // rounds and stores it.  The CUDA cores only drain, convert and store.
-constexpr int NT_ALL2 = NT + 128;   // + the MMA warp, the source / vertical-weight / horizontal-weight TMA warps
+constexpr int NT_ALL2 = NT + 128;   // + the vertical MMA warp, the source / vertical-weight TMA warps, the horizontal (weights + MMA) warp
 constexpr uint32_t NR2 = 4;          // TMEM regions of the vertical pass (96 columns each, from column 128)
 constexpr uint32_t TMEM_V0 = 128;    // columns [0, 128): D2 of the two row tiles
-constexpr uint32_t H_LAG = 2;        // vertical groups issued between a row tile's last group and its horizontal MMAs
 
 struct Tc2Pipe {
     uint32_t t_ready, d2_full, d2_free, wh_full, wh_free;  // mbarrier arrays (8 bytes per entry)
@@ -613,61 +612,82 @@ struct Tc2Pipe {
     uint32_t n_mt;                                // row tiles (1 or 2)
 };
 
-// horizontal-weight TMA thread: one bulk copy per chunk into slot chunk % n_wh, after the horizontal MMAs of the chunk that used it
+// Horizontal thread: fetches the chunk's weight tiles (one bulk copy into slot chunk % n_wh) and issues the 24
+// horizontal MMAs of a row tile as soon as the consumers have written it.  A thread of its own: the vertical
+// MMA thread never waits behind a row tile that is not ready, and the tensor pipe interleaves the two streams.
 template <uint32_t N2>
-__device__ __forceinline__ void tc2_wh_role(const TcPipe &p, const Tc2Pipe &h, const uint8_t *tb, const uint32_t *hrec) {
-    for (uint32_t ch = 0; ch < p.n_chunks; ch++) {
-        if (ch >= h.n_wh) mbar_wait(h.wh_free + 8 * (ch % h.n_wh), (ch / h.n_wh - 1) & 1);  // the slot's previous tiles were read
-        const uint32_t bar = h.wh_full + 8 * (ch % h.n_wh);
+__device__ __forceinline__ void tc2_h_role(const TcPipe &p, const Tc2Pipe &h, const uint8_t *tb, const uint32_t *hrec) {
+    constexpr uint32_t IDESC_H = (1u << 4) | (1u << 15) | ((N2 >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
+    long long w_wh = 0, w_tr = 0, w_df = 0, w_wf = 0, i_h = 0;
+    const long long t_start = clock64();
+    auto load_wh = [&](uint32_t ch) {
+        const uint32_t slot = ch % h.n_wh, bar = h.wh_full + 8 * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(N2 * 512u) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(h.sWh_u + (ch % h.n_wh) * N2 * 512u),
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(h.sWh_u + slot * N2 * 512u),
                      "l"(tb + __ldg(hrec + 3 * ch)), "r"(N2 * 512u), "r"(bar)
                      : "memory");
+    };
+    load_wh(0);
+    for (uint32_t ch = 0; ch < p.n_chunks; ch++) {
+        const uint32_t slot = ch % h.n_wh;
+        if (h.n_wh == 2 && ch + 1 < p.n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
+            if (ch >= 1) PW(w_wf, h.wh_free + 8 * ((ch + 1) & 1), ((ch - 1) >> 1) & 1);
+            load_wh(ch + 1);
+        }
+        PW(w_wh, h.wh_full + 8 * slot, (ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
+        for (uint32_t mt = 0; mt < h.n_mt; mt++) {
+            PW(w_tr, h.t_ready + 8 * mt, ch & 1);                    // the consumers have written the tile's rows
+            if (ch > 0) PW(w_df, h.d2_free + 8 * mt, (ch - 1) & 1);  // ... and read the previous chunk's D2
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef TC2_PROF
+            const long long ti0 = clock64();
+#endif
+            const uint32_t a_hi = h.sT_u + mt * 32768u, a_lo = a_hi + h.t_bytes;
+            const uint32_t b_hi = h.sWh_u + slot * N2 * 512u, b_lo = b_hi + N2 * 256u;
+            const uint32_t d_tmem = p.tmem_base + mt * N2;
+#pragma unroll
+            for (int combo = 0; combo < 3; combo++) {
+                uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);  // LBO: next 8 columns (K), SBO: next 8 rows (M)
+                uint64_t db = umma_desc(combo == 2 ? b_lo : b_hi, 128, 2048);  // LBO: next 8 columns (K), SBO: next 8 accumulator columns (N)
+#pragma unroll
+                for (int ks = 0; ks < 8; ks++) {
+                    if (combo == 0 && ks == 0)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
+                                     "l"(db), "r"(IDESC_H)
+                                     : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
+                                     "l"(db), "r"(IDESC_H)
+                                     : "memory");
+                    da += 256 >> 4;  // 16 columns = two core matrices along K
+                    db += 256 >> 4;
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(h.d2_full + 8 * mt) : "memory");
+            if (mt + 1 == h.n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(h.wh_free + 8 * slot) : "memory");
+#ifdef TC2_PROF
+            i_h += clock64() - ti0;
+#endif
+        }
+        if (h.n_wh == 1 && ch + 1 < p.n_chunks) {  // the only slot: its tiles were read once the chunk's MMAs have retired
+            PW(w_wf, h.wh_free, ch & 1);
+            load_wh(ch + 1);
+        }
     }
+#ifdef TC2_PROF
+    if (blockIdx.x == 300)
+        printf("horizontal thread: total %lld clk; waits: weights landed %lld, T tile %lld, D2 drained %lld, weight slot free %lld; issue %lld\n", clock64() - t_start, w_wh,
+               w_tr, w_df, w_wf, i_h);
+#else
+    (void)t_start; (void)w_wh; (void)w_tr; (void)w_df; (void)w_wf; (void)i_h;
+#endif
 }
 
-// MMA thread: the vertical groups as in tc_mma_role (regions of NR2), and H_LAG groups after the last
-// group of a row tile, that tile's 24 horizontal MMAs
-template <uint32_t N2>
-__device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) {
-    constexpr uint32_t IDESC_H = (1u << 4) | (1u << 15) | ((N2 >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
+// Vertical MMA thread: tc_mma_role with NR2 regions behind the D2 columns
+__device__ __forceinline__ void tc2_v_role(const TcPipe &p) {
     const uint32_t total = p.n_chunks * p.n_groups;
-    long long w_b = 0, w_a = 0, w_tf = 0, w_wh = 0, w_tr = 0, w_df = 0;
+    long long w_b = 0, w_a = 0, w_tf = 0, i_v = 0;
     const long long t_start = clock64();
-    uint32_t h_ch = 0, h_mt = 0;  // next horizontal MMA batch: chunk, row tile
-    uint32_t h_trigger = min(3u, p.n_groups - 1) + H_LAG;
-    auto issue_h = [&]() {
-        const uint32_t slot = h_ch % h.n_wh;
-        if (h_mt == 0) PW(w_wh, h.wh_full + 8 * slot, (h_ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
-        PW(w_tr, h.t_ready + 8 * h_mt, h_ch & 1);                            // the consumers have written the tile's rows
-        if (h_ch > 0) PW(w_df, h.d2_free + 8 * h_mt, (h_ch - 1) & 1);        // ... and read the previous chunk's D2
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_hi = h.sT_u + h_mt * 32768u, a_lo = a_hi + h.t_bytes;
-        const uint32_t b_hi = h.sWh_u + slot * N2 * 512u, b_lo = b_hi + N2 * 256u;
-        const uint32_t d_tmem = p.tmem_base + h_mt * N2;
-#pragma unroll
-        for (int combo = 0; combo < 3; combo++) {
-            uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);  // LBO: next 8 columns (K), SBO: next 8 rows (M)
-            uint64_t db = umma_desc(combo == 2 ? b_lo : b_hi, 128, 2048);  // LBO: next 8 columns (K), SBO: next 8 accumulator columns (N)
-#pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-                if (combo == 0 && ks == 0)
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
-                                 "l"(db), "r"(IDESC_H)
-                                 : "memory");
-                else
-                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
-                                 "l"(db), "r"(IDESC_H)
-                                 : "memory");
-                da += 256 >> 4;  // 16 columns = two core matrices along K
-                db += 256 >> 4;
-            }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(h.d2_full + 8 * h_mt) : "memory");
-        if (h_mt + 1 == h.n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(h.wh_free + 8 * slot) : "memory");
-        if (++h_mt == h.n_mt) { h_mt = 0; h_ch++; }
-        h_trigger = h_ch * p.n_groups + min(4 * h_mt + 3, p.n_groups - 1) + H_LAG;
-    };
     uint32_t g = 0, slot = 0, suse = 0;
     for (uint32_t gg = 0; gg < total; gg++) {
         const uint32_t region = gg % NR2, ruse = gg / NR2, bslot = gg % NB;
@@ -676,6 +696,9 @@ __device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) 
         PW(w_a, p.a_full + 8 * slot, suse & 1);
         if (ruse > 0) PW(w_tf, p.tmem_free + 8 * region, (ruse - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef TC2_PROF
+        const long long tv0 = clock64();
+#endif
         uint64_t da = umma_desc(p.sA_u + slot * p.kg_max * TC_M, 16, 1024, 2);
         uint64_t db = umma_desc(p.sB_u + bslot * TC_N * p.kg_max, 128, (kg / 16) * 128);
         const uint32_t d_tmem = p.tmem_base + TMEM_V0 + region * TC_N;
@@ -690,17 +713,17 @@ __device__ __forceinline__ void tc2_mma_role(const TcPipe &p, const Tc2Pipe &h) 
                          : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(p.mbar + 8 * region) : "memory");
+#ifdef TC2_PROF
+        i_v += clock64() - tv0;
+#endif
         if (++slot == p.n_a) { slot = 0; suse++; }
         if (++g == p.n_groups) g = 0;
-        while (h_ch < p.n_chunks && h_trigger <= gg) issue_h();
     }
-    while (h_ch < p.n_chunks) issue_h();
 #ifdef TC2_PROF
     if (blockIdx.x == 300)
-        printf("MMA thread: total %lld clk; waits: vertical weights %lld, source rows %lld, TMEM region %lld, horizontal weights %lld, T tile %lld, D2 drained %lld\n",
-               clock64() - t_start, w_b, w_a, w_tf, w_wh, w_tr, w_df);
+        printf("vertical MMA thread: total %lld clk; waits: weights %lld, source rows %lld, TMEM region %lld; issue %lld\n", clock64() - t_start, w_b, w_a, w_tf, i_v);
 #else
-    (void)t_start; (void)w_b; (void)w_a; (void)w_tf; (void)w_wh; (void)w_tr; (void)w_df;
+    (void)t_start; (void)w_b; (void)w_a; (void)w_tf; (void)i_v;
 #endif
 }
 
@@ -808,9 +831,9 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
     } else if (warp == NT / 32 + 2) {
         if (elect_one()) tc_weight_role<NR2>(pipe, tb);
     } else if (warp == NT / 32 + 3) {
-        if (elect_one()) tc2_wh_role<N2>(pipe, hp, tb, hrec);
+        if (elect_one()) tc2_h_role<N2>(pipe, hp, tb, hrec);
     } else if (warp == NT / 32) {
-        if (elect_one()) tc2_mma_role<N2>(pipe, hp);
+        if (elect_one()) tc2_v_role(pipe);
     } else {
         // ================= consumer warps =================
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
