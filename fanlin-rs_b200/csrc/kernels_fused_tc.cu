@@ -43,7 +43,7 @@ constexpr uint32_t NA_MAX = 4;    // most shared-memory slots for a group's sour
 constexpr uint32_t NR = 5;        // TMEM accumulator regions of 96 columns
 constexpr int S = FUSED_SLOTS;
 #ifndef TC_PF_AHEAD
-#define TC_PF_AHEAD 6
+#define TC_PF_AHEAD 4
 #endif
 constexpr uint32_t TMEM_COLS = 512;  // NR regions of 96 columns
 
