@@ -1,5 +1,10 @@
-// Fused separable Lanczos3 resample with the vertical pass on the sm_100a tensor
-// cores (tcgen05.mma kind::i8, accumulators in TMEM).  See fused_tc.h.
+// Fused separable Lanczos3 resample on the sm_100a tensor cores (accumulators in TMEM).  See fused_tc.h.
+// Three kernels share the operand pipeline below:
+//   fused_resample_tc2_kernel  both passes on the tensor cores (vertical kind::i8, horizontal kind::f16 on
+//                              f16 hi / lo tiles); the shipped path where the output ring fits -- second half of the file
+//   fused_resample_tc_kernel   vertical pass on the tensor cores, horizontal scatter stage on the CUDA cores
+//   blur_v_tc_kernel           vertical Gaussian pass of the blur
+// What follows describes fused_resample_tc_kernel; the tc2 kernel has its own header further down.
 //
 // Per CTA (1 CTA / SM): 8 consumer warps, an MMA-issuing warp and two TMA-issuing warps; one
 // band of <= 192 output rows of one image, swept left to right in chunks of 128 source bytes
