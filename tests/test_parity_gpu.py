@@ -447,3 +447,32 @@ def test_tensor_core_horizontal_stage_is_the_c2_kernel(fanlin, dev):
         want = O.process(src[i].cpu().numpy(), w=300, h=200)
         assert hist(dst[i].cpu().numpy(), want)[">=2"] == 0
     batch.free()
+
+
+@pytest.mark.parametrize("pattern", ["white", "black", "checker", "stripes_x", "stripes_y", "impulses"])
+def test_tensor_core_horizontal_stage_extremes(fanlin, dev, pattern):
+    """Largest Lanczos overshoot (0 / 255 patterns: the f16 halves of the vertical results reach -40 .. 295, the
+    clamp works on both sides) and constants (weights sum to one: a constant image stays constant)."""
+    h, w = 1080, 1920
+    yy, xx = np.mgrid[0:h, 0:w]
+    if pattern == "white":
+        a = np.full((h, w), 255)
+    elif pattern == "black":
+        a = np.zeros((h, w), int)
+    elif pattern == "checker":
+        a = (((yy // 7) + (xx // 7)) % 2) * 255
+    elif pattern == "stripes_x":
+        a = ((xx // 5) % 2) * 255
+    elif pattern == "stripes_y":
+        a = ((yy // 5) % 2) * 255
+    else:
+        a = ((yy % 13 == 0) & (xx % 11 == 0)) * 255
+    img = np.repeat(a[..., None], 3, axis=2).astype(np.uint8)
+    img[..., 1] = 255 - img[..., 1] if pattern not in ("white", "black") else img[..., 1]
+    q = fanlin.Query("w=300&h=200")
+    want = O.process(img, w=300, h=200)
+    got = fanlin.process_image(dev, img, q)
+    hh = hist(got, want)
+    assert hh[">=2"] == 0, hh
+    if pattern in ("white", "black"):
+        assert np.array_equal(got, want)
