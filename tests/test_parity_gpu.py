@@ -476,3 +476,42 @@ def test_tensor_core_horizontal_stage_extremes(fanlin, dev, pattern):
     assert hh[">=2"] == 0, hh
     if pattern in ("white", "black"):
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("offset", [1, 2, 3])
+def test_device_batch_misaligned_destination(fanlin, dev, offset):
+    """Caller-owned device buffers need not be 4-byte aligned: the letterboxed RGBA output of the tensor-core
+    kernels lands at dst + 1 / 2 / 3 (staged rows keep the alignment phase of their canvas address; whole words
+    where they exist, bytes at the edges) and matches the aligned result byte for byte."""
+    import ctypes as C
+    import torch
+
+    n = 3
+    src = torch.stack([torch.from_numpy(synth_image(70 + i, 1080, 1920, 3)) for i in range(n)]).cuda()
+    out_bytes = 200 * 300 * 4
+    dst = torch.zeros(n * out_bytes + 64, dtype=torch.uint8, device="cuda")
+    ref = torch.zeros(n * out_bytes, dtype=torch.uint8, device="cuda")
+    q = fanlin.Query("w=300&h=200")
+    proto = fanlin.Job()
+    fanlin.lib().fanlin_job_from_query(C.byref(q._q), 0, C.byref(proto))
+
+    def run(base_ptr):
+        jobs = (fanlin.Job * n)()
+        for i in range(n):
+            C.memmove(C.byref(jobs, i * C.sizeof(fanlin.Job)), C.byref(proto), C.sizeof(fanlin.Job))
+            jobs[i].src = src.data_ptr() + i * 1080 * 1920 * 3
+            jobs[i].src_w, jobs[i].src_h, jobs[i].src_channels = 1920, 1080, 3
+            jobs[i].dst = base_ptr + i * out_bytes
+            jobs[i].dst_capacity = out_bytes
+        batch = dev.prepare(jobs, 0)
+        batch.launch(None)
+        torch.cuda.synchronize()
+        batch.free()
+
+    run(ref.data_ptr())
+    run(dst.data_ptr() + offset)
+    got = dst[offset:offset + n * out_bytes]
+    assert torch.equal(got, ref)
+    assert int(dst[:offset].sum()) == 0 and int(dst[offset + n * out_bytes:].sum()) == 0  # nothing written outside
+    want = O.process(src[0].cpu().numpy(), w=300, h=200)
+    assert hist(ref[:out_bytes].cpu().numpy().reshape(200, 300, 4), want)[">=2"] == 0
