@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check (kernel ablation runs only)")
     ap.add_argument("--exact", action="store_true", help="bit-exact kernels (crate operation order)")
-    ap.add_argument("--vertical-path", type=int, default=0, help="0: tensor cores (default), 1: CUDA cores, 2: tensor cores for the vertical pass only")
+    ap.add_argument("--vertical-path", type=int, default=0, help="0: tensor cores (default), 1: CUDA cores, 2: tensor cores for the vertical pass only, 3: both passes whatever the batch size")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get("RANK", "0"))

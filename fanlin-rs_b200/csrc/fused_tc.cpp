@@ -256,6 +256,17 @@ static bool build_hmma(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
         if (fin != o_end) return false;
     }
     std::vector<uint32_t> rec(size_t(3) * g.n_chunks);
+    // f16 halves of every tap once (a tap is written c times per chunk it falls into)
+    std::vector<uint16_t> w_hi(t.weights.size()), w_lo(t.weights.size());
+    for (uint32_t o = o0; o < o_end; o++) {
+        const TapEntry &e = t.entries[o];
+        for (uint32_t tt = 0; tt < e.count; tt++) {
+            const float w = t.weights[e.woff + tt] * TC2_WSCALE;
+            const __half wh = __float2half_rn(w);
+            w_hi[e.woff + tt] = __half_as_ushort(wh);
+            w_lo[e.woff + tt] = __half_as_ushort(__float2half_rn(w - __half2float(wh)));
+        }
+    }
     uint32_t fin = o0, touch = o0;
     for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
         const uint32_t b0 = g.b0 + TC_M * ch, b1 = b0 + TC_M, x_hi = (b1 - 1) / C;
@@ -265,16 +276,17 @@ static bool build_hmma(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
         uint16_t *hi = reinterpret_cast<uint16_t *>(&tct->b[off]), *lo = hi + size_t(N2) * 128;
         for (uint32_t o = fin; o < touch; o++) {
             const TapEntry &e = t.entries[o];
-            for (uint32_t tt = 0; tt < e.count; tt++) {
-                const float w = t.weights[e.woff + tt] * TC2_WSCALE;
-                const __half wh = __float2half_rn(w), wl = __float2half_rn(w - __half2float(wh));
+            // taps whose pixel has a byte in [b0, b1)
+            const uint32_t ta = e.left * C + C > b0 ? 0u : (b0 - (e.left * C + C - 1) + C - 1) / C;
+            for (uint32_t tt = ta; tt < e.count && (e.left + tt) * C < b1; tt++) {
+                const uint16_t wh = w_hi[e.woff + tt], wl = w_lo[e.woff + tt];
                 for (uint32_t chn = 0; chn < C; chn++) {
                     const uint32_t byte = (e.left + tt) * C + chn;
                     if (byte < b0 || byte >= b1) continue;
                     const uint32_t k = byte - b0, n = ((o - o0) % RP) * C + chn;
                     const size_t at = (size_t(n / 8) * 16 + k / 8) * 64 + (n % 8) * 8 + k % 8;  // in f16 elements
-                    hi[at] = __half_as_ushort(wh);
-                    lo[at] = __half_as_ushort(wl);
+                    hi[at] = wh;
+                    lo[at] = wl;
                 }
             }
         }

@@ -285,9 +285,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
     std::vector<uint8_t> gather_a(n_jobs, 0); // stage A is a Nearest resample: the compose kernel gathers through the tap tables
     std::vector<StagePlan> a_pre(n_jobs);     // present: stage A as the tensor-core kernel sees it behind a colour-op pass
-    std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(ctx->cfg.vertical_path == 0), fused_tc_cache_free);
+    // Both passes on the tensor cores need ~1 MB of per-chunk weight tiles per geometry (built and uploaded per batch:
+    // +0.25 ms on a single C2 request, +0.6 ms on a C5 one): worth it from a few waves of images on, not for the handful
+    // of requests the batcher merges.  vertical_path 3 forces it (tests, A/B runs).
+    const bool allow_hmma = ctx->cfg.vertical_path == 3 || (ctx->cfg.vertical_path == 0 && n_jobs >= TC2_MIN_JOBS);
+    std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(allow_hmma), fused_tc_cache_free);
     FusedTcTables tctabs;
-    const bool use_tc = ctx->cfg.vertical_path == 0 || ctx->cfg.vertical_path == 2;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
+    const bool use_tc = ctx->cfg.vertical_path != 1;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
     std::vector<uint8_t> fast_b(n_jobs, 0);  // stage B takes the fast blur kernels
     BlurTables btabs;
     std::vector<BlurItem> bitems;

@@ -180,7 +180,8 @@ class Device:
     def __init__(self, device_ids=None, *, exact=False, device_scratch_bytes=0, pinned_bytes=0,
                  batch_window_us=0, max_batch_jobs=0, tensor_cores=True, vertical_path=None):
         """vertical_path: None = from tensor_cores (0 / 1); 2 = tensor cores for the vertical pass only
-        (the horizontal stage stays on the CUDA cores)."""
+        (the horizontal stage stays on the CUDA cores); 3 = both passes on the tensor cores whatever the
+        batch size (0 takes them from 256 jobs per batch on)."""
         cfg = Config(C.sizeof(Config), int(exact), device_scratch_bytes, pinned_bytes, batch_window_us, max_batch_jobs,
                      (0 if tensor_cores else 1) if vertical_path is None else int(vertical_path), 0)
         h = C.c_void_p()

@@ -96,7 +96,7 @@ typedef struct fanlin_config {
     uint64_t pinned_bytes;       /* per-device pinned staging ring; 0 = default */
     uint32_t batch_window_us;    /* request batcher collection window; 0 = default */
     uint32_t max_batch_jobs;     /* 0 = default */
-    uint32_t vertical_path;      /* 0 = tensor cores (both passes where eligible, else the vertical pass), 1 = CUDA cores only, 2 = tensor cores for the vertical pass only */
+    uint32_t vertical_path;      /* 0 = tensor cores: both passes for batches of >= 256 jobs where eligible, else the vertical pass; 1 = CUDA cores only; 2 = tensor cores for the vertical pass only; 3 = both passes whatever the batch size */
     uint32_t reserved1;
 } fanlin_config;
 

@@ -379,6 +379,14 @@ def test_two_devices_shard_a_batch(fanlin, dev):
 # ---- both passes on the tensor cores (fused_resample_tc2_kernel) ------------------------------------
 
 @pytest.fixture(scope="module")
+def dev_tc2(fanlin):
+    """Both passes on the tensor cores whatever the batch size (a default context takes them from 256 jobs on)."""
+    d = fanlin.Device([0], vertical_path=3)
+    yield d
+    d.close()
+
+
+@pytest.fixture(scope="module")
 def dev_tc_vertical_only(fanlin):
     d = fanlin.Device([0], vertical_path=2)
     yield d
@@ -404,7 +412,8 @@ HMMA_CASES = [
 
 
 @pytest.mark.parametrize("seed,h,w,c,qs", HMMA_CASES, ids=[f"{p[1]}x{p[2]}x{p[3]}-{p[4]}" for p in HMMA_CASES])
-def test_tensor_core_horizontal_stage(fanlin, dev, dev_tc_vertical_only, seed, h, w, c, qs):
+def test_tensor_core_horizontal_stage(fanlin, dev_tc2, dev_tc_vertical_only, seed, h, w, c, qs):
+    dev = dev_tc2
     img = synth_image(seed, h, w, c)
     q = fanlin.Query(qs)
     kw = dict(crop=q.cropping(), rgb=q.fill_color())
@@ -419,13 +428,15 @@ def test_tensor_core_horizontal_stage(fanlin, dev, dev_tc_vertical_only, seed, h
     assert hist(got, other)[">=2"] == 0
 
 
-def test_tensor_core_horizontal_stage_is_the_c2_kernel(fanlin, dev):
-    """The bench workload's shape runs fused_resample_tc2_kernel (and nothing else) on a default context."""
+@pytest.mark.parametrize("n,kernel", [(256, "fused_resample_tc2_kernel"), (8, "fused_resample_tc_kernel")])
+def test_default_context_picks_the_kernel_by_batch_size(fanlin, dev, n, kernel):
+    """C2-shaped jobs on a default context: both passes on the tensor cores from 256 jobs per batch on (the per-chunk
+    weight tiles cost ~0.25 ms per geometry to build and upload), the CUDA-core horizontal stage below."""
     import ctypes as C
     import torch
 
-    n = 8
-    src = torch.stack([torch.from_numpy(synth_image(60 + i, 1080, 1920, 3)) for i in range(n)]).cuda()
+    base = torch.stack([torch.from_numpy(synth_image(60 + i, 1080, 1920, 3)) for i in range(4)]).cuda()
+    src = base.repeat((n + 3) // 4, 1, 1, 1)[:n].contiguous()
     dst = torch.zeros((n, 200, 300, 4), dtype=torch.uint8, device="cuda")
     q = fanlin.Query("w=300&h=200")
     proto = fanlin.Job()
@@ -442,7 +453,7 @@ def test_tensor_core_horizontal_stage_is_the_c2_kernel(fanlin, dev):
     batch.launch(None)
     torch.cuda.synchronize()
     names = {k for k, _ in batch.kernel_times()}
-    assert names == {"fused_resample_tc2_kernel"}, names
+    assert names == {kernel}, names
     for i in (0, n - 1):
         want = O.process(src[i].cpu().numpy(), w=300, h=200)
         assert hist(dst[i].cpu().numpy(), want)[">=2"] == 0
@@ -450,7 +461,8 @@ def test_tensor_core_horizontal_stage_is_the_c2_kernel(fanlin, dev):
 
 
 @pytest.mark.parametrize("pattern", ["white", "black", "checker", "stripes_x", "stripes_y", "impulses"])
-def test_tensor_core_horizontal_stage_extremes(fanlin, dev, pattern):
+def test_tensor_core_horizontal_stage_extremes(fanlin, dev_tc2, pattern):
+    dev = dev_tc2
     """Largest Lanczos overshoot (0 / 255 patterns: the f16 halves of the vertical results reach -40 .. 295, the
     clamp works on both sides) and constants (weights sum to one: a constant image stays constant)."""
     h, w = 1080, 1920
@@ -479,7 +491,8 @@ def test_tensor_core_horizontal_stage_extremes(fanlin, dev, pattern):
 
 
 @pytest.mark.parametrize("offset", [1, 2, 3])
-def test_device_batch_misaligned_destination(fanlin, dev, offset):
+def test_device_batch_misaligned_destination(fanlin, dev_tc2, offset):
+    dev = dev_tc2
     """Caller-owned device buffers need not be 4-byte aligned: the letterboxed RGBA output of the tensor-core
     kernels lands at dst + 1 / 2 / 3 (staged rows keep the alignment phase of their canvas address; whole words
     where they exist, bytes at the edges) and matches the aligned result byte for byte."""

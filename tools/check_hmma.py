@@ -26,18 +26,18 @@ CASES = [  # (h, w, c, query)
     (1500, 2000, 2, "w=300&h=300"),
     (512, 512, 3, "w=300&h=200"),
 ]
-dev = {vp: pkg.Device([0], vertical_path=vp) for vp in (0, 2)}
+dev = {vp: pkg.Device([0], vertical_path=vp) for vp in (3, 2)}
 bad = 0
 for (h, w, c, q) in CASES:
     img = synth_image(77 + h + c, h, w, c)
     want = O.process(img, **{k: (v == "true" if v in ("true", "false") else int(v)) for k, v in (kv.split("=") for kv in q.split("&"))})
     line = f"{h}x{w}x{c} {q:28s}"
-    for vp in (0, 2):
+    for vp in (3, 2):
         got = pkg.process_image(dev[vp], img, pkg.Query(q))
         # which kernel: prepare a device batch with timing
         d = np.abs(got.astype(np.int16) - want.astype(np.int16))
         line += f" | path {vp}: d1={int((d == 1).sum()):6d} d2+={int((d >= 2).sum()):6d} max={int(d.max())}"
-        if vp == 0:
+        if vp == 3:
             bad += int((d >= 2).sum())
     print(line, flush=True)
 print("FAIL" if bad else "OK")
