@@ -144,7 +144,7 @@ def reduce_timing(ms_total_local, steps, images_per_rank, world, dist, device):
     return ms_per_step, world * images_per_rank * MPIX_PER_IMAGE / (ms_per_step * 1e-3)
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out_fd):
     """Reference arm: the reference's CPU implementation of the path (the oracle port: the
     image crate cannot be built here) on all host threads, bounded sample per step."""
     if rank != 0:
@@ -164,10 +164,20 @@ def run_reference(args, rank):
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line, out_fd)
+
+
+def emit(line, out_fd):
+    """The one JSON line of the run, alone on the process's real stdout."""
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
 
 
 def main():
+    # Everything any library prints to fd 1 from here on (NCCL prints its version banner there under torchrun when
+    # NCCL_DEBUG is set) goes to stderr: stdout carries the JSON line and nothing else.
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -187,7 +197,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, out_fd)
         return
 
     import numpy as np
@@ -360,7 +370,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
             "clocks": clocks, "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line, out_fd)
     if dist:
         dist.destroy_process_group()
 
