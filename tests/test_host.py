@@ -200,3 +200,22 @@ def test_plan_output_layouts(fanlin):
             fanlin.plan_job(j)
         j.flags &= ~TO_RGB8
         assert fanlin.plan_job(j).out_channels == 4
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (no GPU needed): exactly one line on stdout, valid JSON, with the keys the
+    driver reads; whatever libraries print goes to stderr."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
