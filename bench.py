@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
 
@@ -76,7 +76,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -85,13 +85,20 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pw.append(0.0)
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        # samples under load: the upper half (idle samples before/after the region pull the median down)
-        load = sorted(sm)[len(sm) // 2:] if sm else []
+        # samples under load = those drawing at least 60 % of the highest power seen (the sampler also runs through the
+        # idle stretches around the warm-up and the timed region; idle SM clocks sit at the maximum on this part)
+        top = max(pw) if pw else 0.0
+        load = [c for c, w in zip(sm, pw) if w >= 0.6 * top] if top > 0 else sm
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(load),
+                "sm_mhz_min_under_load": min(load) if load else None, "power_w_max": top or None}
 
 
 def synth_batch_on_device(torch, n, seed, device):
@@ -246,14 +253,17 @@ def main():
 
     # ---- device-resident leg ------------------------------------------------------------
     batch.set_timing(True)
+    # the clock sampler starts before the warm-up: nvidia-smi needs a few hundred ms before its first line, and the timed
+    # region is tens of ms (its idle samples are dropped in stop(): the upper half of the SM clocks is what ran under load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.5)
     for _ in range(warm):
         batch.launch(stream.cuda_stream)
     torch.cuda.synchronize(device)
     batch.kernel_times()  # drop the warm-up record
     ktimes = {}
     launches0 = dev.stats()["kernel_launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     stream.synchronize()
