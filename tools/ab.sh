@@ -2,7 +2,7 @@
 # A/B of built libraries on one GPU box: tools/ab.sh libA.so libB.so ... (each run twice, interleaved)
 keep=/tmp/keep_$$.so
 cp fanlin-rs_b200/libfanlin_device.so $keep
-for rep in 1 2; do
+for rep in ${AB_REPS:-1 2}; do
   for lib in "$@"; do
     cp "$lib" fanlin-rs_b200/libfanlin_device.so
     python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-parity ${AB_ARGS} 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$lib', d['roofline']['kernel'], round(d['ms_per_step'],3), round(d['roofline']['frac'],4), d['clocks']['sm_mhz'], d['clocks']['reasons'])"
