@@ -56,7 +56,8 @@ def _qs(p):
 
 @pytest.fixture(scope="module")
 def devices(fanlin):
-    ds = {"exact": fanlin.Device([0], exact=True), "tensor-core": fanlin.Device([0]), "cuda-core": fanlin.Device([0], tensor_cores=False)}
+    ds = {"exact": fanlin.Device([0], exact=True), "tensor-core": fanlin.Device([0]), "cuda-core": fanlin.Device([0], tensor_cores=False),
+          "tensor-core-both": fanlin.Device([0], vertical_path=3)}  # both Lanczos3 passes on the tensor cores whatever the batch size
     yield ds
     for d in ds.values():
         d.close()
@@ -65,7 +66,7 @@ def devices(fanlin):
 @pytest.mark.parametrize("block", range(10))
 def test_random_requests_match_the_oracle(fanlin, devices, block):
     rng = np.random.default_rng(7000 + block)
-    worst = {"tensor-core": 0.0, "cuda-core": 0.0}
+    worst = {"tensor-core": 0.0, "cuda-core": 0.0, "tensor-core-both": 0.0}
     for k in range(30):
         h, w, c, p, exif = _case(rng)
         img = synth_image(8000 + 100 * block + k, h, w, c)
@@ -73,14 +74,14 @@ def test_random_requests_match_the_oracle(fanlin, devices, block):
         want = O.process(img, orientation=exif, **p)
         got = fanlin.process_image(devices["exact"], img, q, orientation=exif)
         assert got.shape == want.shape and np.array_equal(got, want), ("exact", h, w, c, p, exif)
-        for name in ("tensor-core", "cuda-core"):
+        for name in ("tensor-core", "cuda-core", "tensor-core-both"):
             got = fanlin.process_image(devices[name], img, q, orientation=exif)
             assert got.shape == want.shape, (name, h, w, c, p, exif)
             d = np.abs(got.astype(np.int16) - want.astype(np.int16))
             assert d.max(initial=0) <= 1, (name, h, w, c, p, exif, int(d.max()))
             worst[name] = max(worst[name], float((d == 1).mean()) if d.size > 2000 else 0.0)
     # off-by-one only where the f32 sum sits on a rounding boundary: rare even in the worst image of the block
-    assert worst["tensor-core"] <= 0.004 and worst["cuda-core"] <= 0.004, worst
+    assert max(worst.values()) <= 0.004, worst
 
 
 def test_random_batches_ragged(fanlin, devices):
@@ -92,3 +93,35 @@ def test_random_batches_ragged(fanlin, devices):
         together = fanlin.process_images(devices[name], imgs, q)
         for im, a in zip(imgs, together):
             assert np.array_equal(a, fanlin.process_image(devices[name], im, q)), name
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_random_strong_downscales_both_passes_on_the_tensor_cores(fanlin, devices, block):
+    """Large sources, small outputs (ratios 4 .. 25): the shapes fused_resample_tc2_kernel takes -- output ring of every
+    channel count, one and two row tiles, several bands, crop windows off the 16-byte grid, all colour ops in front."""
+    rng = np.random.default_rng(7200 + block)
+    worst = 0.0
+    for k in range(12):
+        c = int(rng.choice([1, 2, 3, 3, 3, 4]))
+        h, w = int(rng.integers(500, 2300)), int(rng.integers(600, 3100))
+        p = {"w": int(rng.integers(24, 420)), "h": int(rng.integers(24, 420))}
+        if rng.random() < 0.4:
+            p["crop"] = True
+        if rng.random() < 0.5:
+            p["rgb"] = tuple(int(v) for v in rng.integers(0, 256, 3))
+        kk = rng.random()
+        if kk < 0.2:
+            p["grayscale"] = True
+        elif kk < 0.35:
+            p["inverse"] = True
+        exif = int(rng.integers(2, 9)) if rng.random() < 0.2 else 1
+        img = synth_image(8800 + 100 * block + k, h, w, c)
+        q = fanlin.Query(_qs(p))
+        want = O.process(img, orientation=exif, **p)
+        for name in ("tensor-core-both", "tensor-core"):
+            got = fanlin.process_image(devices[name], img, q, orientation=exif)
+            assert got.shape == want.shape, (name, h, w, c, p, exif)
+            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+            assert d.max(initial=0) <= 1, (name, h, w, c, p, exif, int(d.max()))
+            worst = max(worst, float((d == 1).mean()) if d.size > 2000 else 0.0)
+    assert worst <= 0.004, worst
