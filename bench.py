@@ -362,7 +362,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns = max(16 * cores, 64)
+        ns = max(64 * cores, 256)  # ~25 s of CPU work: one image takes ~25 ms on one core
         v, dt = cpu_baseline(ns, cores)
         cpu = {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port",
                "sample": f"{ns} of the {n} C2 images, one image per thread, {dt:.2f} s"}
