@@ -450,6 +450,7 @@ def test_default_context_picks_the_kernel_by_batch_size(fanlin, dev, n, kernel):
         jobs[i].dst_capacity = 200 * 300 * 4
     batch = dev.prepare(jobs, 0)
     batch.set_timing(True)
+    torch.cuda.synchronize()  # inputs / zeroed outputs were written on torch's stream; the library launches on its own
     batch.launch(None)
     torch.cuda.synchronize()
     names = {k for k, _ in batch.kernel_times()}
@@ -517,6 +518,7 @@ def test_device_batch_misaligned_destination(fanlin, dev_tc2, offset):
             jobs[i].dst = base_ptr + i * out_bytes
             jobs[i].dst_capacity = out_bytes
         batch = dev.prepare(jobs, 0)
+        torch.cuda.synchronize()  # inputs / zeroed outputs were written on torch's stream; the library launches on its own
         batch.launch(None)
         torch.cuda.synchronize()
         batch.free()
@@ -528,3 +530,38 @@ def test_device_batch_misaligned_destination(fanlin, dev_tc2, offset):
     assert int(dst[:offset].sum()) == 0 and int(dst[offset + n * out_bytes:].sum()) == 0  # nothing written outside
     want = O.process(src[0].cpu().numpy(), w=300, h=200)
     assert hist(ref[:out_bytes].cpu().numpy().reshape(200, 300, 4), want)[">=2"] == 0
+
+
+def test_tensor_core_horizontal_stage_is_deterministic_across_ctas(fanlin, dev_tc2):
+    """300 jobs over 4 distinct sources in one launch (two waves of CTAs with different timing on 148 SMs): every copy of
+    a source gives the same bytes, and a second launch gives the same bytes again."""
+    import ctypes as C
+    import torch
+
+    n = 300
+    base = torch.stack([torch.from_numpy(synth_image(90 + i, 1080, 1920, 3)) for i in range(4)]).cuda()
+    src = base.repeat(n // 4, 1, 1, 1).contiguous()
+    dst = torch.zeros((n, 200, 300, 4), dtype=torch.uint8, device="cuda")
+    q = fanlin.Query("w=300&h=200")
+    proto = fanlin.Job()
+    fanlin.lib().fanlin_job_from_query(C.byref(q._q), 0, C.byref(proto))
+    jobs = (fanlin.Job * n)()
+    for i in range(n):
+        C.memmove(C.byref(jobs, i * C.sizeof(fanlin.Job)), C.byref(proto), C.sizeof(fanlin.Job))
+        jobs[i].src = src.data_ptr() + i * 1080 * 1920 * 3
+        jobs[i].src_w, jobs[i].src_h, jobs[i].src_channels = 1920, 1080, 3
+        jobs[i].dst = dst.data_ptr() + i * 200 * 300 * 4
+        jobs[i].dst_capacity = 200 * 300 * 4
+    batch = dev_tc2.prepare(jobs, 0)
+    torch.cuda.synchronize()  # inputs / zeroed outputs were written on torch's stream; the library launches on its own
+    batch.launch(None)
+    torch.cuda.synchronize()
+    first = dst.clone()
+    for i in range(4, n):
+        assert torch.equal(dst[i], dst[i % 4]), i
+    dst.zero_()
+    torch.cuda.synchronize()  # the library launches on its own stream
+    batch.launch(None)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, first)
+    batch.free()
