@@ -39,6 +39,28 @@ OUT_W, OUT_H, OUT_C = 300, 200, 4
 BATCH = 4096
 MPIX_PER_IMAGE = OUT_W * OUT_H / 1e6
 WORKLOAD = "C2: 4096 x 1920x1080 RGB -> w=300&h=200 fit + letterbox fill (RGBA8 300x200)"
+METRIC = "output Mpix/s, fused resize+fill+blur pipeline, 1/2/4/8 B200; % of HBM peak"  # BASELINE.json's string
+# what the dominant kernel computes in: vertical pass u8 x s8 (three base-128 digits of the 2^-21-quantised weights) -> s32 on
+# tcgen05 kind::i8, recombined exactly in f32; horizontal pass f16 hi/lo x f16 hi/lo -> f32 on tcgen05 kind::f16; u8 out
+DTYPE = "u8*s8->s32 (vertical, exact) + f16 hi/lo*f16 hi/lo->f32 (horizontal), u8 out"
+DTYPE_CPU = "f32 (image-crate operation order)"
+
+# The other BASELINE.json configs, device-resident, parity-checked, reported under the line's `configs` key.
+#   key, BASELINE config, h, w, c, query, gif, images per GPU and launch, total images of a strong-scaling run (or None)
+OTHER_CONFIGS = [
+    ("C1", "configs[0] shape: 512x512 RGB -> w=300&h=200&rgb=32,32,32 (fit + letterbox), batch 1024", 512, 512, 3, "w=300&h=200&rgb=32,32,32", False, 1024, None),
+    ("C3_resize_crop", "configs[2] without blur: 3840x2160 RGBA -> w=1618&h=1000&crop=true, batch 1024", 2160, 3840, 4, "w=1618&h=1000&crop=true", False, 1024, None),
+    ("C3", "configs[2]: 3840x2160 RGBA -> w=1618&h=1000&crop=true&blur=10, batch 1024", 2160, 3840, 4, "w=1618&h=1000&crop=true&blur=10", False, 1024, None),
+    ("C4", "configs[3] literal: 200 GIF frames 480x270 RGBA, w=200&grayscale=true&inverse=true (no h: no resize; grayscale wins)", 270, 480, 4,
+     "w=200&grayscale=true&inverse=true", True, 200, None),
+    ("C4_h113", "configs[3] with h: 200 GIF frames 480x270 RGBA, w=200&h=113&grayscale=true&inverse=true (Nearest)", 270, 480, 4,
+     "w=200&h=113&grayscale=true&inverse=true", True, 200, None),
+    ("C5_crop", "configs[4] crop variant: 8192 x 4000x3000 RGB -> w=1618&h=1000&crop=true&grayscale=true&blur=10 (L8 out), resident chunks of <= 2048 per GPU",
+     3000, 4000, 3, "w=1618&h=1000&crop=true&grayscale=true&blur=10", False, 2048, 8192),
+    ("C5_fit", "configs[4] fit + fill variant: 8192 x 4000x3000 RGB -> w=1618&h=1000&rgb=32,32,32&grayscale=true&blur=10 (RGBA8 out), resident chunks of <= 2048 per GPU",
+     3000, 4000, 3, "w=1618&h=1000&rgb=32,32,32&grayscale=true&blur=10", False, 2048, 8192),
+]
+FP32_FMA_PER_S = 148 * 128 * 1.965e9  # CUDA-core FMA peak (the direct-form blur is FP32-bound)
 
 
 def load_peaks():
@@ -139,6 +161,98 @@ def cpu_baseline(n_images, threads, steps=1):
     return n_images * MPIX_PER_IMAGE / dt, dt
 
 
+def config_dict(images_per_gpu, exact=False):
+    """`config` of the JSON line: the same keys and values on both arms."""
+    return {"workload": WORKLOAD, "images_per_gpu": images_per_gpu, "l2": "inputs (25.5 GB/GPU) larger than L2",
+            "sharding": "by image index, no collective", "exact_mode": bool(exact)}
+
+
+def run_other_configs(args, pkg, dev, torch, np, device, stream, peak, world, dist, rank):
+    """Device-timed, parity-checked record of every other BASELINE.json config (what tools/bench_configs.py prints),
+    at the stated batch sizes; C5 as a strong-scaling run of 8192 images over the ranks in resident chunks."""
+    from oracle import oracle as O
+    from synth import synth_image
+
+    out = {}
+    for key, desc, h, w, c, qs, gif, per_launch, total in OTHER_CONFIGS:
+        if args.only_configs and key not in args.only_configs.split(","):
+            continue
+        n_rank = per_launch if total is None else max(1, total // world)   # images this rank owns per step
+        n = min(per_launch, n_rank)                                         # resident chunk: images per launch
+        launches = (n_rank + n - 1) // n
+        base = [torch.from_numpy(synth_image(900 + 10 * rank + i, h, w, c)).to(device) for i in range(4)]
+        src = torch.empty((n, h, w, c), dtype=torch.uint8, device=device)
+        for i in range(4):
+            src[i::4] = base[i]
+        q = pkg.Query(qs)
+        proto = pkg.Job()
+        pkg.lib().fanlin_job_from_query(C.byref(q._q), int(gif), C.byref(proto))
+        proto.src_w, proto.src_h, proto.src_channels = w, h, c
+        plan = pkg.plan_job(proto)
+        dst = torch.zeros((n, plan.out_h, plan.out_w, plan.out_channels), dtype=torch.uint8, device=device)
+        jobs = (pkg.Job * n)()
+        for i in range(n):
+            C.memmove(C.byref(jobs, i * C.sizeof(pkg.Job)), C.byref(proto), C.sizeof(pkg.Job))
+            jobs[i].src = src.data_ptr() + i * h * w * c
+            jobs[i].dst = dst.data_ptr() + i * plan.out_bytes
+            jobs[i].dst_capacity = plan.out_bytes
+        torch.cuda.synchronize(device)
+        b = dev.prepare(jobs, 0)
+        b.set_timing(True)
+        for _ in range(3):
+            b.launch(stream.cuda_stream)
+        torch.cuda.synchronize(device)
+        b.kernel_times()
+        steps = max(1, min(args.steps, 5))
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps * launches):
+            b.launch(stream.cuda_stream)
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        kt = {}
+        for k, v in b.kernel_times():
+            kt.setdefault(k, []).append(v)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if dist and world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / steps                      # one step = this rank's n_rank images (launches x n)
+        imgs_step = world * n * launches
+        alg = plan.algorithmic_bytes * n * launches
+        rec = {"workload": desc, "query": qs, "images_per_gpu_per_launch": n, "launches_per_step": launches, "images_per_step_all_gpus": imgs_step,
+               "steps": steps, "ms_per_step": ms, "us_per_image": ms * 1e3 / (n * launches),
+               "out_mpix_s": imgs_step * plan.out_w * plan.out_h / 1e6 / (ms * 1e-3),
+               "algorithmic_bytes_per_image": int(plan.algorithmic_bytes), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
+               "kernels_ms_per_launch": {k: sum(v) / len(v) for k, v in kt.items()},
+               "scaling": "weak" if total is None else f"strong: {total} images over {world} GPU(s)"}
+        if q.blur() and not gif:
+            # SURVEY 8d: the direct-form blur is FP32-bound -- report the blur kernels against the CUDA-core FMA peak too
+            # (2 passes x taps FMAs per output element), whatever unit actually runs them
+            taps = 2 * int(np.ceil(2 * q.blur() - 0.5)) + 1
+            fma = 2.0 * taps * plan.out_w * plan.out_h * plan.out_channels * n
+            blur_ms = sum(v for k, v in rec["kernels_ms_per_launch"].items() if "blur" in k)
+            if blur_ms > 0:
+                rec["blur"] = {"taps": taps, "ms_per_launch": blur_ms, "fp32_frac": fma / (blur_ms * 1e-3) / FP32_FMA_PER_S}
+        if rank == 0:  # parity of two images of the batch (one per distinct base image) at full size
+            kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=0.0 if gif else q.blur(), rgb=q.fill_color(), gif=gif)
+            if q.dimensions():
+                kw["w"], kw["h"] = q.dimensions()
+            d1 = d2 = nn = 0
+            for i in (1, n - 1):
+                want = O.process(base[i % 4].cpu().numpy(), **kw)
+                d = np.abs(dst[i].cpu().numpy().astype(np.int16) - want.astype(np.int16))
+                d1 += int((d == 1).sum()); d2 += int((d >= 2).sum()); nn += int(d.size)
+            rec["parity"] = {"images_checked": 2, "values": nn, "diff1": d1, "diff_ge2": d2}
+            assert d2 == 0, (key, rec["parity"])
+        out[key] = rec
+        b.free()
+        del src, dst, base
+        torch.cuda.empty_cache()
+    return out
+
+
 def reduce_timing(ms_total_local, steps, images_per_rank, world, dist, device):
     """Max over ranks of the device time, and the whole-job aggregate it implies (weak scaling:
     every rank processed images_per_rank per step).  Returns (ms_per_step, Mpix/s)."""
@@ -163,10 +277,10 @@ def run_reference(args, rank, out_fd):
     v, dt = cpu_baseline(n, cores, steps=args.steps)
     sample = f"{n} of the {BATCH} C2 images per step, one image per thread"
     line = {
-        "impl": "reference", "metric": "output Mpix/s, fused resize+fill pipeline", "value": v, "unit": "Mpix/s",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_CPU, "data": "synthetic",
+        "config": config_dict(BATCH), "sample": sample,
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -195,6 +309,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check (kernel ablation runs only)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the records of the other BASELINE configs")
+    ap.add_argument("--only-configs", default="", help="comma-separated keys of OTHER_CONFIGS to run")
     ap.add_argument("--exact", action="store_true", help="bit-exact kernels (crate operation order)")
     ap.add_argument("--vertical-path", type=int, default=0, help="0: tensor cores (default), 1: CUDA cores, 2: tensor cores for the vertical pass only, 3: both passes whatever the batch size")
     args = ap.parse_args()
@@ -353,8 +469,12 @@ def main():
                "h2d_bytes_per_step": n * img_bytes, "d2h_bytes_per_step": n * out_bytes,
                "steps": e_steps, "ms_per_step": dt / e_steps * 1e3, "host_pool_images": pool,
                "api": "fanlin_run (C ABI), pinned host buffers from fanlin_host_alloc"}
-        got = hout[:out_bytes].reshape(OUT_H, OUT_W, OUT_C)
-        assert np.array_equal(got, dst[0].cpu().numpy()), "e2e output differs from the device-resident leg"
+        # every image of every sub-batch against the device-resident leg's result for the same source image
+        dref = dst[:pool].cpu().numpy().reshape(pool, out_bytes)
+        hall = hout[:n * out_bytes].reshape(n, out_bytes)
+        bad = [i for i in range(n) if not np.array_equal(hall[i], dref[i % pool])]
+        assert not bad, f"e2e output differs from the device-resident leg for {len(bad)} images, first {bad[:5]}"
+        e2e["images_compared_with_device_leg"] = n
         dev.host_free(hin)
         dev.host_free(hout)
 
@@ -368,17 +488,20 @@ def main():
                "sample": f"{ns} of the {n} C2 images, one image per thread, {dt:.2f} s"}
 
     batch.free()
+    del src, dst
+    torch.cuda.empty_cache()
+    configs = None
+    if not args.no_configs and not args.exact:
+        configs = run_other_configs(args, pkg, dev, torch, np, device, stream, peak, world, dist, rank)
     dev.close()
     if rank == 0:
         line = {
-            "metric": "output Mpix/s, fused resize+fill pipeline", "value": value, "unit": "Mpix/s",
+            "metric": METRIC, "value": value, "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images_per_gpu": n, "l2": "inputs (25.5 GB/GPU) larger than L2",
-                       "sharding": "by image index, no collective", "exact_mode": bool(args.exact),
-                       "hbm_frac_whole_step": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak},
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE if not args.exact else DTYPE_CPU, "data": "synthetic",
+            "config": config_dict(n, args.exact), "hbm_frac_whole_step": (alg_bytes / (ms_per_step * 1e-3) / 1e9) / peak,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(gpu_launches),
-            "clocks": clocks, "parity": parity,
+            "clocks": clocks, "parity": parity, "configs": configs,
         }
         emit(line, out_fd)
     if dist:

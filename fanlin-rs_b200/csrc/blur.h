@@ -13,7 +13,7 @@ struct BlurItem {
     uint8_t *dst;
     float *tmp;            // f32 intermediate [h][w * c]
     uint32_t w, h, c, src_pitch;
-    uint32_t radius;       // floor(2 sigma)
+    uint32_t radius;       // ceil(2 sigma - 0.5): taps on either side of the centre (blur_radius)
     uint32_t taps_pad;     // 2 radius + 1 rounded up to a multiple of 8 (zero weights beyond)
     uint32_t u_off;        // float offset of the interior weights u[taps_pad]
     uint32_t corrv_off;    // float offset of the per-row border factors [h]
@@ -27,6 +27,7 @@ struct BlurTables {
     std::map<uint32_t, uint32_t> u;                            // sigma bits -> float offset
 };
 
+uint32_t blur_radius(float sigma);
 // True when stage `s` (a Gaussian stage) can take the fast blur kernels.
 bool blur_eligible(const StagePlan &s);
 // Appends tables as needed to `w` and fills the geometry/table fields of `item`.

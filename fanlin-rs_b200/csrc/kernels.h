@@ -31,6 +31,11 @@ struct LaunchCtx {
     }
 };
 
+// Dynamic shared memory opt-in of a kernel: only ever RAISED, under a lock, per (device, kernel) -- the context is
+// Send + Sync, and a per-launch cudaFuncSetAttribute to that launch's own size could lower the limit between
+// another thread's set and its launch.  Returns false (and leaves the error for cudaGetLastError) on failure.
+bool ensure_dynamic_smem(const void *kernel, size_t bytes);
+
 struct LaunchGeom {
     uint32_t n_jobs;
     uint32_t max_n_rows, max_n_sx, max_n_cols;  // over the descriptors of this launch

@@ -1,6 +1,6 @@
 // Separable Gaussian blur (image-0.25.6 imageops::blur as called by reference
 // src/handler.rs:250-255): vertical pass u8 -> f32, horizontal pass f32 -> u8,
-// 2*floor(2 sigma)+1 taps (41..81), windows truncated at the borders and renormalised.
+// 2 R + 1 taps, R = ceil(2 sigma - 0.5) (41..81 for the integer sigmas of Query::blur()), windows truncated at the borders and renormalised.
 //
 // Both passes stage a tile with its halo in shared memory as f32 and slide a register window
 // along the filtered axis: per 8 taps a thread loads 8 new values and issues 128 FMAs for its 16
@@ -212,9 +212,9 @@ int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint3
                 uint32_t taps_pad, const float *d_w, bool skip_v, LaunchCtx &lc) {
     if (n_items == 0) return 0;
     const size_t sv = blur_v_smem(radius, taps_pad), sh = blur_h_smem(radius, taps_pad, c);
-    cudaFuncSetAttribute(blur_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sv));
+    ensure_dynamic_smem(reinterpret_cast<const void *>(blur_v_kernel), sv);
     auto hk = c == 1 ? blur_h_kernel<1> : c == 2 ? blur_h_kernel<2> : c == 3 ? blur_h_kernel<3> : blur_h_kernel<4>;
-    cudaFuncSetAttribute(hk, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sh));
+    ensure_dynamic_smem(reinterpret_cast<const void *>(hk), sh);
     const uint32_t rb = HT / c;
     if (!skip_v) {  // else the f32 intermediate was written by blur_v_tc_kernel
         lc.begin("blur_v_kernel");

@@ -9,6 +9,9 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 namespace fanlin {
 
@@ -331,6 +334,20 @@ int launch_compose(const StageDesc *d_descs, const TapEntry *d_tab, const Launch
     compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs, d_tab);
     lc.end();
     return 1;
+}
+
+
+bool ensure_dynamic_smem(const void *kernel, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> granted;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &have = granted[std::make_pair(dev, kernel)];
+    if (bytes <= have) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)) != cudaSuccess) return false;
+    have = bytes;
+    return true;
 }
 
 }  // namespace fanlin

@@ -301,7 +301,7 @@ void launch_variant(const FusedItem *d_items, uint32_t n_items, uint32_t max_ban
                     const uint32_t *d_info, LaunchCtx &lc) {
     const size_t smem = fused_smem_bytes(C, CMEM, max_band_rows);
     auto kern = fused_resample_kernel<C, CMEM, OP>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fused_smem_bytes(C, CMEM, fused_max_band(C, CMEM))));
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), fused_smem_bytes(C, CMEM, fused_max_band(C, CMEM)));
     lc.begin("fused_resample_kernel");
     kern<<<n_items, NT, smem, lc.st>>>(d_items, d_w, d_info);
     lc.end();

@@ -146,6 +146,9 @@ __device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMa
     // the copy itself (issued when a slot frees up) finds its lines in L2
     uint32_t pg = 0, pchunk = 0;
     const uint32_t pf_ahead = p.pf_ahead;
+    // The tensor map lives in global memory, written by a host copy into a recycled block: the tensormap proxy must
+    // not serve a stale descriptor it cached for an earlier launch's map at the same address.
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
     for (uint32_t k = 0; k < pf_ahead && pchunk < p.n_chunks; k++)
         if (++pg == p.n_groups) { pg = 0; pchunk++; }
     for (uint32_t gg = 0; gg < total; gg++) {
@@ -1024,7 +1027,7 @@ template <int C>
 void launch_tc2_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b, const uint32_t *d_info,
                         LaunchCtx &lc) {
     auto kern = fused_resample_tc2_kernel<C>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);  // a failure surfaces as the launch error
     lc.begin("fused_resample_tc2_kernel");
     kern<<<n_items, NT_ALL2, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
     lc.end();
@@ -1034,7 +1037,7 @@ template <int C>
 void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
                        const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
     auto kern = fused_resample_tc_kernel<C>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     lc.begin("fused_resample_tc_kernel");
     kern<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_w, d_info);
     lc.end();
@@ -1066,7 +1069,7 @@ int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_
 int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
                      const uint32_t *d_info, LaunchCtx &lc) {
     if (n_items == 0) return 0;
-    cudaFuncSetAttribute(blur_v_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    ensure_dynamic_smem(reinterpret_cast<const void *>(blur_v_tc_kernel), smem);
     lc.begin("blur_v_tc_kernel");
     blur_v_tc_kernel<<<n_items, NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
     lc.end();

@@ -1,0 +1,119 @@
+"""BASELINE.json configs at their STATED sizes through the C ABI against the CPU oracle.
+
+C1 lenna 512x512 RGB -> w=300&h=200&rgb=32,32,32; C2 1920x1080 RGB -> 300x200 fit + fill;
+C3 3840x2160 RGBA -> w=1618&h=1000&crop=true&blur=10 (opaque and random-alpha images);
+C4 480x270 RGBA GIF frames (in test_parity_gpu.py at full size already); C5 4000x3000 RGB ->
+w=1618&h=1000 with grayscale + blur=10, crop and fit + fill sub-configs (SURVEY.md section 8:
+crop and fill exclude each other, so "resize+crop+fill+blur+grayscale" is two requests); one
+sigma = 20 (81 taps) case at full size.  Each on a default context (what a single request
+takes) and on a `vertical_path = 3` context (what the BASELINE batches take: both Lanczos3
+passes on the tensor cores where the geometry allows).  Bars: Lanczos3 / blur within 1 LSB,
+histogram asserted (>= 2 must be empty); a batch through the device-resident entry point must
+give the same bytes as the single request.  Reference call sites: src/handler.rs:224-255.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from synth import synth_image
+
+pytestmark = pytest.mark.gpu
+
+
+def hist(a, b):
+    d = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    return {0: int((d == 0).sum()), 1: int((d == 1).sum()), ">=2": int((d >= 2).sum())}
+
+
+@pytest.fixture(scope="module", params=[0, 3], ids=["default_ctx", "vertical_path3"])
+def dev(fanlin, request):
+    d = fanlin.Device([0], vertical_path=request.param)
+    yield d
+    d.close()
+
+
+#        name                 seed  h     w     c  query                                                    oracle kwargs
+FULL = [
+    ("c2_fit_fill",           2001, 1080, 1920, 3, "w=300&h=200",                                           dict(w=300, h=200)),
+    ("c3_crop_blur10",          16, 2160, 3840, 4, "w=1618&h=1000&crop=true&blur=10",                       dict(w=1618, h=1000, crop=True, blur=10.0)),
+    ("c3_crop_blur10_alpha",    23, 2160, 3840, 4, "w=1618&h=1000&crop=true&blur=10",                       dict(w=1618, h=1000, crop=True, blur=10.0)),
+    ("c3_crop_noblur_alpha",    31, 2160, 3840, 4, "w=1618&h=1000&crop=true",                               dict(w=1618, h=1000, crop=True)),
+    ("c3_crop_blur20",          17, 2160, 3840, 4, "w=1618&h=1000&crop=true&blur=20",                       dict(w=1618, h=1000, crop=True, blur=20.0)),
+    ("c5_crop_gray_blur10",   5001, 3000, 4000, 3, "w=1618&h=1000&crop=true&grayscale=true&blur=10",        dict(w=1618, h=1000, crop=True, grayscale=True, blur=10.0)),
+    ("c5_fit_fill_gray_blur", 5002, 3000, 4000, 3, "w=1618&h=1000&rgb=200,16,99&grayscale=true&blur=10",    dict(w=1618, h=1000, rgb=(200, 16, 99), grayscale=True, blur=10.0)),
+    ("c5_crop_inverse_blur",  5003, 3000, 4000, 3, "w=1618&h=1000&crop=true&inverse=true&blur=15",          dict(w=1618, h=1000, crop=True, inverse=True, blur=15.0)),
+]
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c[0] for c in FULL])
+def test_baseline_config_full_size(fanlin, dev, case):
+    name, seed, h, w, c, qs, kw = case
+    img = synth_image(seed, h, w, c)
+    if c == 4 and "alpha" in name:
+        assert (img[..., 3] != 255).any()  # seed % 8 == 7: the f32 blend / alpha filtering is exercised
+    want = O.process(img, **kw)
+    got = fanlin.process_image(dev, img, fanlin.Query(qs))
+    assert got.shape == want.shape, (got.shape, want.shape)
+    hh = hist(got, want)
+    print(name, "mismatch histogram", hh)
+    assert hh[">=2"] == 0, hh
+    assert hh[1] <= got.size // 50, hh  # the fast paths differ by one on a tiny share of values, not on a percent
+
+
+def test_c1_lenna_full_request(fanlin, dev, lenna):
+    want = O.process(lenna, w=300, h=200, rgb=(32, 32, 32))
+    got = fanlin.process_image(dev, lenna, fanlin.Query("w=300&h=200&rgb=32,32,32"))
+    assert got.shape == (200, 300, 4)
+    hh = hist(got, want)
+    assert hh[">=2"] == 0, hh
+    # fill is bit-exact: the letterbox bars are the fill colour, opaque
+    assert (got[:, :50] == np.array([32, 32, 32, 255], np.uint8)).all() and (got[:, 250:] == np.array([32, 32, 32, 255], np.uint8)).all()
+
+
+@pytest.mark.parametrize("sigma", [0.8, 1.3, 10.3, 12.4, 17.76, 20.0])
+def test_blur_fractional_sigma(fanlin, dev, sigma):
+    """The C ABI takes any float sigma (Query::blur() only yields integers): the window is
+    ceil(2 sigma - 0.5) taps either side (10.3 -> 43 taps, 0.8 -> 5), not floor(2 sigma)."""
+    img = synth_image(77, 97, 131, 4 if sigma > 5 else 3)
+    j = fanlin.make_job(img, fanlin.Query(""))
+    j.blur_sigma = sigma
+    p = fanlin.plan_job(j)
+    out = np.zeros((p.out_h, p.out_w, p.out_channels), np.uint8)
+    j.dst, j.dst_capacity = out.ctypes.data, out.nbytes
+    dev.run([j])
+    want = O.process(img, blur=float(np.float32(sigma)))
+    hh = hist(out, want)
+    assert out.shape == want.shape and hh[">=2"] == 0, (sigma, hh)
+
+
+def test_device_batch_equals_single_requests_full_size(fanlin, dev):
+    """8 C3-shaped images (one with random alpha) as ONE device-resident batch: the bytes a merged
+    launch produces are the bytes each request produces alone."""
+    import torch
+
+    qs = "w=1618&h=1000&crop=true&blur=10"
+    seeds = [40, 41, 42, 47]  # 47 % 8 == 7: random alpha
+    imgs = [synth_image(s, 2160, 3840, 4) for s in seeds]
+    singles = [fanlin.process_image(dev, im, fanlin.Query(qs)) for im in imgs]
+    device = torch.device("cuda", 0)
+    src = torch.stack([torch.from_numpy(im) for im in imgs]).to(device)
+    dst = torch.zeros((len(imgs), 1000, 1618, 4), dtype=torch.uint8, device=device)
+    torch.cuda.synchronize()
+    q = fanlin.Query(qs)
+    jobs = (fanlin.Job * len(imgs))()
+    for i in range(len(imgs)):
+        fanlin.lib().fanlin_job_from_query(C.byref(q._q), 0, C.byref(jobs[i]))
+        jobs[i].src = src.data_ptr() + i * imgs[0].nbytes
+        jobs[i].src_w, jobs[i].src_h, jobs[i].src_channels = 3840, 2160, 4
+        jobs[i].dst = dst.data_ptr() + i * 1000 * 1618 * 4
+        jobs[i].dst_capacity = 1000 * 1618 * 4
+    b = dev.prepare(jobs, 0)
+    b.launch(None)
+    b.launch(None)  # relaunching a prepared batch is idempotent
+    torch.cuda.synchronize()
+    got = dst.cpu().numpy()
+    b.free()
+    for i, s in enumerate(singles):
+        assert np.array_equal(got[i], s), (seeds[i], hist(got[i], s))
