@@ -225,7 +225,8 @@ def run_other_configs(args, pkg, dev, torch, np, device, stream, peak, world, di
                "steps": steps, "ms_per_step": ms, "us_per_image": ms * 1e3 / (n * launches),
                "out_mpix_s": imgs_step * plan.out_w * plan.out_h / 1e6 / (ms * 1e-3),
                "algorithmic_bytes_per_image": int(plan.algorithmic_bytes), "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak,
-               "kernels_ms_per_launch": {k: sum(v) / len(v) for k, v in kt.items()},
+               # summed over the kernel instances of one batch launch (a batch whose scratch is chunked launches a kernel several times)
+               "kernels_ms_per_launch": {k: sum(v) / (steps * launches) for k, v in kt.items()},
                "scaling": "weak" if total is None else f"strong: {total} images over {world} GPU(s)"}
         if q.blur() and not gif:
             # the direct-form blur is FP32-bound -- report the blur kernels against the CUDA-core FMA peak too

@@ -71,6 +71,8 @@ int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 // DynamicImage::to_rgb8 of the final image (FANLIN_TO_RGB8), scratch -> dst.
 int launch_to_rgb8(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+// YCCK -> CMYK of the decode side (reference src/handler.rs:420-439); src == dst allowed.
+int launch_ycck_to_cmyk(const uint8_t *d_src, uint8_t *d_dst, size_t n_px, LaunchCtx &lc);
 // EXIF orientation (+ colour op) of the stored image into scratch, in front of every other stage.
 int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 

@@ -288,6 +288,53 @@ int launch_orient_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx 
     return 1;
 }
 
+// YCCK -> CMYK of convert_jpeg_color_if_needed (reference src/handler.rs:420-439): per 4-byte
+// pixel r/g/b = clamp(f32 expression of y, cb, cr) truncated, k = 255 - k.  The reference's f32 evaluation order
+// with separately rounded multiplies and adds (__fmul_rn / __fadd_rn: no FMA contraction) makes this bit-exact.
+// Four pixels (16 bytes) per thread and step, grid-stride; src == dst is allowed (the reference works in place).
+__device__ __forceinline__ uint32_t ycck_px(uint32_t p) {
+    const float y = float(p & 0xffu), cb = float((p >> 8) & 0xffu), cr = float((p >> 16) & 0xffu);
+    float r = __fadd_rn(__fadd_rn(y, __fmul_rn(1.40200f, cr)), -179.456f);
+    float g = __fadd_rn(__fadd_rn(__fadd_rn(y, -__fmul_rn(0.34414f, cb)), -__fmul_rn(0.71414f, cr)), 135.45984f);
+    float b = __fadd_rn(__fadd_rn(y, __fmul_rn(1.77200f, cb)), -226.816f);
+    r = fminf(fmaxf(r, 0.0f), 255.0f);
+    g = fminf(fmaxf(g, 0.0f), 255.0f);
+    b = fminf(fmaxf(b, 0.0f), 255.0f);
+    return uint32_t(r) | uint32_t(g) << 8 | uint32_t(b) << 16 | (255u - (p >> 24)) << 24;  // `as u8`: truncation
+}
+
+__global__ void __launch_bounds__(256) ycck_to_cmyk_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n_px) {
+    const size_t n4 = n_px / 4;
+    const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+    const size_t stride = size_t(gridDim.x) * 256;
+    if (vec) {
+        for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < n4; i += stride) {
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+            v.x = ycck_px(v.x); v.y = ycck_px(v.y); v.z = ycck_px(v.z); v.w = ycck_px(v.w);
+            reinterpret_cast<uint4 *>(dst)[i] = v;
+        }
+    }
+    // unaligned buffers, and the last n_px % 4 pixels: one pixel per thread, byte accesses
+    const size_t first = vec ? n4 * 4 : 0;
+    for (size_t i = first + size_t(blockIdx.x) * 256 + threadIdx.x; i < n_px; i += stride) {
+        const uint8_t *p = src + 4 * i;
+        const uint32_t o = ycck_px(uint32_t(p[0]) | uint32_t(p[1]) << 8 | uint32_t(p[2]) << 16 | uint32_t(p[3]) << 24);
+        uint8_t *q = dst + 4 * i;
+        q[0] = uint8_t(o); q[1] = uint8_t(o >> 8); q[2] = uint8_t(o >> 16); q[3] = uint8_t(o >> 24);
+    }
+}
+
+int launch_ycck_to_cmyk(const uint8_t *d_src, uint8_t *d_dst, size_t n_px, LaunchCtx &lc) {
+    if (n_px == 0) return 0;
+    // 148 SMs x 8 resident blocks of 256 threads; fewer for small buffers
+    const size_t want = (n_px / 4 + 255) / 256 + 1;
+    const uint32_t blocks = uint32_t(std::min<size_t>(148 * 8, want));
+    lc.begin("ycck_to_cmyk_kernel");
+    ycck_to_cmyk_kernel<<<blocks, 256, 0, lc.st>>>(d_src, d_dst, n_px);
+    lc.end();
+    return 1;
+}
+
 int launch_to_rgb8(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;
     const uint32_t blocks = std::min<uint32_t>(1024, (g.max_canvas_w * g.max_canvas_h + 255) / 256);

@@ -854,6 +854,61 @@ extern "C" void fanlin_shard_range(uint32_t n_jobs, uint32_t n_shards, uint32_t 
     if (hi) *hi = b;
 }
 
+// ---- YCCK -> CMYK (decode side, src/handler.rs:420-439) ---------------------------------------
+
+extern "C" int fanlin_ycck_to_cmyk_device(fanlin_ctx *ctx, int device_index, const uint8_t *src, uint8_t *dst, uint64_t n_pixels,
+                                          void *cuda_stream) {
+    if (!ctx || (n_pixels && (!src || !dst))) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
+    if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
+    if (device_index < 0 || device_index >= int(ctx->devs.size())) { set_error("fanlin: bad device index"); return FANLIN_EINVAL; }
+    DeviceState *dev = ctx->devs[device_index].get();
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    LaunchCtx lc;
+    lc.st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : dev->stream;
+    const int n = launch_ycck_to_cmyk(src, dst, size_t(n_pixels), lc);
+    CUDA_TRY(cudaGetLastError());
+    ctx->kernel_launches += uint64_t(n);
+    return FANLIN_OK;
+}
+
+extern "C" int fanlin_ycck_to_cmyk(fanlin_ctx *ctx, const uint8_t *src, uint8_t *dst, uint64_t n_pixels) {
+    if (!ctx || (n_pixels && (!src || !dst))) { set_error("fanlin: null argument"); return FANLIN_EINVAL; }
+    if (ctx->down) { set_error("fanlin: context is shut down"); return FANLIN_ESHUTDOWN; }
+    if (n_pixels == 0) return FANLIN_OK;
+    const int dev_index = int(ctx->rr++ % uint32_t(ctx->devs.size()));
+    DeviceState *dev = ctx->devs[dev_index].get();
+    std::lock_guard<std::mutex> lk(dev->mu);
+    CUDA_TRY(cudaSetDevice(dev->ordinal));
+    const uint64_t chunk_px = uint64_t(8) << 20;  // 32 MB per chunk, two in flight
+    cudaStream_t sts[2] = {dev->copy_in, dev->copy_out};
+    uint8_t *d_buf[2] = {nullptr, nullptr};
+    int rc = FANLIN_OK;
+    for (int k = 0; k < 2 && rc == FANLIN_OK; k++)
+        if (cudaMallocAsync(reinterpret_cast<void **>(&d_buf[k]), size_t(std::min(chunk_px, n_pixels)) * 4, sts[k]) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("fanlin: device allocation failed");
+            rc = FANLIN_ENOMEM;
+        }
+    uint32_t k = 0;
+    for (uint64_t p0 = 0; p0 < n_pixels && rc == FANLIN_OK; p0 += chunk_px, k ^= 1u) {
+        const uint64_t np = std::min(chunk_px, n_pixels - p0);
+        LaunchCtx lc;
+        lc.st = sts[k];  // stream order: the chunk that used this buffer two rounds ago has left it
+        if (cudaMemcpyAsync(d_buf[k], src + 4 * p0, size_t(np) * 4, cudaMemcpyHostToDevice, sts[k]) != cudaSuccess) { rc = FANLIN_ECUDA; break; }
+        ctx->kernel_launches += uint64_t(launch_ycck_to_cmyk(d_buf[k], d_buf[k], size_t(np), lc));
+        if (cudaMemcpyAsync(dst + 4 * p0, d_buf[k], size_t(np) * 4, cudaMemcpyDeviceToHost, sts[k]) != cudaSuccess) { rc = FANLIN_ECUDA; break; }
+        ctx->h2d_bytes += np * 4;
+        ctx->d2h_bytes += np * 4;
+    }
+    for (int q = 0; q < 2; q++) {
+        const cudaError_t se = cudaStreamSynchronize(sts[q]);
+        if (se != cudaSuccess && rc == FANLIN_OK) rc = FANLIN_ECUDA;
+        if (d_buf[q]) cudaFreeAsync(d_buf[q], sts[q]);
+    }
+    if (rc == FANLIN_ECUDA) set_error(std::string("fanlin: CUDA error in ycck_to_cmyk: ") + cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
 // Request batcher: one collector thread per device.  Small fanlin_run calls (a request = one
 // image, src/main.rs:179 calls process_image from up to max_clients tokio workers at once) queue
 // here; the collector waits batch_window_us after the first arrival, merges what came in into one

@@ -108,6 +108,8 @@ def lib():
         L.fanlin_get_stats.argtypes = [vp, P(Stats)]
         L.fanlin_shard_range.argtypes = [u32, u32, u32, P(u32), P(u32)]
         L.fanlin_shard_range.restype = None
+        L.fanlin_ycck_to_cmyk.argtypes = [vp, vp, vp, C.c_uint64]
+        L.fanlin_ycck_to_cmyk_device.argtypes = [vp, C.c_int, vp, vp, C.c_uint64, vp]
         L.fanlin_last_error.restype = C.c_char_p
         L.fanlin_query_parse.argtypes = [C.c_char_p, P(QueryStruct)]
         L.fanlin_query_dimensions.argtypes = [P(QueryStruct), P(u32), P(u32)]
@@ -228,6 +230,19 @@ class Device:
         h = C.c_void_p()
         check(lib().fanlin_batch_prepare(self._h, device_index, arr, n, plans, C.byref(h)))
         return DeviceBatch(self, h, plans, n)
+
+    def ycck_to_cmyk(self, raw: np.ndarray) -> np.ndarray:
+        """The YCCK -> CMYK loop of convert_jpeg_color_if_needed (src/handler.rs:420-439) on the device:
+        flat u8 buffer of 4-byte pixels in, converted copy out."""
+        a = np.ascontiguousarray(raw, dtype=np.uint8)
+        out = np.empty_like(a)
+        check(lib().fanlin_ycck_to_cmyk(self._h, C.c_void_p(a.ctypes.data), C.c_void_p(out.ctypes.data), a.size // 4))
+        if a.size % 4:
+            out.reshape(-1)[a.size - a.size % 4:] = a.reshape(-1)[a.size - a.size % 4:]
+        return out
+
+    def ycck_to_cmyk_device(self, src_ptr: int, dst_ptr: int, n_pixels: int, device_index: int = 0, cuda_stream: int | None = None):
+        check(lib().fanlin_ycck_to_cmyk_device(self._h, device_index, C.c_void_p(src_ptr), C.c_void_p(dst_ptr), n_pixels, C.c_void_p(cuda_stream or 0)))
 
     def host_alloc(self, nbytes: int) -> np.ndarray:
         """Pinned host buffer from the context's pool as a u8 array (free with host_free)."""

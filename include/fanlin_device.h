@@ -144,6 +144,16 @@ FANLIN_API void fanlin_batch_free(fanlin_batch *batch);
 FANLIN_API int fanlin_batch_set_timing(fanlin_batch *batch, int enable);
 FANLIN_API int fanlin_batch_kernel_times(fanlin_batch *batch, const char **names, float *ms, int cap);
 
+/* YCCK -> CMYK of a decoded Adobe JPEG, the float loop of convert_jpeg_color_if_needed
+ * (src/handler.rs:420-439): n_pixels 4-byte pixels {Y, Cb, Cr, K} -> {C', M', Y', 255 - K} with
+ * the reference's f32 expression order, clamp and truncating cast -- bit-exact.  src == dst is allowed (the reference
+ * converts in place).  The lcms2 CMYK -> RGB transform that follows (:469-493) stays on the host.
+ * fanlin_ycck_to_cmyk: host buffers, blocking (chunks alternate between two streams so copies overlap the kernel);
+ * fanlin_ycck_to_cmyk_device: device pointers on device_index, asynchronous on cuda_stream (NULL = the context's). */
+FANLIN_API int fanlin_ycck_to_cmyk(fanlin_ctx *ctx, const uint8_t *src, uint8_t *dst, uint64_t n_pixels);
+FANLIN_API int fanlin_ycck_to_cmyk_device(fanlin_ctx *ctx, int device_index, const uint8_t *src, uint8_t *dst, uint64_t n_pixels,
+                                          void *cuda_stream);
+
 /* Pinned host buffers from the context's pool, so decoders can write pixels
  * where the copy engine can read them without a staging memcpy. */
 FANLIN_API void *fanlin_host_alloc(fanlin_ctx *ctx, size_t bytes);

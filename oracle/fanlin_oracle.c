@@ -639,4 +639,33 @@ int fo_process_batch(fo_job *jobs, uint32_t n, uint32_t n_threads) {
     return rc;
 }
 
+/* ---- YCCK -> CMYK (decode side) -----------------------------------------
+ * Restates /root/reference/src/handler.rs:420-439 -- IN TREE, so this function is pinned by the
+ * reference's own source (unlike the image-crate restatement above): per 4-byte pixel
+ *   r = clamp(y + 1.40200 cr - 179.456, 0, 255)              ((y + 1.402 cr) - 179.456, f32, no FMA)
+ *   g = clamp(y - 0.34414 cb - 0.71414 cr + 135.45984, 0, 255)
+ *   b = clamp(y + 1.77200 cb - 226.816, 0, 255)
+ *   k = 255 - raw[3]
+ * stored with Rust's `as u8` (truncation), in place.  A trailing partial pixel is left as it is
+ * (the reference's loop would index out of bounds; zune-jpeg never yields one). */
+void fo_ycck_to_cmyk(uint8_t *raw, size_t n_bytes) {
+    for (size_t i = 0; i + 3 < n_bytes; i += 4) {
+        const float y = (float)raw[i], cb = (float)raw[i + 1], cr = (float)raw[i + 2];
+        float r = y + 1.40200f * cr;
+        r = r - 179.456f;
+        float g = y - 0.34414f * cb;
+        g = g - 0.71414f * cr;
+        g = g + 135.45984f;
+        float b = y + 1.77200f * cb;
+        b = b - 226.816f;
+        r = r < 0.0f ? 0.0f : (r > 255.0f ? 255.0f : r);
+        g = g < 0.0f ? 0.0f : (g > 255.0f ? 255.0f : g);
+        b = b < 0.0f ? 0.0f : (b > 255.0f ? 255.0f : b);
+        raw[i] = (uint8_t)r;
+        raw[i + 1] = (uint8_t)g;
+        raw[i + 2] = (uint8_t)b;
+        raw[i + 3] = (uint8_t)(255u - raw[i + 3]);
+    }
+}
+
 uint32_t fo_job_size(void) { return (uint32_t)sizeof(fo_job); }

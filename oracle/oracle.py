@@ -71,6 +71,8 @@ def lib():
         L.fo_overlay.restype = None
         L.fo_weight_table.argtypes = [C.c_int, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
         L.fo_weight_table.restype = C.c_uint32
+        L.fo_ycck_to_cmyk.argtypes = [C.c_void_p, C.c_size_t]
+        L.fo_ycck_to_cmyk.restype = None
         L.fo_apply_orientation.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -190,6 +192,13 @@ def apply_orientation(img, exif: int) -> np.ndarray:
     if rc:
         raise ValueError(f"fo_apply_orientation rc={rc}")
     return out.reshape(oh.value, ow.value, c)
+
+
+def ycck_to_cmyk(raw) -> np.ndarray:
+    """The YCCK -> CMYK loop of convert_jpeg_color_if_needed (src/handler.rs:420-439) on a flat u8 buffer of 4-byte pixels."""
+    a = np.ascontiguousarray(raw, dtype=np.uint8).copy()
+    lib().fo_ycck_to_cmyk(a.ctypes.data, a.size)
+    return a
 
 
 def out_capacity(j: Job) -> int:
