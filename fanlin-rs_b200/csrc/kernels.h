@@ -56,7 +56,8 @@ int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc);
 // Host: encodes the TMA tensor map (128 bytes at `out`) through which that kernel fetches rows of
 // one image: dims {row bytes, rows}, box {128 B, box_rows}, 128-byte swizzle.  Returns false on failure.
-bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t rows, uint32_t box_rows);
+// width_bytes: valid bytes per row (0 = pitch); columns beyond it are filled with zeros by the copy.
+bool encode_row_tile_map(void *out, const void *base, uint32_t pitch, uint32_t rows, uint32_t box_rows, uint32_t width_bytes = 0);
 // Fast Gaussian blur (kernels_blur.cu): items share channel count, radius and padded tap count.
 struct BlurItem;
 int launch_blur(const BlurItem *d_items, uint32_t n_items, uint32_t max_w, uint32_t max_h, uint32_t c, uint32_t radius,
@@ -67,6 +68,10 @@ int launch_compose(const StageDesc *d_descs, const TapEntry *d_tab, const Launch
 struct BlurVTcItem;
 int launch_blur_v_tc(const BlurVTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b,
                      const uint32_t *d_info, LaunchCtx &lc);
+// Blur with both passes on the tensor cores, u8 in, u8 out, no intermediate in HBM (kernels_blur_tc.cu).
+struct BlurTcItem;
+int launch_blur_tc(const BlurTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b, const uint32_t *d_info,
+                   const float *d_w, LaunchCtx &lc);
 // Colour op alone over the needed source rows (in front of the tensor-core resample).
 int launch_color_pass(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 // DynamicImage::to_rgb8 of the final image (FANLIN_TO_RGB8), scratch -> dst.

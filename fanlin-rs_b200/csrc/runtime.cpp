@@ -293,8 +293,11 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     FusedTcTables tctabs;
     const bool use_tc = ctx->cfg.vertical_path != 1;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
     std::vector<uint8_t> fast_b(n_jobs, 0);  // stage B takes the fast blur kernels
+    std::vector<uint8_t> tc_b(n_jobs, 0);    // ... both passes on the tensor cores, no f32 intermediate (kernels_blur_tc.cu)
     BlurTables btabs;
     std::vector<BlurItem> bitems;
+    std::vector<BlurTcItem> btitems;
+    std::unique_ptr<BlurTcCache, void (*)(BlurTcCache *)> btcache(blur_tc_cache_new(), blur_tc_cache_free);
 
     // 1. plans + table arena
     std::map<const AxisTable *, uint32_t> tab_base;
@@ -346,6 +349,15 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         if (!fused_a[i] && !gather_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         fast_b[i] = !exact && blur_eligible(p.b);
+        if (fast_b[i] && use_tc && ctx->cfg.blur_path != 1) {
+            // rows of the blur's input: the caller's image, or scratch (orientation pass / the canvas of stage A: 256-byte
+            // aligned blocks, rows on a 16-byte stride)
+            const bool from_caller = p.b.src_is_input && !p.pre.present;
+            const uint8_t *bsrc = from_caller ? jobs[i].src : nullptr;
+            const uint32_t bpitch = p.b.src_is_input ? (ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels)
+                                                     : (p.b.in_pitch ? p.b.in_pitch : p.b.in_w * p.b.c);
+            tc_b[i] = blur_tc_eligible(p.b, bpitch, bsrc);
+        }
         if (!fast_b[i]) { add_table(p.b.vtab); add_table(p.b.htab); }
     }
 
@@ -362,7 +374,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_pitch) * p.a.canvas_h, 256);
             size_t ta = 0, tb = 0;
             if (p.a.present && p.a.separable && !fused_a[i] && !gather_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
-            if (p.b.present) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of either blur path
+            if (p.b.present && !tc_b[i]) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of the two-kernel blur paths
             js[i].tmp = align_up(std::max(ta, tb), 256);
             if (p.post_c_in) js[i].fin = align_up(size_t(p.pub.out_w) * p.pub.out_h * p.post_c_in, 256);  // the final image before to_rgb8
             const size_t need = js[i].pre + js[i].inter + js[i].tmp + js[i].fin;
@@ -503,8 +515,22 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             *pitch = p.b.src_is_input ? (ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels)
                                       : (p.b.in_pitch ? p.b.in_pitch : p.b.in_w * p.b.c);
         };
+        {  // both blur passes on the tensor cores: one launch for all such jobs of the chunk
+            HostStep hb{9, btitems.size(), LaunchGeom{}, 0, 0, 0, 0};
+            for (uint32_t i = begin; i < end; i++) {
+                if (!tc_b[i]) continue;
+                const JobPlan &p = b->plans[i];
+                const uint8_t *src; uint32_t pitch;
+                b_src(i, &src, &pitch);
+                const int rc = blur_tc_build(p.b, src, pitch, ej[i].dst, p.b.in_w * p.b.c, btcache.get(), &btabs, &ftabs, &tctabs, &btitems);
+                if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core blur tables"); return rc; }
+            }
+            hb.n_items = uint32_t(btitems.size() - hb.first);
+            for (size_t k = hb.first; k < btitems.size(); k++) hb.smem = std::max(hb.smem, blur_tc_smem_bytes(btitems[k].box_rows, btitems[k].kg_max, btitems[k].n_win));
+            if (hb.n_items) hsteps.push_back(hb);
+        }
         for (uint32_t i = begin; i < end; i++)
-            if (fast_b[i]) {
+            if (fast_b[i] && !tc_b[i]) {
                 uint32_t sb;
                 std::memcpy(&sb, &b->plans[i].b.sigma, 4);
                 const uint8_t *src; uint32_t pitch;
@@ -572,7 +598,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     const size_t off_bi = off_tm + align_up(tcitems.size() * 128, 256);
     const size_t off_bvi = off_bi + align_up(bitems.size() * sizeof(BlurItem), 256);
     const size_t off_bvm = off_bvi + align_up(bvitems.size() * sizeof(BlurVTcItem), 256);
-    const size_t meta_bytes = off_bvm + align_up(bvitems.size() * 128, 256) + 256;
+    const size_t off_bti = off_bvm + align_up(bvitems.size() * 128, 256);
+    const size_t off_btm = off_bti + align_up(btitems.size() * sizeof(BlurTcItem), 256);
+    const size_t meta_bytes = off_btm + align_up(btitems.size() * 128, 256) + 256;
     b->h_meta = ctx->pinned.alloc(meta_bytes);  // pinned, kept until the batch is freed: the upload is asynchronous
     if (!b->h_meta) { set_error("fanlin: pinned allocation failed"); return FANLIN_ENOMEM; }
     struct MetaView {
@@ -586,6 +614,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     if (!bvitems.empty()) std::memcpy(meta.data() + off_bvi, bvitems.data(), bvitems.size() * sizeof(BlurVTcItem));
     for (size_t k = 0; k < bvitems.size(); k++) {
         if (!encode_row_tile_map(meta.data() + off_bvm + k * 128, bvitems[k].src, bvitems[k].src_pitch, bvitems[k].src_h, bvitems[k].kg_max)) {
+            set_error("fanlin: cuTensorMapEncodeTiled failed");
+            return FANLIN_ECUDA;
+        }
+    }
+    if (!btitems.empty()) std::memcpy(meta.data() + off_bti, btitems.data(), btitems.size() * sizeof(BlurTcItem));
+    for (size_t k = 0; k < btitems.size(); k++) {  // the row bytes beyond n_e (pitch padding) must read as zeros: the map's width is n_e
+        if (!encode_row_tile_map(meta.data() + off_btm + k * 128, btitems[k].src, btitems[k].src_pitch, btitems[k].src_h, btitems[k].box_rows, btitems[k].n_e)) {
             set_error("fanlin: cuTensorMapEncodeTiled failed");
             return FANLIN_ECUDA;
         }
@@ -623,6 +658,17 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 b->steps.push_back(st);
                 b->launches_per_run += hs.n_paired ? 1 : 2;
             }
+            continue;
+        }
+        if (hs.kind == 9) {
+            fanlin_batch::Step st{};
+            st.kind = 9;
+            st.bt_items = reinterpret_cast<const BlurTcItem *>(mbase + off_bti) + hs.first;
+            st.tmaps = mbase + off_btm + hs.first * 128;
+            st.n_items = hs.n_items;
+            st.smem = hs.smem;
+            b->steps.push_back(st);
+            b->launches_per_run += 1;
             continue;
         }
         if (hs.kind == 7) {
@@ -689,6 +735,8 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
     for (const fanlin_batch::Step &s : b->steps) {
         if (s.kind == 4) {
             n += launch_blur(s.blur_items, s.n_items, s.max_w, s.max_h, s.c, s.radius, s.taps_pad, b->d_fw, s.n_paired != 0, lc);
+        } else if (s.kind == 9) {
+            n += launch_blur_tc(s.bt_items, s.tmaps, s.n_items, s.smem, b->d_tb, b->d_finfo, b->d_fw, lc);
         } else if (s.kind == 7) {
             n += launch_blur_v_tc(s.bv_items, s.tmaps, s.n_items, s.smem, b->d_tb, b->d_finfo, lc);
         } else if (s.kind == 3) {

@@ -12,6 +12,7 @@
 #include <thread>
 #include <vector>
 
+#include "blur.h"
 #include "kernels.h"
 #include "plan.h"
 
@@ -75,11 +76,12 @@ struct fanlin_batch {
     uint32_t n_jobs = 0;
     std::vector<fanlin::JobPlan> plans;
     struct Step {
-        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores), 4 blur, 5 colour pass, 6 orientation pass, 7 vertical blur (tensor cores), 8 to_rgb8
+        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores), 4 blur, 5 colour pass, 6 orientation pass, 7 vertical blur (tensor cores), 8 to_rgb8, 9 blur with both passes on the tensor cores
         const fanlin::BlurItem *blur_items;
         uint32_t max_w, max_h, c, radius, taps_pad;
         const fanlin::FusedTcItem *tc_items;
         const fanlin::BlurVTcItem *bv_items;
+        const fanlin::BlurTcItem *bt_items;
         const void *tmaps;  // CUtensorMap per tc item
         size_t smem;
         const fanlin::StageDesc *descs;

@@ -49,7 +49,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("exact", C.c_uint32),
         ("device_scratch_bytes", C.c_uint64), ("pinned_bytes", C.c_uint64),
         ("batch_window_us", C.c_uint32), ("max_batch_jobs", C.c_uint32),
-        ("vertical_path", C.c_uint32), ("reserved1", C.c_uint32),
+        ("vertical_path", C.c_uint32), ("blur_path", C.c_uint32),
     ]
 
 
@@ -180,12 +180,12 @@ class Device:
     """fanlin_ctx: created once at start-up, shared by all request threads."""
 
     def __init__(self, device_ids=None, *, exact=False, device_scratch_bytes=0, pinned_bytes=0,
-                 batch_window_us=0, max_batch_jobs=0, tensor_cores=True, vertical_path=None):
+                 batch_window_us=0, max_batch_jobs=0, tensor_cores=True, vertical_path=None, blur_path=0):
         """vertical_path: None = from tensor_cores (0 / 1); 2 = tensor cores for the vertical pass only
         (the horizontal stage stays on the CUDA cores); 3 = both passes on the tensor cores whatever the
         batch size (0 takes them from 256 jobs per batch on)."""
         cfg = Config(C.sizeof(Config), int(exact), device_scratch_bytes, pinned_bytes, batch_window_us, max_batch_jobs,
-                     (0 if tensor_cores else 1) if vertical_path is None else int(vertical_path), 0)
+                     (0 if tensor_cores else 1) if vertical_path is None else int(vertical_path), int(blur_path))
         h = C.c_void_p()
         if device_ids:
             arr = (C.c_int * len(device_ids))(*device_ids)

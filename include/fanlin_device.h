@@ -97,7 +97,7 @@ typedef struct fanlin_config {
     uint32_t batch_window_us;    /* request batcher collection window; 0 = default */
     uint32_t max_batch_jobs;     /* 0 = default */
     uint32_t vertical_path;      /* 0 = tensor cores: both passes for batches of >= 256 jobs where eligible, else the vertical pass; 1 = CUDA cores only; 2 = tensor cores for the vertical pass only; 3 = both passes whatever the batch size */
-    uint32_t reserved1;
+    uint32_t blur_path;          /* 0 = both blur passes on the tensor cores where eligible (no f32 intermediate in HBM); 1 = the two-kernel blur (vertical pass on the tensor cores, horizontal on the CUDA cores) */
 } fanlin_config;
 
 typedef struct fanlin_stats {
