@@ -19,6 +19,8 @@ struct TcBand {
 struct TcGeom {
     bool ok = false;
     bool hm = false;        // horizontal stage on the tensor cores
+    bool ring = false;      // ... with its sums accumulated in TMEM across chunks (fused_resample_tc3_kernel)
+    uint32_t ring_cols = 0, n_vr = 0, stage_stride = 0, wh_bytes = 0;
     uint32_t hrec_off = 0;  // its per-chunk records
     uint32_t b0 = 0, n_chunks = 0, chunk_off = 0, hw_off = 0, hinfo_off = 0, cpre_off = 0, out_stride = 1;
     float scale = 1.f;
@@ -116,7 +118,15 @@ size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint
     return a + b + wh + t + out;  // the kernel's static shared memory is a multiple of 1024 bytes: the dynamic part starts aligned
 }
 
+size_t fused_tc3_smem_bytes(uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t wh_bytes, uint32_t stage_stride) {
+    const size_t a = size_t(n_a) * kg_max * TC_M, b = 2 * size_t(TC_N) * kg_max;  // source slots, two vertical weight-tile slots
+    const size_t t = 2 * size_t(n_groups) * 32 * 256;                             // T hi + lo
+    const size_t stage = 8 * ((16 + size_t(32) * stage_stride * 4 + 15) & ~size_t(15));  // per consumer warp: guard + [32 rows][stage_stride words]
+    return a + b + t + size_t(n_wh) * wh_bytes + stage;
+}
+
 size_t fused_tc_item_smem(const FusedTcItem &it) {
+    if (it.hmma == 2) return fused_tc3_smem_bytes(it.n_groups, it.kg_max, it.n_a, it.n_wh, it.wh_bytes, it.stage_stride);
     return it.hmma ? fused_tc2_smem_bytes(it.c, it.n_groups, it.kg_max, it.n_a, it.n_wh, it.band_rows, it.out_stride)
                    : fused_tc_smem_bytes(it.c, it.band_rows, it.kg_max, it.out_stride, it.n_a);
 }
@@ -299,6 +309,118 @@ static bool build_hmma(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
     return true;
 }
 
+// Horizontal stage with the sums accumulated in TMEM (fused_resample_tc3_kernel): output pixel o lives in ring slot
+// (o - ox0) mod RP of its row tile, at accumulator columns slot * c + channel; a chunk's MMAs add into the window of slots
+// its 128 tile columns touch (split in two where the window wraps), the consumers drain, round and zero the slots whose
+// taps ended in the chunk.  The ring only has to hold the outputs a chunk touches, so ratios near 2 (C1, C3) fit.
+// Per chunk: one f16 tile pair hi | lo [n_total][128] (K-major core matrices; row n = window column n) and a record of
+// 8 words {tile offset, first output finished (relative to ox0), outputs finished, window column, window columns,
+// ring slot of the first finished output, 0, 0}.
+static uint32_t ring_slot_align(uint32_t c) { return c == 4 ? 4u : c == 2 ? 8u : 16u; }  // RP * c is a multiple of 16
+
+static bool build_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTables *tct) {
+    const AxisTable &t = *s.htab;
+    const uint32_t C = s.c, o0 = s.ox0, o_end = s.ox0 + s.n_cols;
+    uint32_t live_max = 0, fin_max = 0;
+    {
+        uint32_t fin = o0, touch = o0;
+        for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+            const uint32_t b1 = g.b0 + TC_M * (ch + 1), x_hi = (b1 - 1) / C, first = fin;
+            while (touch < o_end && t.entries[touch].left <= x_hi) touch++;
+            live_max = std::max(live_max, touch - fin);
+            while (fin < touch && (t.entries[fin].left + t.entries[fin].count) * C <= b1) fin++;
+            fin_max = std::max(fin_max, fin - first);
+        }
+        if (fin != o_end) return false;
+    }
+    const uint32_t al = ring_slot_align(C);
+    const uint32_t RP = (std::max(live_max, 1u) + al - 1) / al * al, RINGC = RP * C;
+    if (RINGC > 256) return false;
+    g.ring_cols = RINGC;
+    g.stage_stride = ((fin_max * s.c_out + 3) / 4 + 1) | 1u;  // words per staged row, odd: rows on distinct banks
+    std::vector<uint16_t> w_hi(t.weights.size()), w_lo(t.weights.size());
+    for (uint32_t o = o0; o < o_end; o++) {
+        const TapEntry &e = t.entries[o];
+        for (uint32_t tt = 0; tt < e.count; tt++) {
+            const float w = t.weights[e.woff + tt] * TC2_WSCALE;
+            const __half wh = __float2half_rn(w);
+            w_hi[e.woff + tt] = __half_as_ushort(wh);
+            w_lo[e.woff + tt] = __half_as_ushort(__float2half_rn(w - __half2float(wh)));
+        }
+    }
+    std::vector<uint32_t> rec(size_t(8) * g.n_chunks, 0u);
+    uint32_t fin = o0, touch = o0, n_max = 0;
+    for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+        const uint32_t b0 = g.b0 + TC_M * ch, b1 = b0 + TC_M, x_hi = (b1 - 1) / C;
+        while (touch < o_end && t.entries[touch].left <= x_hi) touch++;
+        const uint32_t u0 = ((fin - o0) % RP) * C, len = (touch - fin) * C;  // window in ring columns, before wrapping
+        const uint32_t w0 = u0 & ~15u;
+        uint32_t n_total = (u0 + len - w0 + 15) & ~15u;
+        if (n_total == 0) n_total = 16;  // a chunk no output touches still issues its (all-zero) MMAs
+        if (n_total > RINGC) return false;
+        n_max = std::max(n_max, n_total);
+        const size_t off = (tct->b.size() + 127) & ~size_t(127);
+        tct->b.resize(off + size_t(n_total) * 512, 0);
+        uint16_t *hi = reinterpret_cast<uint16_t *>(&tct->b[off]), *lo = hi + size_t(n_total) * 128;
+        for (uint32_t o = fin; o < touch; o++) {
+            const TapEntry &e = t.entries[o];
+            const uint32_t ta = e.left * C + C > b0 ? 0u : (b0 - (e.left * C + C - 1) + C - 1) / C;
+            for (uint32_t tt = ta; tt < e.count && (e.left + tt) * C < b1; tt++) {
+                for (uint32_t chn = 0; chn < C; chn++) {
+                    const uint32_t byte = (e.left + tt) * C + chn;
+                    if (byte < b0 || byte >= b1) continue;
+                    const uint32_t k = byte - b0, n = u0 - w0 + (o - fin) * C + chn;
+                    const size_t at = (size_t(n / 8) * 16 + k / 8) * 64 + (n % 8) * 8 + k % 8;  // in f16 elements
+                    hi[at] = w_hi[e.woff + tt];
+                    lo[at] = w_lo[e.woff + tt];
+                }
+            }
+        }
+        const uint32_t first = fin;
+        while (fin < touch && (t.entries[fin].left + t.entries[fin].count) * C <= b1) fin++;
+        uint32_t *r = &rec[size_t(8) * ch];
+        r[0] = uint32_t(off); r[1] = first - o0; r[2] = fin - first; r[3] = w0; r[4] = n_total; r[5] = (first - o0) % RP;
+    }
+    g.wh_bytes = n_max * 512;
+    g.hrec_off = uint32_t(tabs->info.size());
+    tabs->info.insert(tabs->info.end(), rec.begin(), rec.end());
+    return true;
+}
+
+// Bands, TMEM and shared-memory plan of the ring variant; fills g on success.
+static bool try_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTables *tct) {
+    const size_t info_mark = tabs->info.size(), b_mark = tct->b.size();
+    if (!build_ring(s, g, tabs, tct)) { tabs->info.resize(info_mark); tct->b.resize(b_mark); return false; }
+    const int sh = weight_shift(*s.vtab);
+    bool fits = false;
+    uint32_t band_rows = s.n_rows;
+    for (uint32_t n_bands = 1; n_bands <= 64 && !fits; n_bands++) {
+        band_rows = (s.n_rows + n_bands - 1) / n_bands;
+        fits = true;
+        for (uint32_t r0 = 0; r0 < s.n_rows && fits; r0 += band_rows) {
+            uint32_t ng = 0, kgm = 0;
+            fits = plan_band(*s.vtab, s.oy0, r0, std::min(band_rows, s.n_rows - r0), 8, &ng, &kgm) && ng <= 8;
+            if (!fits) break;
+            const uint32_t n_mt = (ng + 3) / 4;
+            fits = n_mt * g.ring_cols + 2 * TC_N <= 512 &&
+                   fused_tc3_smem_bytes(ng, kgm, 2, 1, g.wh_bytes, g.stage_stride) <= TC_SMEM_LIMIT;
+        }
+    }
+    if (!fits) { tabs->info.resize(info_mark); tct->b.resize(b_mark); return false; }
+    g.scale = std::ldexp(1.0f, -sh);
+    g.out_stride = g.stage_stride;
+    for (uint32_t r0 = 0; r0 < s.n_rows; r0 += band_rows) {
+        TcBand bt{};
+        if (!build_band(*s.vtab, s.oy0, r0, std::min(band_rows, s.n_rows - r0), sh, 8, tabs, tct, &bt)) {
+            g.bands.clear();
+            return false;  // (tables appended so far stay: unreferenced bytes)
+        }
+        g.bands.push_back(bt);
+    }
+    g.hm = true; g.ring = true; g.ok = true;
+    return true;
+}
+
 static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
     const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c | (s.c_out << 8));
     auto it = cache->geoms.find(key);
@@ -355,6 +477,7 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
             }
             g.bands.clear();
         }
+        if (try_ring(s, g, tabs, tct)) return cache->geoms.emplace(key, std::move(g)).first->second;
     }
     std::vector<PxPair> pairs;
     std::vector<uint32_t> recs;
@@ -430,7 +553,11 @@ bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *
 
 bool fused_tc_uses_hmma(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
     const TcGeom &g = geom_of(s, cache, tabs, tct);
-    return g.ok && g.hm;
+    return g.ok && g.hm && !g.ring;
+}
+bool fused_tc_uses_ring(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
+    const TcGeom &g = geom_of(s, cache, tabs, tct);
+    return g.ok && g.ring;
 }
 
 int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
@@ -453,7 +580,15 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         f.dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
         f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;
         f.first_band = b == 0; f.last_band = b + 1 == g.bands.size();
-        if (g.hm) {
+        if (g.ring) {
+            f.hmma = 2; f.hrec_off = g.hrec_off;
+            f.ring_cols = g.ring_cols; f.stage_stride = g.stage_stride; f.wh_bytes = g.wh_bytes;
+            const uint32_t n_mt = (bt.n_groups + 3) / 4;
+            f.n_vr = std::min(4u, (512u - n_mt * g.ring_cols) / TC_N);
+            f.n_a = std::min(4u, f.n_vr); f.n_wh = 1;  // n_a <= n_vr: a slot's release is read off the barrier of the region its group used, one phase back at most
+            while (f.n_a > 2 && fused_tc3_smem_bytes(bt.n_groups, bt.kg_max, f.n_a, 1, g.wh_bytes, g.stage_stride) > TC_SMEM_LIMIT) f.n_a--;
+            if (fused_tc3_smem_bytes(bt.n_groups, bt.kg_max, f.n_a, 2, g.wh_bytes, g.stage_stride) <= TC_SMEM_LIMIT) f.n_wh = 2;
+        } else if (g.hm) {
             f.hmma = 1; f.hrec_off = g.hrec_off;
             f.n_a = 4; f.n_wh = 1;
             while (f.n_a > 2 && fused_tc2_smem_bytes(s.c, bt.n_groups, bt.kg_max, f.n_a, 1, bt.rows, g.out_stride) > TC_SMEM_LIMIT) f.n_a--;

@@ -53,6 +53,11 @@ struct FusedTcItem {
     // tensor-core horizontal stage (fused_resample_tc2_kernel): per-chunk records {byte offset of the chunk's f16
     // weight tiles, first output finished by the chunk (relative to the first produced column), outputs finished}
     uint32_t hmma, hrec_off, n_wh;
+    // hmma == 2: the horizontal sums stay in TMEM across chunks (fused_resample_tc3_kernel): a ring of ring_cols accumulator
+    // columns per row tile (output pixel o at column (o mod ring pixels) * c), n_vr vertical regions behind the rings,
+    // stage_stride words per row of a consumer warp's output staging tile; per-chunk records of 8 words
+    // {tile offset, first output finished, outputs finished, window column, window columns, ring slot of the first finished, 0, 0}
+    uint32_t ring_cols, n_vr, stage_stride, wh_bytes;
 };
 
 // Tensor-core horizontal stage: the chunk's 128 tile columns (K) are contracted with an f16 weight
@@ -61,6 +66,7 @@ inline uint32_t fused_tc2_n(uint32_t c) { return c == 3 ? 48u : 64u; }
 constexpr uint32_t TC2_MIN_JOBS = 256; // batches below this keep the CUDA-core horizontal stage (no per-chunk weight tiles to build)
 constexpr float TC2_WSCALE = 16.0f;  // horizontal weights are stored x16: their low halves stay f16 normals
 size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t band_rows, uint32_t out_stride);
+size_t fused_tc3_smem_bytes(uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t wh_bytes, uint32_t stage_stride);
 size_t fused_tc_item_smem(const FusedTcItem &it);
 
 // Vertical Gaussian pass of the blur on the tensor cores (kernels_fused_tc.cu blur_v_tc_kernel):
@@ -87,6 +93,7 @@ FusedTcCache *fused_tc_cache_new(bool allow_hmma = true);
 void fused_tc_cache_free(FusedTcCache *);
 bool fused_tc_geometry_ok(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs);
 bool fused_tc_uses_hmma(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs);
+bool fused_tc_uses_ring(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs);
 int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src, uint32_t src_pitch, uint8_t *dst,
                    FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tctabs, std::vector<FusedTcItem> *items);
 

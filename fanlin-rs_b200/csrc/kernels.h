@@ -54,6 +54,8 @@ int launch_fused(const FusedItem *d_items, uint32_t n_items, uint32_t variant, u
 struct FusedTcItem;
 int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc);
+int launch_fused_tc3(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
+                     const uint32_t *d_info, LaunchCtx &lc);
 // Host: encodes the TMA tensor map (128 bytes at `out`) through which that kernel fetches rows of
 // one image: dims {row bytes, rows}, box {128 B, box_rows}, 128-byte swizzle.  Returns false on failure.
 // width_bytes: valid bytes per row (0 = pitch); columns beyond it are filled with zeros by the copy.

@@ -958,6 +958,7 @@ void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t
 int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
     if (n_items == 0) return 0;
+    if (c & 16) return launch_fused_tc3(d_items, d_tmaps, n_items, c & 7, smem, d_b, d_info, lc);  // ... with the horizontal sums kept in TMEM
     if (c & 8) {  // both passes on the tensor cores
         switch (c & 7) {
         case 1: launch_tc2_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;

@@ -1,0 +1,417 @@
+// Fused separable Lanczos3 resample, both passes on the sm_100a tensor cores, horizontal sums ACCUMULATED IN TMEM
+// across chunks (fused_resample_tc3_kernel).  Same vertical pass and T tiles as fused_resample_tc2_kernel
+// (kernels_fused_tc.cu: banded u8 x s8 contraction, three weight digits, f16 hi / lo operand tiles), but the horizontal
+// contraction of a chunk adds into a RING of accumulator columns per row tile instead of producing partial sums the
+// consumers keep in registers: output pixel o lives at columns ((o - ox0) mod RP) * c + channel, a chunk's MMAs cover
+// the window of slots its 128 tile columns touch (two pieces where the window wraps), and the consumers read, round,
+// store and zero only the slots whose taps ended in the chunk.  The ring has to hold what ONE chunk touches (not what
+// fits a thread's registers), so downscales near 2 (BASELINE C1: 512 -> 200, C3: 3840 -> 1778 RGBA) take this kernel.
+//
+// Roles (1 CTA / SM, 12 warps): source TMA thread, vertical-weight TMA thread, vertical MMA thread, horizontal thread
+// (weight tiles + MMAs), 8 consumer warps.  A consumer warp owns 32 band rows of ONE row tile for the drain (warp = tile *
+// 4 + lane quarter when the band has two tiles; with one tile the two warps of a quarter split the finished pixels), stages
+// its pixels in its own shared-memory tile and stores them as aligned words of a few rows per store.
+// Reference call sites: src/handler.rs:229-248 (resize / resize_to_fill + letterbox), image-0.25.6 imageops::resize.
+#include <cuda.h>
+
+#include "fused_device.cuh"
+#include "fused_tc.h"
+#include "kernels.h"
+#include "tc_device.cuh"
+
+namespace fanlin {
+
+namespace {
+
+constexpr int T3_NT = 256;            // consumer threads
+constexpr int T3_NT_ALL = T3_NT + 128;
+constexpr uint32_t T3_NB = 2;         // vertical weight-tile slots
+constexpr uint32_t T3_NA_MAX = 4;
+#ifndef T3_PF_AHEAD
+#define T3_PF_AHEAD 4
+#endif
+
+__device__ __forceinline__ void t3_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+template <int C>
+__global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const FusedTcItem *__restrict__ items, const CUtensorMap *__restrict__ tmaps,
+                                                                          const uint8_t *__restrict__ tb, const uint32_t *__restrict__ tinfo) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ FusedTcItem it_s;
+    __shared__ __align__(8) uint64_t v_full[4], v_free[4], a_full[T3_NA_MAX], b_full[T3_NB];
+    __shared__ __align__(8) uint64_t t_ready[2], d2_full[2], d2_free[2], wh_full[2], wh_free[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t grp[4 * 8];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    if (tid == 0) {
+        it_s = items[blockIdx.x];
+        auto init = [](uint64_t *b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); };
+        for (uint32_t r = 0; r < 4; r++) { init(&v_full[r], 1); init(&v_free[r], 8); }
+        for (uint32_t r = 0; r < T3_NA_MAX; r++) init(&a_full[r], 1);
+        for (uint32_t r = 0; r < T3_NB; r++) init(&b_full[r], 1);
+        for (uint32_t r = 0; r < 2; r++) {
+            init(&t_ready[r], 8);
+            init(&d2_full[r], 1);
+            init(&d2_free[r], 8);
+            init(&wh_full[r], 1);
+            init(&wh_free[r], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const FusedTcItem &it = it_s;
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp < T3_NT / 32) fill_bars(it, warp, lane, T3_NT / 32);
+
+    // ---- shared memory: T hi | T lo | source slots | vertical weight slots | horizontal weight slots | output staging per consumer warp
+    const uint32_t kg_max = it.kg_max, n_a = it.n_a, n_groups = it.n_groups, n_chunks = it.n_chunks;
+    const uint32_t t_bytes = n_groups * 32u * 256u;
+    const uint32_t n_mt = (n_groups + 3) / 4, n_vr = it.n_vr, ring_cols = it.ring_cols;
+    const uint32_t v0 = n_mt * ring_cols;  // first TMEM column of the vertical regions
+    const uint32_t sT_u = smem_u32(smem);
+    const uint32_t sA_u = sT_u + 2 * t_bytes;
+    const uint32_t sB_u = sA_u + n_a * kg_max * TC_M;
+    const uint32_t sWh_u = sB_u + T3_NB * TC_N * kg_max;
+    const uint32_t n_wh = it.n_wh, wh_bytes = it.wh_bytes;
+    const uint32_t stage_warp = (16u + 32u * it.stage_stride * 4u + 15u) & ~15u;
+    const uint32_t stage_u = sWh_u + n_wh * wh_bytes;
+    for (uint32_t k = tid; k < 4 * n_groups; k += T3_NT_ALL) grp[k] = tinfo[it.grp_off + k];
+    __syncthreads();
+    const uint32_t total = n_chunks * n_groups;
+    const uint32_t *hrec = tinfo + it.hrec_off;
+
+    if (warp == T3_NT / 32 + 1) {
+        // ================= source TMA thread: one tensor copy per group, n_a groups deep =================
+        if (elect_one()) {
+            const CUtensorMap *tmap = tmaps + blockIdx.x;
+            asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
+            uint32_t g = 0, chunk = 0, slot = 0, pg = 0, pchunk = 0;
+            uint32_t wreg = 0, wuse = 0;  // region / use count of the group whose MMAs free the slot being refilled (group gg - n_a)
+            for (uint32_t k = 0; k < T3_PF_AHEAD && pchunk < n_chunks; k++)
+                if (++pg == n_groups) { pg = 0; pchunk++; }
+            for (uint32_t gg = 0; gg < total; gg++) {
+                if (pchunk < n_chunks) {
+                    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(it.b0 + TC_M * pchunk), "r"(grp[4 * pg]) : "memory");
+                    if (++pg == n_groups) { pg = 0; pchunk++; }
+                }
+                if (gg >= n_a) {
+                    mbar_wait(smem_u32(&v_full[wreg]), wuse & 1);
+                    if (++wreg == n_vr) { wreg = 0; wuse++; }
+                }
+                const uint32_t bar = smem_u32(&a_full[slot]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(sA_u + slot * kg_max * TC_M),
+                             "l"(tmap), "r"(bar), "r"(it.b0 + TC_M * chunk), "r"(grp[4 * g])
+                             : "memory");
+                if (++slot == n_a) slot = 0;
+                if (++g == n_groups) { g = 0; chunk++; }
+            }
+        }
+    } else if (warp == T3_NT / 32 + 2) {
+        // ================= vertical-weight TMA thread =================
+        if (elect_one()) {
+            uint32_t g = 0, wreg = 0, wuse = 0;
+            for (uint32_t gg = 0; gg < total; gg++) {
+                if (gg >= T3_NB) {
+                    mbar_wait(smem_u32(&v_full[wreg]), wuse & 1);  // the slot's previous tile was read by the MMAs of group gg - 2
+                    if (++wreg == n_vr) { wreg = 0; wuse++; }
+                }
+                const uint32_t kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
+                const uint32_t bar = smem_u32(&b_full[gg & 1]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sB_u + (gg & 1) * TC_N * kg_max),
+                             "l"(tb + b_off), "r"(kg * TC_N), "r"(bar)
+                             : "memory");
+                if (++g == n_groups) g = 0;
+            }
+        }
+    } else if (warp == T3_NT / 32) {
+        // ================= vertical MMA thread =================
+        if (elect_one()) {
+            uint32_t g = 0, slot = 0, suse = 0, region = 0, ruse = 0;
+            for (uint32_t gg = 0; gg < total; gg++) {
+                const uint32_t bslot = gg & 1, kg = grp[4 * g + 1];
+                mbar_wait(smem_u32(&b_full[bslot]), (gg >> 1) & 1);
+                mbar_wait(smem_u32(&a_full[slot]), suse & 1);
+                if (ruse > 0) mbar_wait(smem_u32(&v_free[region]), (ruse - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                uint64_t da = umma_desc(sA_u + slot * kg_max * TC_M, 16, 1024, 2);
+                uint64_t db = umma_desc(sB_u + bslot * TC_N * kg_max, 128, (kg / 16) * 128);
+                const uint32_t d_tmem = tmem_base + v0 + region * TC_N;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(da),
+                             "l"(db), "r"(UMMA_IDESC)
+                             : "memory");
+                for (uint32_t ks = 1; ks < kg / 32; ks++) {
+                    da += (32 * TC_M) >> 4;
+                    db += (2 * 128) >> 4;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                                 "l"(da), "l"(db), "r"(UMMA_IDESC)
+                                 : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&v_full[region])) : "memory");
+                if (++slot == n_a) { slot = 0; suse++; }
+                if (++region == n_vr) { region = 0; ruse++; }
+                if (++g == n_groups) g = 0;
+            }
+        }
+    } else if (warp == T3_NT / 32 + 3) {
+        // ================= horizontal thread: weight tiles + MMAs into the rings =================
+        if (elect_one()) {
+            auto load_wh = [&](uint32_t ch) {
+                const uint32_t slot = n_wh == 2 ? (ch & 1) : 0u, bar = smem_u32(&wh_full[slot]);
+                const uint32_t bytes = __ldg(hrec + 8 * ch + 4) * 512u;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWh_u + slot * wh_bytes),
+                             "l"(tb + __ldg(hrec + 8 * ch)), "r"(bytes), "r"(bar)
+                             : "memory");
+            };
+            load_wh(0);
+            for (uint32_t ch = 0; ch < n_chunks; ch++) {
+                const uint32_t slot = n_wh == 2 ? (ch & 1) : 0u;
+                if (n_wh == 2 && ch + 1 < n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
+                    if (ch >= 1) mbar_wait(smem_u32(&wh_free[(ch + 1) & 1]), ((ch - 1) >> 1) & 1);
+                    load_wh(ch + 1);
+                }
+                mbar_wait(smem_u32(&wh_full[slot]), (n_wh == 2 ? (ch >> 1) : ch) & 1);
+                const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
+                const uint32_t n1 = min(n_total, ring_cols - w0);
+                const uint32_t b_hi0 = sWh_u + slot * wh_bytes, b_lo0 = b_hi0 + n_total * 256u;
+                for (uint32_t mt = 0; mt < n_mt; mt++) {
+                    mbar_wait(smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
+                    if (ch > 0) mbar_wait(smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = sT_u + mt * 32768u, a_lo = a_hi + t_bytes;
+                    // window piece: accumulator columns [col, col + n) += T . W[brow .. brow + n)
+                    auto piece = [&](uint32_t col, uint32_t n, uint32_t brow) {
+                        const uint32_t idesc = (1u << 4) | (1u << 15) | ((n >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
+                        const uint32_t d_tmem = tmem_base + mt * ring_cols + col;
+#pragma unroll
+                        for (int combo = 0; combo < 3; combo++) {
+                            uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);
+                            uint64_t db = umma_desc((combo == 2 ? b_lo0 : b_hi0) + (brow >> 3) * 2048u, 128, 2048);
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks++) {
+                                asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                                             "l"(da), "l"(db), "r"(idesc)
+                                             : "memory");
+                                da += 256 >> 4;
+                                db += 256 >> 4;
+                            }
+                        }
+                    };
+                    piece(w0, n1, 0);
+                    if (n1 < n_total) piece(0, n_total - n1, n1);
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&d2_full[mt])) : "memory");
+                    if (mt + 1 == n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&wh_free[slot])) : "memory");
+                }
+                if (n_wh == 1 && ch + 1 < n_chunks) {  // the only slot: its tiles were read once the chunk's MMAs have retired
+                    mbar_wait(smem_u32(&wh_free[0]), ch & 1);
+                    load_wh(ch + 1);
+                }
+            }
+        }
+    } else {
+        // ================= consumer warps =================
+        const float scale = it.scale, scale_hi = it.scale * 16384.0f;
+        const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        const uint32_t grp_rows = it.grp_rows;
+        const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows, h_epi = it.epi, h_fill = it.fill;
+        const uint32_t RP = ring_cols / C;
+        uint8_t *const h_row0 = it.dst + size_t(it.dst_y + it.band_r0) * it.dst_pitch + size_t(it.dst_x) * h_cout;  // first canvas byte of the band
+        const uint32_t my_stage = stage_u + warp * stage_warp + 16u;  // 16 bytes in front: "word -1" of row 0 is readable
+        const uint32_t stride4 = it.stage_stride * 4u;
+        // the rings start at zero: warp (q, half) clears its lanes of the tiles' columns, half of them each
+        for (uint32_t c0 = half * 16; c0 < v0; c0 += 32) tmem_st16_zero(tmem_base + ((q * 32u) << 16) + c0);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // drain duty of this warp: with two row tiles warp (q, half) owns tile `half`; with one tile the two warps of a
+        // lane quarter split the pixels a chunk finishes
+        const uint32_t my_mt = n_mt == 2 ? half : 0u;
+
+        // the pixels chunk `chunk` finished in row tile `mt`: ring -> registers -> rounded bytes -> staging -> canvas
+        auto drain_ring = [&](uint32_t chunk, uint32_t mt) {
+            mbar_wait(smem_u32(&d2_full[mt]), chunk & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t fin_first = __ldg(hrec + 8 * chunk + 1), n_fin = __ldg(hrec + 8 * chunk + 2), fin_slot = __ldg(hrec + 8 * chunk + 5);
+            uint32_t p0 = 0, p1 = n_fin;  // this warp's share of the finished pixels
+            if (mt != my_mt) { p1 = 0; }
+            else if (n_mt == 1) { const uint32_t hsplit = (n_fin + 1) / 2; p0 = half ? hsplit : 0u; p1 = half ? n_fin : hsplit; }
+            const uint32_t tbase = tmem_base + mt * ring_cols + ((q * 32u) << 16);
+            const uint32_t g = mt * 4 + q;
+            const bool row_ok = g < n_groups && lane < grp[4 * min(g, n_groups - 1) + 3];
+            const uint32_t sw = my_stage + lane * stride4;
+            __syncwarp();  // the previous chunk's words have left the staging tile
+            for (uint32_t pb = p0; pb < p1; pb += 4) {  // four pixels in flight per wait
+                uint32_t v[4][4];
+                const uint32_t np = min(4u, p1 - pb);
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++) {
+                    if (i < np) {
+                        uint32_t slot = fin_slot + pb + i;
+                        if (slot >= RP) slot -= RP;
+                        const uint32_t ta = tbase + slot * C;
+                        if constexpr (C == 4) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]) : "r"(ta));
+                        else if constexpr (C == 3) {
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[i][0]), "=r"(v[i][1]) : "r"(ta));
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[i][2]) : "r"(ta + 2));
+                        } else if constexpr (C == 2) asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[i][0]), "=r"(v[i][1]) : "r"(ta));
+                        else asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[i][0]) : "r"(ta));
+                    }
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const uint32_t z = 0;
+#pragma unroll
+                for (uint32_t i = 0; i < 4; i++) {
+                    if (i < np) {
+                        uint32_t slot = fin_slot + pb + i;
+                        if (slot >= RP) slot -= RP;
+                        const uint32_t ta = tbase + slot * C;
+                        if constexpr (C == 4) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(ta), "r"(z) : "memory");
+                        else if constexpr (C == 3) {
+                            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(ta), "r"(z) : "memory");
+                            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta + 2), "r"(z) : "memory");
+                        } else if constexpr (C == 2) asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(ta), "r"(z) : "memory");
+                        else asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta), "r"(z) : "memory");
+                        uint32_t u[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int c = 0; c < C; c++) u[c] = round_u8(__uint_as_float(v[i][c]) * (1.0f / TC2_WSCALE));
+                        const uint32_t sp = sw + (pb + i - p0) * h_cout;  // staged at its byte offset within this warp's segment
+                        if (h_epi == EPI_PLAIN) {
+                            if constexpr (C == 4) {
+                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp), "r"(u[0] | u[1] << 8 | u[2] << 16 | u[3] << 24) : "memory");
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < C; c++) sts8(sp + c, u[c]);
+                            }
+                        } else {
+                            uint32_t px = to_rgba_packed(u, C);
+                            if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
+                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp), "r"(px) : "memory");
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) t3_arrive(smem_u32(&d2_free[mt]));  // all eight warps arrive, whether they drained pixels of this tile or not
+            if (p1 <= p0) return;
+            __syncwarp();
+            // ---- write out: 32 rows x nb bytes at canvas byte (fin_first + p0) * c_out of each row
+            (void)row_ok;
+            const uint32_t nb = (p1 - p0) * h_cout;
+            uint8_t *const seg0 = h_row0 + size_t(mt * 4 + q) * grp_rows * h_pitch + size_t(fin_first + p0) * h_cout;  // row = g * grp_rows + lane
+            const uint32_t rows_here = (mt * 4 + q) < n_groups ? grp[4 * (mt * 4 + q) + 3] : 0u;
+            const uint32_t nw_max = (nb + 3 + 3) / 4;  // words a segment can span, whatever its alignment
+            uint32_t lpr = 1;                          // lanes per row: the power of two >= nw_max
+            while (lpr < nw_max) lpr <<= 1;
+            if (lpr > 32) lpr = 32;
+            const uint32_t rpi = 32 / lpr, k0 = lane & (lpr - 1);
+            for (uint32_t rr = lane / lpr; rr < rows_here; rr += rpi) {
+                uint8_t *a = seg0 + size_t(rr) * h_pitch;
+                const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
+                const uint32_t nw = (ph + nb + 3) / 4;
+                for (uint32_t k = k0; k < nw; k += lpr) {
+                    const uint32_t s0 = my_stage + rr * stride4 + 4u * k;
+                    const uint32_t wa = lds_u32(s0 - 4), wb = lds_u32(s0);
+                    const uint32_t val = ph ? __funnelshift_r(wa, wb, 8 * (4 - ph)) : wb;
+                    const int b0 = int(4 * k) - int(ph);
+                    uint8_t *gw = a + b0;
+                    const int va = max(-b0, 0), vb = min(int(nb) - b0, 4);
+                    if (va == 0 && vb == 4) {
+                        *reinterpret_cast<uint32_t *>(gw) = val;
+                    } else if (va == 2 && vb == 4) {
+                        *reinterpret_cast<uint16_t *>(gw + 2) = uint16_t(val >> 16);
+                    } else if (va == 0 && vb == 2) {
+                        *reinterpret_cast<uint16_t *>(gw) = uint16_t(val);
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 4; b++)
+                            if (b >= va && b < vb) gw[b] = uint8_t(val >> (8 * b));
+                    }
+                }
+            }
+        };
+
+        uint32_t gg = 0, region = 0, ruse = 0;
+        for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+            for (uint32_t g = 0; g < n_groups; g++, gg++) {
+                // the tile's rows are about to be overwritten: its horizontal MMAs of the previous chunk must have retired --
+                // which is also when the pixels they finished can be drained
+                if ((g & 3) == 0 && chunk > 0) drain_ring(chunk - 1, g >> 2);
+                mbar_wait(smem_u32(&v_full[region]), ruse & 1);  // the vertical MMAs of group gg have retired
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t taddr = tmem_base + v0 + region * TC_N + ((q * 32u) << 16) + half * 16;
+                uint32_t hi[16], mid[16], lo[16];
+                tmem_ld16(taddr, hi);
+                tmem_ld16(taddr + 32, mid);
+                tmem_ld16(taddr + 64, lo);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                if (lane == 0) t3_arrive(smem_u32(&v_free[region]));
+                if (++region == n_vr) { region = 0; ruse++; }
+                uint32_t ph[8], pl[8];
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {  // value = (hi 2^14 + mid 2^7 + lo) 2^-s, two rows per f32x2 op
+                    const float2 fh = make_float2(float(int(hi[e])), float(int(hi[e + 1])));
+                    const float2 fl = make_float2(float(int(mid[e]) * 128 + int(lo[e])), float(int(mid[e + 1]) * 128 + int(lo[e + 1])));
+                    float2 r = make_float2(0.f, 0.f);
+                    ffma2(r, fl, scale);
+                    ffma2(r, fh, scale_hi);
+                    const uint32_t h2 = pack_f16x2(r.x, r.y);
+                    const float2 back = unpack_f16x2(h2);
+                    ph[e / 2] = h2;
+                    pl[e / 2] = pack_f16x2(r.x - back.x, r.y - back.y);
+                }
+                const uint32_t t0 = sT_u + (g * 4 + half * 2) * 2048u + m * 16u;
+                sts128(t0, ph[0], ph[1], ph[2], ph[3]);
+                sts128(t0 + 2048, ph[4], ph[5], ph[6], ph[7]);
+                sts128(t0 + t_bytes, pl[0], pl[1], pl[2], pl[3]);
+                sts128(t0 + t_bytes + 2048, pl[4], pl[5], pl[6], pl[7]);
+                if ((g & 3) == 3 || g + 1 == n_groups) {  // the row tile is complete: hand it to the tensor core
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) t3_arrive(smem_u32(&t_ready[g >> 2]));
+                }
+            }
+        }
+        drain_ring(n_chunks - 1, 0);
+        if (n_mt > 1) drain_ring(n_chunks - 1, 1);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+template <int C>
+void launch_tc3_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b, const uint32_t *d_info,
+                        LaunchCtx &lc) {
+    auto kern = fused_resample_tc3_kernel<C>;
+    ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
+    lc.begin("fused_resample_tc3_kernel");
+    kern<<<n_items, T3_NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
+    lc.end();
+}
+
+}  // namespace
+
+int launch_fused_tc3(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
+                     const uint32_t *d_info, LaunchCtx &lc) {
+    if (n_items == 0) return 0;
+    switch (c) {
+    case 1: launch_tc3_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 2: launch_tc3_variant<2>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 3: launch_tc3_variant<3>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 4: launch_tc3_variant<4>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    }
+    return -1;
+}
+
+}  // namespace fanlin

@@ -414,7 +414,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (fused_a[i] == 1) by_variant[fused_variant(b->plans[i].a)].push_back(i);
             if (fused_a[i] == 2) {  // key: channels | 8 when the horizontal stage runs on the tensor cores too (another kernel)
                 const StagePlan &ta = a_pre[i].present ? a_pre[i] : b->plans[i].a;
-                tc_by_c[ta.c | (fused_tc_uses_hmma(ta, tcache.get(), &ftabs, &tctabs) ? 8u : 0u)].push_back(i);
+                tc_by_c[ta.c | (fused_tc_uses_hmma(ta, tcache.get(), &ftabs, &tctabs) ? 8u : 0u) |
+                        (fused_tc_uses_ring(ta, tcache.get(), &ftabs, &tctabs) ? 16u : 0u)].push_back(i);
             }
         }
         {  // orientation passes: the stored image turned (and its colour op applied) into scratch, in front of everything
