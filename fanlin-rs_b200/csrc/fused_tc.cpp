@@ -337,7 +337,9 @@ static bool build_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
     const uint32_t RP = (std::max(live_max, 1u) + al - 1) / al * al, RINGC = RP * C;
     if (RINGC > 256) return false;
     g.ring_cols = RINGC;
-    g.stage_stride = ((fin_max * s.c_out + 3) / 4 + 1) | 1u;  // words per staged row, odd: rows on distinct banks
+    // words per staged row, == 4 (mod 8): 16-byte aligned rows whose four-word stores (lanes = rows) fall on distinct banks
+    g.stage_stride = (fin_max * s.c_out + 3) / 4 + 1;
+    g.stage_stride += (4 + 8 - (g.stage_stride & 7)) & 7;
     std::vector<uint16_t> w_hi(t.weights.size()), w_lo(t.weights.size());
     for (uint32_t o = o0; o < o_end; o++) {
         const TapEntry &e = t.entries[o];

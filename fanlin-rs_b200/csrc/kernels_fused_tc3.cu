@@ -31,6 +31,12 @@ constexpr uint32_t T3_NA_MAX = 4;
 #define T3_PF_AHEAD 4
 #endif
 
+#ifdef T3_PROF
+#define T3W(acc, ...) do { const long long t0_ = clock64(); mbar_wait(__VA_ARGS__); (acc) += clock64() - t0_; } while (0)
+#else
+#define T3W(acc, ...) mbar_wait(__VA_ARGS__)
+#endif
+
 __device__ __forceinline__ void t3_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 template <int C>
@@ -54,7 +60,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
         for (uint32_t r = 0; r < 2; r++) {
             init(&t_ready[r], 8);
             init(&d2_full[r], 1);
-            init(&d2_free[r], 8);
+            init(&d2_free[r], it_s.n_groups > 4 ? 4 : 8);  // drained by the tile's own four warps when the band has two tiles, else by all eight
             init(&wh_full[r], 1);
             init(&wh_free[r], 1);
         }
@@ -138,11 +144,13 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
         // ================= vertical MMA thread =================
         if (elect_one()) {
             uint32_t g = 0, slot = 0, suse = 0, region = 0, ruse = 0;
+            long long w_b = 0, w_a = 0, w_r = 0;
+            const long long t_start = clock64();
             for (uint32_t gg = 0; gg < total; gg++) {
                 const uint32_t bslot = gg & 1, kg = grp[4 * g + 1];
-                mbar_wait(smem_u32(&b_full[bslot]), (gg >> 1) & 1);
-                mbar_wait(smem_u32(&a_full[slot]), suse & 1);
-                if (ruse > 0) mbar_wait(smem_u32(&v_free[region]), (ruse - 1) & 1);
+                T3W(w_b, smem_u32(&b_full[bslot]), (gg >> 1) & 1);
+                T3W(w_a, smem_u32(&a_full[slot]), suse & 1);
+                if (ruse > 0) T3W(w_r, smem_u32(&v_free[region]), (ruse - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint64_t da = umma_desc(sA_u + slot * kg_max * TC_M, 16, 1024, 2);
                 uint64_t db = umma_desc(sB_u + bslot * TC_N * kg_max, 128, (kg / 16) * 128);
@@ -162,6 +170,11 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                 if (++region == n_vr) { region = 0; ruse++; }
                 if (++g == n_groups) g = 0;
             }
+#ifdef T3_PROF
+            if (blockIdx.x == 300) printf("tc3 vertical MMA thread: total %lld clk, %u chunks x %u groups; waits: weights %lld, source rows %lld, TMEM region %lld\n", clock64() - t_start, n_chunks, n_groups, w_b, w_a, w_r);
+#else
+            (void)t_start; (void)w_b; (void)w_a; (void)w_r;
+#endif
         }
     } else if (warp == T3_NT / 32 + 3) {
         // ================= horizontal thread: weight tiles + MMAs into the rings =================
@@ -175,19 +188,21 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                              : "memory");
             };
             load_wh(0);
+            long long w_wh = 0, w_tr = 0, w_df = 0, w_wf = 0;
+            const long long t_start = clock64();
             for (uint32_t ch = 0; ch < n_chunks; ch++) {
                 const uint32_t slot = n_wh == 2 ? (ch & 1) : 0u;
                 if (n_wh == 2 && ch + 1 < n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
-                    if (ch >= 1) mbar_wait(smem_u32(&wh_free[(ch + 1) & 1]), ((ch - 1) >> 1) & 1);
+                    if (ch >= 1) T3W(w_wf, smem_u32(&wh_free[(ch + 1) & 1]), ((ch - 1) >> 1) & 1);
                     load_wh(ch + 1);
                 }
-                mbar_wait(smem_u32(&wh_full[slot]), (n_wh == 2 ? (ch >> 1) : ch) & 1);
+                T3W(w_wh, smem_u32(&wh_full[slot]), (n_wh == 2 ? (ch >> 1) : ch) & 1);
                 const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
                 const uint32_t n1 = min(n_total, ring_cols - w0);
                 const uint32_t b_hi0 = sWh_u + slot * wh_bytes, b_lo0 = b_hi0 + n_total * 256u;
                 for (uint32_t mt = 0; mt < n_mt; mt++) {
-                    mbar_wait(smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
-                    if (ch > 0) mbar_wait(smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
+                    T3W(w_tr, smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
+                    if (ch > 0) T3W(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = sT_u + mt * 32768u, a_lo = a_hi + t_bytes;
                     // window piece: accumulator columns [col, col + n) += T . W[brow .. brow + n)
@@ -214,10 +229,15 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     if (mt + 1 == n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&wh_free[slot])) : "memory");
                 }
                 if (n_wh == 1 && ch + 1 < n_chunks) {  // the only slot: its tiles were read once the chunk's MMAs have retired
-                    mbar_wait(smem_u32(&wh_free[0]), ch & 1);
+                    T3W(w_wf, smem_u32(&wh_free[0]), ch & 1);
                     load_wh(ch + 1);
                 }
             }
+#ifdef T3_PROF
+            if (blockIdx.x == 300) printf("tc3 horizontal thread: total %lld clk, n_wh %u, n_a %u, n_vr %u, ring %u; waits: weight tile landed %lld, T tile %lld, ring drained %lld, weight slot free %lld\n", clock64() - t_start, n_wh, n_a, n_vr, ring_cols, w_wh, w_tr, w_df, w_wf);
+#else
+            (void)t_start; (void)w_wh; (void)w_tr; (void)w_df; (void)w_wf;
+#endif
         }
     } else {
         // ================= consumer warps =================
@@ -235,106 +255,158 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
         // drain duty of this warp: with two row tiles warp (q, half) owns tile `half`; with one tile the two warps of a
         // lane quarter split the pixels a chunk finishes
         const uint32_t my_mt = n_mt == 2 ? half : 0u;
+        const bool words_ok = h_cout == 4 && ((reinterpret_cast<uintptr_t>(h_row0) | h_pitch) & 3) == 0;  // every row segment starts on a word
 
         // the pixels chunk `chunk` finished in row tile `mt`: ring -> registers -> rounded bytes -> staging -> canvas
+        long long w_v = 0, w_d2 = 0, t_dr = 0, t_v = 0;
+        const long long t_start = clock64();
         auto drain_ring = [&](uint32_t chunk, uint32_t mt) {
-            mbar_wait(smem_u32(&d2_full[mt]), chunk & 1);
+            T3W(w_d2, smem_u32(&d2_full[mt]), chunk & 1);  // every warp: the tile's T rows may be overwritten from here on
+            if (n_mt == 2 && mt != my_mt) return;          // ... but only the tile's own four warps drain it (and arrive)
+#ifdef T3_PROF
+            const long long td0 = clock64();
+            struct Acc { long long &a; long long t0; __device__ ~Acc() { a += clock64() - t0; } } acc_{t_dr, td0};
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t fin_first = __ldg(hrec + 8 * chunk + 1), n_fin = __ldg(hrec + 8 * chunk + 2), fin_slot = __ldg(hrec + 8 * chunk + 5);
             uint32_t p0 = 0, p1 = n_fin;  // this warp's share of the finished pixels
-            if (mt != my_mt) { p1 = 0; }
-            else if (n_mt == 1) { const uint32_t hsplit = (n_fin + 1) / 2; p0 = half ? hsplit : 0u; p1 = half ? n_fin : hsplit; }
+            if (n_mt == 1) { const uint32_t hsplit = (n_fin + 1) / 2; p0 = half ? hsplit : 0u; p1 = half ? n_fin : hsplit; }
             const uint32_t tbase = tmem_base + mt * ring_cols + ((q * 32u) << 16);
-            const uint32_t g = mt * 4 + q;
-            const bool row_ok = g < n_groups && lane < grp[4 * min(g, n_groups - 1) + 3];
             const uint32_t sw = my_stage + lane * stride4;
             __syncwarp();  // the previous chunk's words have left the staging tile
-            for (uint32_t pb = p0; pb < p1; pb += 4) {  // four pixels in flight per wait
-                uint32_t v[4][4];
-                const uint32_t np = min(4u, p1 - pb);
+            // Batches of PB = 16 / C pixels: ONE tcgen05.ld of 16 columns (what it reads past the batch is ignored) and one
+            // to four stores that zero exactly the batch's columns, a batch ending where the ring wraps.  Per-pixel loads and stores cost an issue slot each next to a tensor core
+            // that keeps the shared-memory and TMEM ports busy (measured: 6.4 k clk per chunk for 15 RGBA pixels).
+            constexpr uint32_t PB = 16 / C;
+            uint32_t slot = fin_slot + p0;
+            if (slot >= RP) slot -= RP;
+            for (uint32_t pb = p0; pb < p1;) {
+                const uint32_t np = min(min(PB, p1 - pb), RP - slot);
+                const uint32_t ta = tbase + slot * C;
+                uint32_t v[16];
+                tmem_ld16(ta, v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint32_t px[PB];
 #pragma unroll
-                for (uint32_t i = 0; i < 4; i++) {
-                    if (i < np) {
-                        uint32_t slot = fin_slot + pb + i;
-                        if (slot >= RP) slot -= RP;
-                        const uint32_t ta = tbase + slot * C;
-                        if constexpr (C == 4) asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[i][0]), "=r"(v[i][1]), "=r"(v[i][2]), "=r"(v[i][3]) : "r"(ta));
-                        else if constexpr (C == 3) {
-                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[i][0]), "=r"(v[i][1]) : "r"(ta));
-                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[i][2]) : "r"(ta + 2));
-                        } else if constexpr (C == 2) asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[i][0]), "=r"(v[i][1]) : "r"(ta));
-                        else asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[i][0]) : "r"(ta));
+                for (uint32_t i = 0; i < PB; i++) {
+                    uint32_t u[4] = {0, 0, 0, 0};
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        u[c] = round_u8(__uint_as_float(v[i * C + c]) * (1.0f / TC2_WSCALE));
+                    }
+                    if (h_epi == EPI_PLAIN) {
+                        px[i] = u[0] | u[1] << 8 | u[2] << 16 | u[3] << 24;  // the pixel's c bytes, low byte first
+                    } else {
+                        px[i] = to_rgba_packed(u, C);
+                        if (h_epi == EPI_BLEND_FILL) px[i] = blend_rgba(h_fill, px[i]);
                     }
                 }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const uint32_t z = 0;
-#pragma unroll
-                for (uint32_t i = 0; i < 4; i++) {
-                    if (i < np) {
-                        uint32_t slot = fin_slot + pb + i;
-                        if (slot >= RP) slot -= RP;
-                        const uint32_t ta = tbase + slot * C;
-                        if constexpr (C == 4) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(ta), "r"(z) : "memory");
-                        else if constexpr (C == 3) {
-                            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(ta), "r"(z) : "memory");
-                            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta + 2), "r"(z) : "memory");
-                        } else if constexpr (C == 2) asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(ta), "r"(z) : "memory");
-                        else asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta), "r"(z) : "memory");
-                        uint32_t u[4] = {0, 0, 0, 0};
-#pragma unroll
-                        for (int c = 0; c < C; c++) u[c] = round_u8(__uint_as_float(v[i][c]) * (1.0f / TC2_WSCALE));
-                        const uint32_t sp = sw + (pb + i - p0) * h_cout;  // staged at its byte offset within this warp's segment
-                        if (h_epi == EPI_PLAIN) {
-                            if constexpr (C == 4) {
-                                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp), "r"(u[0] | u[1] << 8 | u[2] << 16 | u[3] << 24) : "memory");
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < C; c++) sts8(sp + c, u[c]);
-                            }
-                        } else {
-                            uint32_t px = to_rgba_packed(u, C);
-                            if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
-                            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp), "r"(px) : "memory");
+                // zero exactly the columns of the np pixels read: the neighbouring columns belong to live outputs, or to the
+                // pixels the other warp of this lane quarter drains
+                {
+                    const uint32_t z = 0;
+                    if (np == PB) {
+                        if constexpr (PB * C == 16) {
+                            tmem_st16_zero(ta);
+                        } else {  // C == 3: 15 columns = 8 + 4 + 2 + 1
+                            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(ta), "r"(z) : "memory");
+                            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(ta + 8), "r"(z) : "memory");
+                            asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(ta + 12), "r"(z) : "memory");
+                            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(ta + 14), "r"(z) : "memory");
+                        }
+                    } else {
+                        for (uint32_t i = 0; i < np; i++) {
+                            const uint32_t tp = ta + i * C;
+                            if constexpr (C == 4) asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%1,%1,%1};" ::"r"(tp), "r"(z) : "memory");
+                            else if constexpr (C == 3) {
+                                asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(tp), "r"(z) : "memory");
+                                asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tp + 2), "r"(z) : "memory");
+                            } else if constexpr (C == 2) asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%1};" ::"r"(tp), "r"(z) : "memory");
+                            else asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tp), "r"(z) : "memory");
                         }
                     }
                 }
+                const uint32_t sp = sw + (pb - p0) * h_cout;  // staged at its byte offset within this warp's segment
+                if (h_cout == 4) {
+                    if constexpr (PB == 4) {
+                        if (np == 4 && ((pb - p0) & 3) == 0) {
+                            sts128(sp, px[0], px[1], px[2], px[3]);
+                        } else {
+#pragma unroll
+                            for (uint32_t i = 0; i < PB; i++)
+                                if (i < np) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp + 4 * i), "r"(px[i]) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (uint32_t i = 0; i < PB; i++)
+                            if (i < np) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp + 4 * i), "r"(px[i]) : "memory");
+                    }
+                } else {  // plain output of 1..3 channels: byte by byte
+#pragma unroll
+                    for (uint32_t i = 0; i < PB; i++)
+                        if (i < np) {
+#pragma unroll
+                            for (int c = 0; c < C; c++) sts8(sp + i * C + c, px[i] >> (8 * c));
+                        }
+                }
+                pb += np;
+                slot += np;
+                if (slot >= RP) slot -= RP;
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) t3_arrive(smem_u32(&d2_free[mt]));  // all eight warps arrive, whether they drained pixels of this tile or not
+            if (lane == 0) t3_arrive(smem_u32(&d2_free[mt]));
             if (p1 <= p0) return;
             __syncwarp();
-            // ---- write out: 32 rows x nb bytes at canvas byte (fin_first + p0) * c_out of each row
-            (void)row_ok;
+            // ---- write out: this group's rows x nb bytes at canvas byte (fin_first + p0) * c_out of each row
             const uint32_t nb = (p1 - p0) * h_cout;
-            uint8_t *const seg0 = h_row0 + size_t(mt * 4 + q) * grp_rows * h_pitch + size_t(fin_first + p0) * h_cout;  // row = g * grp_rows + lane
-            const uint32_t rows_here = (mt * 4 + q) < n_groups ? grp[4 * (mt * 4 + q) + 3] : 0u;
-            const uint32_t nw_max = (nb + 3 + 3) / 4;  // words a segment can span, whatever its alignment
-            uint32_t lpr = 1;                          // lanes per row: the power of two >= nw_max
-            while (lpr < nw_max) lpr <<= 1;
-            if (lpr > 32) lpr = 32;
-            const uint32_t rpi = 32 / lpr, k0 = lane & (lpr - 1);
-            for (uint32_t rr = lane / lpr; rr < rows_here; rr += rpi) {
-                uint8_t *a = seg0 + size_t(rr) * h_pitch;
-                const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
-                const uint32_t nw = (ph + nb + 3) / 4;
+            const uint32_t gq = mt * 4 + q;
+            uint8_t *const seg0 = h_row0 + size_t(gq) * grp_rows * h_pitch + size_t(fin_first + p0) * h_cout;  // row = group * grp_rows + lane
+            const uint32_t rows_here = gq < n_groups ? grp[4 * gq + 3] : 0u;
+            if (words_ok) {
+                // every row segment starts on a word: nw words per row, lpr lanes per row (a power of two), 32 / lpr rows per store,
+                // four stores in flight
+                const uint32_t nw = nb >> 2;
+                uint32_t sh = 0;
+                while ((1u << sh) < nw && sh < 5) sh++;
+                const uint32_t lpr = 1u << sh, rpi = 32u >> sh, k0 = lane & (lpr - 1), r0 = lane >> sh;
                 for (uint32_t k = k0; k < nw; k += lpr) {
-                    const uint32_t s0 = my_stage + rr * stride4 + 4u * k;
-                    const uint32_t wa = lds_u32(s0 - 4), wb = lds_u32(s0);
-                    const uint32_t val = ph ? __funnelshift_r(wa, wb, 8 * (4 - ph)) : wb;
-                    const int b0 = int(4 * k) - int(ph);
-                    uint8_t *gw = a + b0;
-                    const int va = max(-b0, 0), vb = min(int(nb) - b0, 4);
-                    if (va == 0 && vb == 4) {
-                        *reinterpret_cast<uint32_t *>(gw) = val;
-                    } else if (va == 2 && vb == 4) {
-                        *reinterpret_cast<uint16_t *>(gw + 2) = uint16_t(val >> 16);
-                    } else if (va == 0 && vb == 2) {
-                        *reinterpret_cast<uint16_t *>(gw) = uint16_t(val);
-                    } else {
+                    for (uint32_t rb = r0; rb < rows_here; rb += 4 * rpi) {
+                        uint32_t val[4];
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            if (b >= va && b < vb) gw[b] = uint8_t(val >> (8 * b));
+                        for (uint32_t i = 0; i < 4; i++) val[i] = lds_u32(my_stage + min(rb + i * rpi, 31u) * stride4 + 4u * k);
+#pragma unroll
+                        for (uint32_t i = 0; i < 4; i++)
+                            if (rb + i * rpi < rows_here) *reinterpret_cast<uint32_t *>(seg0 + size_t(rb + i * rpi) * h_pitch + 4u * k) = val[i];
+                    }
+                }
+            } else {
+                const uint32_t nw_max = (nb + 3 + 3) / 4;  // words a segment can span, whatever its alignment
+                uint32_t sh = 0;
+                while ((1u << sh) < nw_max && sh < 5) sh++;
+                const uint32_t lpr = 1u << sh, rpi = 32u >> sh, k0 = lane & (lpr - 1);
+                for (uint32_t rr = lane >> sh; rr < rows_here; rr += rpi) {
+                    uint8_t *a = seg0 + size_t(rr) * h_pitch;
+                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
+                    const uint32_t nw = (ph + nb + 3) / 4;
+                    for (uint32_t k = k0; k < nw; k += lpr) {
+                        const uint32_t s0 = my_stage + rr * stride4 + 4u * k;
+                        const uint32_t wa = lds_u32(s0 - 4), wb = lds_u32(s0);
+                        const uint32_t val = ph ? __funnelshift_r(wa, wb, 8 * (4 - ph)) : wb;
+                        const int b0 = int(4 * k) - int(ph);
+                        uint8_t *gw = a + b0;
+                        const int va = max(-b0, 0), vb = min(int(nb) - b0, 4);
+                        if (va == 0 && vb == 4) {
+                            *reinterpret_cast<uint32_t *>(gw) = val;
+                        } else if (va == 2 && vb == 4) {
+                            *reinterpret_cast<uint16_t *>(gw + 2) = uint16_t(val >> 16);
+                        } else if (va == 0 && vb == 2) {
+                            *reinterpret_cast<uint16_t *>(gw) = uint16_t(val);
+                        } else {
+#pragma unroll
+                            for (int bb = 0; bb < 4; bb++)
+                                if (bb >= va && bb < vb) gw[bb] = uint8_t(val >> (8 * bb));
+                        }
                     }
                 }
             }
@@ -346,7 +418,10 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                 // the tile's rows are about to be overwritten: its horizontal MMAs of the previous chunk must have retired --
                 // which is also when the pixels they finished can be drained
                 if ((g & 3) == 0 && chunk > 0) drain_ring(chunk - 1, g >> 2);
-                mbar_wait(smem_u32(&v_full[region]), ruse & 1);  // the vertical MMAs of group gg have retired
+                T3W(w_v, smem_u32(&v_full[region]), ruse & 1);  // the vertical MMAs of group gg have retired
+#ifdef T3_PROF
+                const long long tv0 = clock64();
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t taddr = tmem_base + v0 + region * TC_N + ((q * 32u) << 16) + half * 16;
                 uint32_t hi[16], mid[16], lo[16];
@@ -380,10 +455,19 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     __syncwarp();
                     if (lane == 0) t3_arrive(smem_u32(&t_ready[g >> 2]));
                 }
+#ifdef T3_PROF
+                t_v += clock64() - tv0;
+#endif
             }
         }
         drain_ring(n_chunks - 1, 0);
         if (n_mt > 1) drain_ring(n_chunks - 1, 1);
+#ifdef T3_PROF
+        if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 5))
+            printf("tc3 consumer warp %u: total %lld clk; waits: vertical results %lld, ring ready %lld; vertical drain %lld, ring drain + write-out %lld\n", warp, clock64() - t_start, w_v, w_d2, t_v, t_dr);
+#else
+        (void)t_start; (void)w_v; (void)w_d2; (void)t_dr; (void)t_v;
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
