@@ -63,7 +63,6 @@ struct FusedTcItem {
 // Tensor-core horizontal stage: the chunk's 128 tile columns (K) are contracted with an f16 weight
 // tile [N2][128] into N2 = ring positions x channels accumulator columns (ring of N2 / c outputs).
 inline uint32_t fused_tc2_n(uint32_t c) { return c == 3 ? 48u : 64u; }
-constexpr uint32_t TC2_MIN_JOBS = 256; // batches below this keep the CUDA-core horizontal stage (no per-chunk weight tiles to build)
 constexpr float TC2_WSCALE = 16.0f;  // horizontal weights are stored x16: their low halves stay f16 normals
 size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t band_rows, uint32_t out_stride);
 size_t fused_tc3_smem_bytes(uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t wh_bytes, uint32_t stage_stride);

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
             asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
             for (uint32_t ch = 0; ch < n_chunks; ch++) {
                 const uint32_t slot = ch & 1, bar = smem_u32(&a_full[slot]);
-                if (ch >= 2) mbar_wait(smem_u32(&a_free[slot]), ((ch >> 1) - 1) & 1);  // the vertical MMAs of chunk ch - 2 have retired
+                if (ch >= 2) mbar_wait_wd(smem_u32(&a_free[slot]), ((ch >> 1) - 1) & 1);  // the vertical MMAs of chunk ch - 2 have retired
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(box_bytes) : "memory");
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(sA_u + slot * box_bytes),
                              "l"(tmap), "r"(bar), "r"(TC_M * ch), "r"(it.box_row0)
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
             uint32_t g = 0;
             for (uint32_t gg = 0; gg < total; gg++) {
                 const uint32_t slot = gg & 1, bar = smem_u32(&b_full[slot]);
-                if (gg >= 2) mbar_wait(smem_u32(&v_full[(gg - 2) % BT_NRV]), ((gg - 2) / BT_NRV) & 1);  // the slot's tile was read by the MMAs of group gg - 2
+                if (gg >= 2) mbar_wait_wd(smem_u32(&v_full[(gg - 2) % BT_NRV]), ((gg - 2) / BT_NRV) & 1);  // the slot's tile was read by the MMAs of group gg - 2
                 const uint32_t kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
                 if (have[slot] == b_off) {
                     mbar_arrive(bar);  // the tile is there already: just complete the phase the MMA thread waits for
@@ -127,9 +127,9 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
             for (uint32_t gg = 0; gg < total; gg++) {
                 const uint32_t region = gg % BT_NRV, ruse = gg / BT_NRV, bslot = gg & 1, aslot = ch & 1;
                 const uint32_t a_off = grp[4 * g], kg = grp[4 * g + 1];
-                mbar_wait(smem_u32(&b_full[bslot]), (gg >> 1) & 1);
-                if (g == 0) mbar_wait(smem_u32(&a_full[aslot]), (ch >> 1) & 1);
-                if (ruse > 0) mbar_wait(smem_u32(&v_free[region]), (ruse - 1) & 1);
+                mbar_wait_wd(smem_u32(&b_full[bslot]), (gg >> 1) & 1);
+                if (g == 0) mbar_wait_wd(smem_u32(&a_full[aslot]), (ch >> 1) & 1);
+                if (ruse > 0) mbar_wait_wd(smem_u32(&v_free[region]), (ruse - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint64_t da = umma_desc(sA_u + aslot * box_bytes + a_off * TC_M, 16, 1024, 2);  // the group's window: a_off rows into the box
                 uint64_t db = umma_desc(sB_u + bslot * TC_N * kg_max, 128, (kg / 16) * 128);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWh_u), "l"(tb + it.hw_off),
                              "r"(n_win * 128u), "r"(bar)
                              : "memory");
-                mbar_wait(bar, 0);
+                mbar_wait_wd(bar, 0);
             }
             const uint32_t b_hi0 = sWh_u, b_lo0 = sWh_u + n_win * 64u;
             // one piece of a window: accumulator columns [col, col + n) += T[:, 32 j .. + 32) . W[brow .. brow + n)
@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
             uint32_t jj = 0;
             for (uint32_t ch = 0; ch < n_chunks; ch++) {
                 const uint32_t buf = ch & 1;
-                mbar_wait(smem_u32(&t_ready[buf]), (ch >> 1) & 1);  // the consumers have written the chunk's T
+                mbar_wait_wd(smem_u32(&t_ready[buf]), (ch >> 1) & 1);  // the consumers have written the chunk's T
                 for (uint32_t j = 0; j < 4; j++, jj++) {
-                    if (jj >= slack) mbar_wait(smem_u32(&d2_free[(jj - slack) & 3]), ((jj - slack) >> 2) & 1);  // the columns this window re-uses are drained and zero
+                    if (jj >= slack) mbar_wait_wd(smem_u32(&d2_free[(jj - slack) & 3]), ((jj - slack) >> 2) & 1);  // the columns this window re-uses are drained and zero
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = sT_u + buf * 2 * BT_T_BYTES + j * 512u;  // 32 columns = four core matrices along K
                     const uint32_t s = (32u * jj + 4096u - r_pad) & 255u;

@@ -85,7 +85,7 @@ __device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMa
             asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(p.x0 + TC_M * pchunk), "r"(p.grp[4 * pg]) : "memory");
             if (++pg == p.n_groups) { pg = 0; pchunk++; }
         }
-        if (gg >= p.n_a) mbar_wait(p.mbar + 8 * ((gg - p.n_a) % NRT), ((gg - p.n_a) / NRT) & 1);  // the slot was read by the MMAs of group gg - n_a
+        if (gg >= p.n_a) mbar_wait_wd(p.mbar + 8 * ((gg - p.n_a) % NRT), ((gg - p.n_a) / NRT) & 1);  // the slot was read by the MMAs of group gg - n_a
         const uint32_t bar = p.a_full + 8 * slot;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.kg_max * TC_M) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
@@ -103,7 +103,7 @@ __device__ __forceinline__ void tc_weight_role(const TcPipe &p, const uint8_t *t
     const uint32_t total = p.n_chunks * p.n_groups;
     uint32_t g = 0;
     for (uint32_t gg = 0; gg < total; gg++) {
-        if (gg >= NB) mbar_wait(p.mbar + 8 * ((gg - NB) % NRT), ((gg - NB) / NRT) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
+        if (gg >= NB) mbar_wait_wd(p.mbar + 8 * ((gg - NB) % NRT), ((gg - NB) / NRT) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
         const uint32_t kg = p.grp[4 * g + 1], b_off = p.grp[4 * g + 2];
         const uint32_t bar = p.b_full + 8 * (gg % NB);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
@@ -122,9 +122,9 @@ __device__ __forceinline__ void tc_mma_role(const TcPipe &p) {
     for (uint32_t gg = 0; gg < total; gg++) {
         const uint32_t region = gg % NR, ruse = gg / NR, bslot = gg % NB;
         const uint32_t kg = p.grp[4 * g + 1];
-        mbar_wait(p.b_full + 8 * bslot, (gg / NB) & 1);                        // the weight tile has landed
-        mbar_wait(p.a_full + 8 * slot, suse & 1);                              // the source rows have landed
-        if (ruse > 0) mbar_wait(p.tmem_free + 8 * region, (ruse - 1) & 1);     // consumers drained the region's previous contents
+        mbar_wait_wd(p.b_full + 8 * bslot, (gg / NB) & 1);                        // the weight tile has landed
+        mbar_wait_wd(p.a_full + 8 * slot, suse & 1);                              // the source rows have landed
+        if (ruse > 0) mbar_wait_wd(p.tmem_free + 8 * region, (ruse - 1) & 1);     // consumers drained the region's previous contents
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // descriptors advance by a constant per K step: 32 rows x 128 B of A, 2 core matrices of B
         uint64_t da = umma_desc(p.sA_u + slot * p.kg_max * TC_M, 16, 1024, 2);  // SBO = 8-row atom stride
@@ -568,13 +568,13 @@ __device__ __forceinline__ void tc2_h_role(const TcPipe &p, const Tc2Pipe &h, co
     for (uint32_t ch = 0; ch < p.n_chunks; ch++) {
         const uint32_t slot = ch % h.n_wh;
         if (h.n_wh == 2 && ch + 1 < p.n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
-            if (ch >= 1) PW(w_wf, h.wh_free + 8 * ((ch + 1) & 1), ((ch - 1) >> 1) & 1);
+            if (ch >= 1) PWR(w_wf, h.wh_free + 8 * ((ch + 1) & 1), ((ch - 1) >> 1) & 1);
             load_wh(ch + 1);
         }
-        PW(w_wh, h.wh_full + 8 * slot, (ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
+        PWR(w_wh, h.wh_full + 8 * slot, (ch / h.n_wh) & 1);  // the chunk's weight tiles have landed
         for (uint32_t mt = 0; mt < h.n_mt; mt++) {
-            PW(w_tr, h.t_ready + 8 * mt, ch & 1);                    // the consumers have written the tile's rows
-            if (ch > 0) PW(w_df, h.d2_free + 8 * mt, (ch - 1) & 1);  // ... and read the previous chunk's D2
+            PWR(w_tr, h.t_ready + 8 * mt, ch & 1);                    // the consumers have written the tile's rows
+            if (ch > 0) PWR(w_df, h.d2_free + 8 * mt, (ch - 1) & 1);  // ... and read the previous chunk's D2
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef TC2_PROF
             const long long ti0 = clock64();
@@ -607,7 +607,7 @@ __device__ __forceinline__ void tc2_h_role(const TcPipe &p, const Tc2Pipe &h, co
 #endif
         }
         if (h.n_wh == 1 && ch + 1 < p.n_chunks) {  // the only slot: its tiles were read once the chunk's MMAs have retired
-            PW(w_wf, h.wh_free, ch & 1);
+            PWR(w_wf, h.wh_free, ch & 1);
             load_wh(ch + 1);
         }
     }
@@ -629,9 +629,9 @@ __device__ __forceinline__ void tc2_v_role(const TcPipe &p) {
     for (uint32_t gg = 0; gg < total; gg++) {
         const uint32_t region = gg % NR2, ruse = gg / NR2, bslot = gg % NB;
         const uint32_t kg = p.grp[4 * g + 1];
-        PW(w_b, p.b_full + 8 * bslot, (gg / NB) & 1);
-        PW(w_a, p.a_full + 8 * slot, suse & 1);
-        if (ruse > 0) PW(w_tf, p.tmem_free + 8 * region, (ruse - 1) & 1);
+        PWR(w_b, p.b_full + 8 * bslot, (gg / NB) & 1);
+        PWR(w_a, p.a_full + 8 * slot, suse & 1);
+        if (ruse > 0) PWR(w_tf, p.tmem_free + 8 * region, (ruse - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #ifdef TC2_PROF
         const long long tv0 = clock64();

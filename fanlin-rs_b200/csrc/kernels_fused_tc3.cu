@@ -33,8 +33,10 @@ constexpr uint32_t T3_NA_MAX = 4;
 
 #ifdef T3_PROF
 #define T3W(acc, ...) do { const long long t0_ = clock64(); mbar_wait(__VA_ARGS__); (acc) += clock64() - t0_; } while (0)
+#define T3WR(acc, ...) do { const long long t0_ = clock64(); mbar_wait_wd(__VA_ARGS__); (acc) += clock64() - t0_; } while (0)
 #else
 #define T3W(acc, ...) mbar_wait(__VA_ARGS__)
+#define T3WR(acc, ...) mbar_wait_wd(__VA_ARGS__)  // role threads: with the watchdog
 #endif
 
 __device__ __forceinline__ void t3_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     if (++pg == n_groups) { pg = 0; pchunk++; }
                 }
                 if (gg >= n_a) {
-                    mbar_wait(smem_u32(&v_full[wreg]), wuse & 1);
+                    mbar_wait_wd(smem_u32(&v_full[wreg]), wuse & 1);
                     if (++wreg == n_vr) { wreg = 0; wuse++; }
                 }
                 const uint32_t bar = smem_u32(&a_full[slot]);
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
             uint32_t g = 0, wreg = 0, wuse = 0;
             for (uint32_t gg = 0; gg < total; gg++) {
                 if (gg >= T3_NB) {
-                    mbar_wait(smem_u32(&v_full[wreg]), wuse & 1);  // the slot's previous tile was read by the MMAs of group gg - 2
+                    mbar_wait_wd(smem_u32(&v_full[wreg]), wuse & 1);  // the slot's previous tile was read by the MMAs of group gg - 2
                     if (++wreg == n_vr) { wreg = 0; wuse++; }
                 }
                 const uint32_t kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
@@ -148,9 +150,9 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
             const long long t_start = clock64();
             for (uint32_t gg = 0; gg < total; gg++) {
                 const uint32_t bslot = gg & 1, kg = grp[4 * g + 1];
-                T3W(w_b, smem_u32(&b_full[bslot]), (gg >> 1) & 1);
-                T3W(w_a, smem_u32(&a_full[slot]), suse & 1);
-                if (ruse > 0) T3W(w_r, smem_u32(&v_free[region]), (ruse - 1) & 1);
+                T3WR(w_b, smem_u32(&b_full[bslot]), (gg >> 1) & 1);
+                T3WR(w_a, smem_u32(&a_full[slot]), suse & 1);
+                if (ruse > 0) T3WR(w_r, smem_u32(&v_free[region]), (ruse - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 uint64_t da = umma_desc(sA_u + slot * kg_max * TC_M, 16, 1024, 2);
                 uint64_t db = umma_desc(sB_u + bslot * TC_N * kg_max, 128, (kg / 16) * 128);
@@ -193,16 +195,16 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
             for (uint32_t ch = 0; ch < n_chunks; ch++) {
                 const uint32_t slot = n_wh == 2 ? (ch & 1) : 0u;
                 if (n_wh == 2 && ch + 1 < n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
-                    if (ch >= 1) T3W(w_wf, smem_u32(&wh_free[(ch + 1) & 1]), ((ch - 1) >> 1) & 1);
+                    if (ch >= 1) T3WR(w_wf, smem_u32(&wh_free[(ch + 1) & 1]), ((ch - 1) >> 1) & 1);
                     load_wh(ch + 1);
                 }
-                T3W(w_wh, smem_u32(&wh_full[slot]), (n_wh == 2 ? (ch >> 1) : ch) & 1);
+                T3WR(w_wh, smem_u32(&wh_full[slot]), (n_wh == 2 ? (ch >> 1) : ch) & 1);
                 const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
                 const uint32_t n1 = min(n_total, ring_cols - w0);
                 const uint32_t b_hi0 = sWh_u + slot * wh_bytes, b_lo0 = b_hi0 + n_total * 256u;
                 for (uint32_t mt = 0; mt < n_mt; mt++) {
-                    T3W(w_tr, smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
-                    if (ch > 0) T3W(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
+                    T3WR(w_tr, smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
+                    if (ch > 0) T3WR(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = sT_u + mt * 32768u, a_lo = a_hi + t_bytes;
                     // window piece: accumulator columns [col, col + n) += T . W[brow .. brow + n)
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     if (mt + 1 == n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&wh_free[slot])) : "memory");
                 }
                 if (n_wh == 1 && ch + 1 < n_chunks) {  // the only slot: its tiles were read once the chunk's MMAs have retired
-                    T3W(w_wf, smem_u32(&wh_free[0]), ch & 1);
+                    T3WR(w_wf, smem_u32(&wh_free[0]), ch & 1);
                     load_wh(ch + 1);
                 }
             }

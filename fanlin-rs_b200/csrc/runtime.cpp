@@ -89,9 +89,62 @@ bool PinnedPool::owns(const void *p, size_t bytes) {
     return q >= base && q + bytes <= base + it->second;
 }
 
+TableBuf::~TableBuf() {
+    if (!d_w && !d_info && !d_b) return;
+    cudaSetDevice(ordinal);
+    cudaFree(d_w);
+    cudaFree(d_info);
+    cudaFree(d_b);
+}
+
+TableGen::TableGen(bool allow_hmma) : fcache(fused_cache_new()), tcache(fused_tc_cache_new(allow_hmma)), btcache(blur_tc_cache_new()) {}
+TableGen::~TableGen() {
+    fused_cache_free(fcache);
+    fused_tc_cache_free(tcache);
+    blur_tc_cache_free(btcache);
+    if (uploaded) cudaEventDestroy(uploaded);
+}
+
 }  // namespace fanlin
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Brings the device copy of a generation's arenas up to date on `st` (under dev->tab_mu): grows the buffers when needed,
+// copies what was appended since the last call and orders `st` behind every earlier upload, whatever stream made it.
+static int upload_tables(fanlin_ctx *ctx, DeviceState *dev, TableGen *g, cudaStream_t st) {
+    const size_t nw = g->ftabs.w.size() * 4, ni = g->ftabs.info.size() * 4, nb = g->tctabs.b.size();
+    if (!g->uploaded && cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming) != cudaSuccess) { set_error("fanlin: cudaEventCreate failed"); return FANLIN_ECUDA; }
+    if (!g->buf || nw > g->buf->cap_w || ni > g->buf->cap_info || nb > g->buf->cap_b) {
+        auto grow = [](size_t need, size_t floor_) { size_t c = floor_; while (c < need) c <<= 1; return c; };
+        std::shared_ptr<TableBuf> nbuf(new TableBuf());
+        nbuf->ordinal = dev->ordinal;
+        nbuf->cap_w = grow(nw, size_t(4) << 20); nbuf->cap_info = grow(ni, size_t(4) << 20); nbuf->cap_b = grow(nb, size_t(32) << 20);
+        if (cudaMalloc(&nbuf->d_w, nbuf->cap_w) != cudaSuccess || cudaMalloc(&nbuf->d_info, nbuf->cap_info) != cudaSuccess ||
+            cudaMalloc(&nbuf->d_b, nbuf->cap_b) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("fanlin: device allocation for the filter tables failed");
+            return FANLIN_ENOMEM;
+        }
+        g->buf = nbuf;  // the old buffers live on in the batches that launch from them
+        g->up_w = g->up_info = g->up_b = 0;
+    } else if (cudaStreamWaitEvent(st, g->uploaded, 0) != cudaSuccess) {
+        set_error("fanlin: cudaStreamWaitEvent failed");
+        return FANLIN_ECUDA;
+    }
+    cudaError_t e = cudaSuccess;
+    if (g->ftabs.w.size() > g->up_w)
+        e = cudaMemcpyAsync(static_cast<float *>(g->buf->d_w) + g->up_w, g->ftabs.w.data() + g->up_w, (g->ftabs.w.size() - g->up_w) * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && g->ftabs.info.size() > g->up_info)
+        e = cudaMemcpyAsync(static_cast<uint32_t *>(g->buf->d_info) + g->up_info, g->ftabs.info.data() + g->up_info, (g->ftabs.info.size() - g->up_info) * 4,
+                            cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && g->tctabs.b.size() > g->up_b)
+        e = cudaMemcpyAsync(static_cast<uint8_t *>(g->buf->d_b) + g->up_b, g->tctabs.b.data() + g->up_b, g->tctabs.b.size() - g->up_b, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { set_error(std::string("fanlin: table upload failed: ") + cudaGetErrorString(e)); return FANLIN_ECUDA; }
+    ctx->table_bytes += (g->ftabs.w.size() - g->up_w) * 4 + (g->ftabs.info.size() - g->up_info) * 4 + (g->tctabs.b.size() - g->up_b);
+    g->up_w = g->ftabs.w.size(); g->up_info = g->ftabs.info.size(); g->up_b = g->tctabs.b.size();
+    if (cudaEventRecord(g->uploaded, st) != cudaSuccess) { set_error("fanlin: cudaEventRecord failed"); return FANLIN_ECUDA; }
+    return FANLIN_OK;
+}
 
 // ---- context --------------------------------------------------------------------
 
@@ -166,6 +219,7 @@ extern "C" void fanlin_shutdown(fanlin_ctx *ctx) {
         if (d->worker.joinable()) d->worker.join();
         cudaSetDevice(d->ordinal);
         cudaStreamSynchronize(d->stream);
+        d->gen.reset();
         cudaStreamDestroy(d->stream);
         cudaStreamDestroy(d->copy_in);
         cudaStreamDestroy(d->copy_out);
@@ -182,6 +236,7 @@ extern "C" int fanlin_get_stats(const fanlin_ctx *ctx, fanlin_stats *out) {
     out->batches = ctx->batches.load();
     out->h2d_bytes = ctx->h2d_bytes.load();
     out->d2h_bytes = ctx->d2h_bytes.load();
+    out->table_bytes = ctx->table_bytes.load();
     return FANLIN_OK;
 }
 
@@ -280,24 +335,27 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     b->n_jobs = n_jobs;
     b->plans.resize(n_jobs);
     const bool exact = ctx->cfg.exact != 0;
-    std::unique_ptr<FusedCache, void (*)(FusedCache *)> fcache(fused_cache_new(), fused_cache_free);
-    FusedTables ftabs;
+    // Geometry caches and table arenas live in the device's table generation (TableGen): what an earlier batch built is
+    // found again, what this batch adds is uploaded behind the loop.  The generation is replaced -- never edited -- when
+    // it has grown past a bound; batches in flight keep their TableBuf.
+    std::unique_lock<std::mutex> tab_lock(dev->tab_mu);
+    const bool allow_hmma = ctx->cfg.vertical_path == 3 || ctx->cfg.vertical_path == 0;  // both Lanczos3 passes on the tensor cores where the geometry allows
+    if (!dev->gen || dev->gen->host_bytes() > (size_t(768) << 20)) dev->gen = std::make_shared<TableGen>(allow_hmma);
+    std::shared_ptr<TableGen> gen = dev->gen;
+    FusedCache *const fcache_p = gen->fcache;
+    FusedTables &ftabs = gen->ftabs;
     std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
     std::vector<uint8_t> gather_a(n_jobs, 0); // stage A is a Nearest resample: the compose kernel gathers through the tap tables
     std::vector<StagePlan> a_pre(n_jobs);     // present: stage A as the tensor-core kernel sees it behind a colour-op pass
-    // Both passes on the tensor cores need ~1 MB of per-chunk weight tiles per geometry (built and uploaded per batch:
-    // +0.25 ms on a single C2 request, +0.6 ms on a C5 one): worth it from a few waves of images on, not for the handful
-    // of requests the batcher merges.  vertical_path 3 forces it (tests, A/B runs).
-    const bool allow_hmma = ctx->cfg.vertical_path == 3 || (ctx->cfg.vertical_path == 0 && n_jobs >= TC2_MIN_JOBS);
-    std::unique_ptr<FusedTcCache, void (*)(FusedTcCache *)> tcache(fused_tc_cache_new(allow_hmma), fused_tc_cache_free);
-    FusedTcTables tctabs;
+    FusedTcCache *const tcache_p = gen->tcache;
+    FusedTcTables &tctabs = gen->tctabs;
     const bool use_tc = ctx->cfg.vertical_path != 1;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
     std::vector<uint8_t> fast_b(n_jobs, 0);  // stage B takes the fast blur kernels
     std::vector<uint8_t> tc_b(n_jobs, 0);    // ... both passes on the tensor cores, no f32 intermediate (kernels_blur_tc.cu)
-    BlurTables btabs;
+    BlurTables &btabs = gen->btabs;
     std::vector<BlurItem> bitems;
     std::vector<BlurTcItem> btitems;
-    std::unique_ptr<BlurTcCache, void (*)(BlurTcCache *)> btcache(blur_tc_cache_new(), blur_tc_cache_free);
+    BlurTcCache *const btcache_p = gen->btcache;
 
     // 1. plans + table arena
     std::map<const AxisTable *, uint32_t> tab_base;
@@ -327,10 +385,12 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
         const JobPlan &p = b->plans[i];
+        for (const auto &t : {p.a.vtab, p.a.htab, p.b.vtab, p.b.htab})
+            if (t) gen->keep.insert(t);
         fused_a[i] = 0;
         gather_a[i] = p.a.present && p.a.separable && p.a.v_kind == KIND_NEAREST && p.a.h_kind == KIND_NEAREST;  // one tap per output: a gather
         if (!exact && use_tc && !gather_a[i]) {
-            if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache.get(), &ftabs, &tctabs)) {
+            if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache_p, &ftabs, &tctabs)) {
                 fused_a[i] = 2;
             } else if (p.a.present && p.a.separable && p.a.color_op != COLOR_NONE && p.a.src_is_input) {
                 // Grayscale / inverse keep the tensor-core path: the source bytes reach the tensor core
@@ -340,13 +400,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 StagePlan m = p.a;
                 m.color_op = COLOR_NONE; m.c_mem = m.c; m.src_is_input = false;
                 m.in_pitch = uint32_t(align_up(size_t(m.in_w) * m.c, 16));
-                if (fused_tc_eligible(m, ej[i]) && fused_tc_geometry_ok(m, tcache.get(), &ftabs, &tctabs)) {
+                if (fused_tc_eligible(m, ej[i]) && fused_tc_geometry_ok(m, tcache_p, &ftabs, &tctabs)) {
                     fused_a[i] = 2;
                     a_pre[i] = m;
                 }
             }
         }
-        if (!fused_a[i] && !gather_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache.get(), &ftabs);
+        if (!fused_a[i] && !gather_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache_p, &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         fast_b[i] = !exact && blur_eligible(p.b);
         if (fast_b[i] && use_tc && ctx->cfg.blur_path != 1) {
@@ -414,8 +474,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (fused_a[i] == 1) by_variant[fused_variant(b->plans[i].a)].push_back(i);
             if (fused_a[i] == 2) {  // key: channels | 8 when the horizontal stage runs on the tensor cores too (another kernel)
                 const StagePlan &ta = a_pre[i].present ? a_pre[i] : b->plans[i].a;
-                tc_by_c[ta.c | (fused_tc_uses_hmma(ta, tcache.get(), &ftabs, &tctabs) ? 8u : 0u) |
-                        (fused_tc_uses_ring(ta, tcache.get(), &ftabs, &tctabs) ? 16u : 0u)].push_back(i);
+                tc_by_c[ta.c | (fused_tc_uses_hmma(ta, tcache_p, &ftabs, &tctabs) ? 8u : 0u) |
+                        (fused_tc_uses_ring(ta, tcache_p, &ftabs, &tctabs) ? 16u : 0u)].push_back(i);
             }
         }
         {  // orientation passes: the stored image turned (and its colour op applied) into scratch, in front of everything
@@ -465,7 +525,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const bool pre = a_pre[i].present;
                 const uint8_t *tsrc = pre ? static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off : ej[i].src;
                 const uint32_t pitch = pre ? a_pre[i].in_pitch : ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
-                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, p.b.present ? inter : ej[i].dst, tcache.get(), &ftabs,
+                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, p.b.present ? inter : ej[i].dst, tcache_p, &ftabs,
                                               &tctabs, &tcitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core tables"); return rc; }
             }
@@ -480,7 +540,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 const uint32_t pitch = ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
-                const int rc = fused_build(p.a, ej[i].src, pitch, p.b.present ? inter : ej[i].dst, fcache.get(), &ftabs, &fitems);
+                const int rc = fused_build(p.a, ej[i].src, pitch, p.b.present ? inter : ej[i].dst, fcache_p, &ftabs, &fitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: fused tables"); return rc; }
             }
             hs.n_items = uint32_t(fitems.size() - hs.first);
@@ -523,7 +583,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const JobPlan &p = b->plans[i];
                 const uint8_t *src; uint32_t pitch;
                 b_src(i, &src, &pitch);
-                const int rc = blur_tc_build(p.b, src, pitch, ej[i].dst, p.b.in_w * p.b.c, btcache.get(), &btabs, &ftabs, &tctabs, &btitems);
+                const int rc = blur_tc_build(p.b, src, pitch, ej[i].dst, p.b.in_w * p.b.c, btcache_p, &btabs, &ftabs, &tctabs, &btitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core blur tables"); return rc; }
             }
             hb.n_items = uint32_t(btitems.size() - hb.first);
@@ -557,7 +617,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 hs.variant = bi.c; hs.n_items++; hs.max_band = bi.radius; hs.smem = bi.taps_pad;
                 bitems.push_back(bi);
                 if (vtc) {
-                    const int rc = blur_v_tc_build(p.b, bi.src, bi.src_pitch, bi.tmp, tcache.get(), &ftabs, &tctabs, &bvitems);
+                    const int rc = blur_v_tc_build(p.b, bi.src, bi.src_pitch, bi.tmp, tcache_p, &ftabs, &tctabs, &bvitems);
                     if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core blur tables"); return rc; }
                 }
             }
@@ -591,11 +651,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     const size_t off_tab = align_up(descs.size() * sizeof(StageDesc), 256);
     const size_t off_w = off_tab + align_up(entries.size() * sizeof(TapEntry), 256);
     const size_t off_fi = off_w + align_up(weights.size() * sizeof(float), 256);
-    const size_t off_fw = off_fi + align_up(fitems.size() * sizeof(FusedItem), 256);
-    const size_t off_fn = off_fw + align_up(ftabs.w.size() * sizeof(float), 256);
-    const size_t off_ti = off_fn + align_up(ftabs.info.size() * sizeof(uint32_t), 256);
-    const size_t off_tb = off_ti + align_up(tcitems.size() * sizeof(FusedTcItem), 256);
-    const size_t off_tm = off_tb + align_up(tctabs.b.size(), 256);
+    const size_t off_ti = off_fi + align_up(fitems.size() * sizeof(FusedItem), 256);
+    const size_t off_tm = off_ti + align_up(tcitems.size() * sizeof(FusedTcItem), 256);
     const size_t off_bi = off_tm + align_up(tcitems.size() * 128, 256);
     const size_t off_bvi = off_bi + align_up(bitems.size() * sizeof(BlurItem), 256);
     const size_t off_bvm = off_bvi + align_up(bvitems.size() * sizeof(BlurVTcItem), 256);
@@ -610,7 +667,6 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     } meta{static_cast<uint8_t *>(b->h_meta)};
     std::memset(meta.data(), 0, meta_bytes);
     if (!tcitems.empty()) std::memcpy(meta.data() + off_ti, tcitems.data(), tcitems.size() * sizeof(FusedTcItem));
-    if (!tctabs.b.empty()) std::memcpy(meta.data() + off_tb, tctabs.b.data(), tctabs.b.size());
     if (!bitems.empty()) std::memcpy(meta.data() + off_bi, bitems.data(), bitems.size() * sizeof(BlurItem));
     if (!bvitems.empty()) std::memcpy(meta.data() + off_bvi, bvitems.data(), bvitems.size() * sizeof(BlurVTcItem));
     for (size_t k = 0; k < bvitems.size(); k++) {
@@ -633,8 +689,6 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         }
     }
     if (!fitems.empty()) std::memcpy(meta.data() + off_fi, fitems.data(), fitems.size() * sizeof(FusedItem));
-    if (!ftabs.w.empty()) std::memcpy(meta.data() + off_fw, ftabs.w.data(), ftabs.w.size() * sizeof(float));
-    if (!ftabs.info.empty()) std::memcpy(meta.data() + off_fn, ftabs.info.data(), ftabs.info.size() * sizeof(uint32_t));
     if (!descs.empty()) std::memcpy(meta.data(), descs.data(), descs.size() * sizeof(StageDesc));
     if (!entries.empty()) std::memcpy(meta.data() + off_tab, entries.data(), entries.size() * sizeof(TapEntry));
     if (!weights.empty()) std::memcpy(meta.data() + off_w, weights.data(), weights.size() * sizeof(float));
@@ -643,9 +697,15 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     const uint8_t *mbase = static_cast<const uint8_t *>(b->d_meta);
     b->d_tab = reinterpret_cast<const TapEntry *>(mbase + off_tab);
     b->d_w = reinterpret_cast<const float *>(mbase + off_w);
-    b->d_fw = reinterpret_cast<const float *>(mbase + off_fw);
-    b->d_finfo = reinterpret_cast<const uint32_t *>(mbase + off_fn);
-    b->d_tb = mbase + off_tb;
+    {  // the generation's tables: upload what this batch appended, then launch from its device copy
+        const int urc = upload_tables(ctx, dev, gen.get(), up_stream);
+        if (urc != FANLIN_OK) return urc;
+        b->tbuf = gen->buf;
+        b->d_fw = static_cast<const float *>(b->tbuf->d_w);
+        b->d_finfo = static_cast<const uint32_t *>(b->tbuf->d_info);
+        b->d_tb = static_cast<const uint8_t *>(b->tbuf->d_b);
+        tab_lock.unlock();
+    }
     for (const HostStep &hs : hsteps) {
         if (hs.kind == 4) {
             for (uint32_t o = 0; o < hs.n_items; o += 65535) {  // grid.z carries the job index

@@ -8,11 +8,14 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "blur.h"
+#include "fused.h"
+#include "fused_tc.h"
 #include "kernels.h"
 #include "plan.h"
 
@@ -46,11 +49,43 @@ struct Request {
     std::condition_variable cv;
 };
 
+// Filter tables of a device that outlive a batch: the geometry caches of the fused / tensor-core / blur builders, the
+// host arenas they append to (weights, info words, weight tiles) and their device copies.  A second batch of a geometry
+// this context has seen uploads no table bytes (fanlin_stats.table_bytes), which is what lets a single request take the
+// kernels whose tables cost ~1 MB per geometry to build.  Offsets handed to the kernels are relative to the arenas and stay
+// valid for the life of the generation; when the device copy has to grow, a new TableBuf is allocated and the old one
+// lives on until the last batch that launches from it is freed.
+struct TableBuf {
+    int ordinal = 0;
+    void *d_w = nullptr, *d_info = nullptr, *d_b = nullptr;
+    size_t cap_w = 0, cap_info = 0, cap_b = 0;  // bytes
+    ~TableBuf();
+};
+struct FusedCache;
+struct FusedTcCache;
+struct TableGen {
+    FusedCache *fcache = nullptr;
+    FusedTcCache *tcache = nullptr;
+    BlurTcCache *btcache = nullptr;
+    FusedTables ftabs;
+    FusedTcTables tctabs;
+    BlurTables btabs;
+    std::set<std::shared_ptr<const AxisTable>> keep;  // the caches are keyed by table address: held here, an address stays one table
+    std::shared_ptr<TableBuf> buf;
+    size_t up_w = 0, up_info = 0, up_b = 0;           // elements (floats, words, bytes) already on the device
+    cudaEvent_t uploaded = nullptr;                   // recorded behind the latest upload
+    explicit TableGen(bool allow_hmma);
+    ~TableGen();
+    size_t host_bytes() const { return ftabs.w.size() * 4 + ftabs.info.size() * 4 + tctabs.b.size(); }
+};
+
 struct DeviceState {
     int ordinal = 0;
     cudaStream_t stream = nullptr;   // context stream (prepare uploads, default launches)
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     std::mutex mu;                   // serialises host-path batches on this device
+    std::mutex tab_mu;               // guards gen (prepare may run on several threads)
+    std::shared_ptr<TableGen> gen;
     // request batcher
     std::mutex qmu;
     std::condition_variable qcv;
@@ -65,7 +100,7 @@ struct fanlin_ctx {
     std::vector<std::unique_ptr<fanlin::DeviceState>> devs;
     fanlin_config cfg{};
     fanlin::PinnedPool pinned;
-    std::atomic<uint64_t> kernel_launches{0}, jobs{0}, batches{0}, h2d_bytes{0}, d2h_bytes{0};
+    std::atomic<uint64_t> kernel_launches{0}, jobs{0}, batches{0}, h2d_bytes{0}, d2h_bytes{0}, table_bytes{0};
     std::atomic<uint32_t> rr{0};
     std::atomic<bool> down{false};
 };
@@ -91,6 +126,7 @@ struct fanlin_batch {
         uint32_t n_paired;  // kind 4: 1 = the vertical pass was done by a kind-7 step
     };
     std::vector<Step> steps;
+    std::shared_ptr<fanlin::TableBuf> tbuf;  // the device tables this batch launches from
     void *d_meta = nullptr;     // descriptors + tables
     cudaStream_t alloc_stream = nullptr;  // stream the device blocks were allocated on (stream-ordered pool)
     void *h_meta = nullptr;     // their pinned host copy (the upload is asynchronous)

@@ -43,7 +43,13 @@ __device__ __forceinline__ bool elect_one() {
 #ifndef MBAR_SLEEP
 #define MBAR_SLEEP 0
 #endif
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// WD + -DMBAR_WATCHDOG (debug builds, `make EXTRA=-DMBAR_WATCHDOG`): after ~2^22 failed tries (seconds; a healthy wait is
+// microseconds) the CTA traps, so that a protocol error in a kernel under development ends in a launch failure and not in
+// a hung GPU.  Off in the shipped build: the counter and the trap cost 4-7 % of the C2 kernel even when only the
+// single-thread role warps carry them (A/B on one box, 20 steps: 6.42-6.51 ms without, 6.67-6.96 ms with) -- the role
+// threads' wait loops sit between the tensor core's completion and the next MMA / copy they issue.
+template <bool WD>
+__device__ __forceinline__ void mbar_wait_impl(uint32_t bar, uint32_t parity) {
     uint32_t done = 0, spins = 0;
     (void)spins;
     while (!done) {
@@ -57,18 +63,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if MBAR_SLEEP
         if (!done) __nanosleep(MBAR_SLEEP);
 #endif
-#ifndef MBAR_NO_WATCHDOG
-        // A protocol error must end in a launch failure (FANLIN_ECUDA, fallback handling of src/main.rs:185-195), not in a
-        // hung GPU: after ~2^22 failed tries (seconds; a healthy wait is microseconds) the CTA traps.
-        if (!done && ++spins > (1u << 22)) __trap();
+#ifdef MBAR_WATCHDOG
+        if constexpr (WD) {
+            if (!done && ++spins > (1u << 22)) __trap();
+        }
 #endif
     }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { mbar_wait_impl<false>(bar, parity); }
+__device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) { mbar_wait_impl<true>(bar, parity); }
 
 #ifdef TC2_PROF
 #define PW(acc, ...) do { const long long t0_ = clock64(); mbar_wait(__VA_ARGS__); (acc) += clock64() - t0_; } while (0)
+#define PWR(acc, ...) do { const long long t0_ = clock64(); mbar_wait_wd(__VA_ARGS__); (acc) += clock64() - t0_; } while (0)
 #else
 #define PW(acc, ...) mbar_wait(__VA_ARGS__)
+#define PWR(acc, ...) mbar_wait_wd(__VA_ARGS__)  // role threads: with the watchdog in debug builds
 #endif
 
 __device__ __forceinline__ void ffma2(float2 &acc, float2 a, float w) {

@@ -55,7 +55,7 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("jobs", C.c_uint64), ("batches", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("table_bytes", C.c_uint64)]
 
 
 class QueryStruct(C.Structure):

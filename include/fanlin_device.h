@@ -96,7 +96,7 @@ typedef struct fanlin_config {
     uint64_t pinned_bytes;       /* per-device pinned staging ring; 0 = default */
     uint32_t batch_window_us;    /* request batcher collection window; 0 = default */
     uint32_t max_batch_jobs;     /* 0 = default */
-    uint32_t vertical_path;      /* 0 = tensor cores: both passes for batches of >= 256 jobs where eligible, else the vertical pass; 1 = CUDA cores only; 2 = tensor cores for the vertical pass only; 3 = both passes whatever the batch size */
+    uint32_t vertical_path;      /* 0 = tensor cores, both Lanczos3 passes where the geometry allows (tables are cached per geometry in the context, so single requests take them too); 1 = CUDA cores only; 2 = tensor cores for the vertical pass only; 3 = same as 0 (kept from ABI 1, where 0 needed >= 256 jobs per batch) */
     uint32_t blur_path;          /* 0 = both blur passes on the tensor cores where eligible (no f32 intermediate in HBM); 1 = the two-kernel blur (vertical pass on the tensor cores, horizontal on the CUDA cores) */
 } fanlin_config;
 
@@ -105,6 +105,7 @@ typedef struct fanlin_stats {
     uint64_t jobs;
     uint64_t batches;
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t table_bytes; /* filter-table bytes uploaded so far: a batch whose geometries the context has seen adds none */
 } fanlin_stats;
 
 FANLIN_API int fanlin_abi_version(void);

@@ -117,3 +117,58 @@ def test_device_batch_equals_single_requests_full_size(fanlin, dev):
     b.free()
     for i, s in enumerate(singles):
         assert np.array_equal(got[i], s), (seeds[i], hist(got[i], s))
+
+
+def test_tables_are_cached_per_geometry(fanlin):
+    """The context keeps the filter tables of every geometry it has seen on the device (TableGen, csrc/runtime.h): a
+    second request -- or batch -- of the same geometry uploads no table bytes, which is what lets a single request take
+    the both-passes tensor-core kernels (~1 MB of weight tiles per geometry)."""
+    d = fanlin.Device([0])
+    try:
+        a = synth_image(2001, 1080, 1920, 3)
+        b = synth_image(2002, 1080, 1920, 3)
+        q = fanlin.Query("w=300&h=200")
+        out_a = fanlin.process_image(d, a, q)
+        t1 = d.stats()["table_bytes"]
+        assert t1 > 100_000  # the per-chunk weight tiles of the 1080p -> 300x169 geometry
+        out_b = fanlin.process_image(d, b, q)
+        outs = fanlin.process_images(d, [a, b, a], q)
+        assert d.stats()["table_bytes"] == t1, "a geometry the context has seen uploaded table bytes again"
+        assert np.array_equal(outs[0], out_a) and np.array_equal(outs[1], out_b) and np.array_equal(outs[2], out_a)
+        fanlin.process_image(d, a, fanlin.Query("w=320&h=200"))  # another geometry: new tables
+        assert d.stats()["table_bytes"] > t1
+        want = O.process(a, w=300, h=200)
+        assert hist(out_a, want)[">=2"] == 0
+    finally:
+        d.close()
+
+
+def test_concurrent_prepares_share_the_table_generation(fanlin):
+    """Several threads preparing batches of old and new geometries on one device at once (the batcher thread and users of the
+    device-batch API do): results identical to the sequential ones."""
+    import threading
+
+    d = fanlin.Device([0])
+    try:
+        imgs = [synth_image(300 + i, 400 + 16 * i, 640, 3) for i in range(6)]
+        qs = ["w=200&h=150", "w=160&h=120&crop=true", "w=100&h=100&blur=10"]
+        want = {(i, k): fanlin.process_image(d, imgs[i], fanlin.Query(qs[k])) for i in range(6) for k in range(3)}
+        d2 = fanlin.Device([0])
+        got, errs = {}, []
+
+        def work(i):
+            try:
+                for k in range(3):
+                    got[(i, k)] = fanlin.process_image(d2, imgs[i], fanlin.Query(qs[k]))
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        d2.close()
+        assert not errs, errs
+        for key, w in want.items():
+            assert np.array_equal(got[key], w), key
+    finally:
+        d.close()
