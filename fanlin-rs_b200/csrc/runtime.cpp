@@ -848,17 +848,60 @@ extern "C" int fanlin_batch_kernel_times(fanlin_batch *b, const char **names, fl
 
 namespace {
 
-// One sub-batch in flight on one stream: device staging buffers and the prepared batch.
+constexpr uint32_t BATCH_STAGING_MIN_JOBS = 32;  // (= BATCHER_DIRECT_JOBS: calls this large are batches)
+
+// True when the copy engine can read / write p directly: memory from fanlin_host_alloc, or anything else the caller
+// pinned (cudaHostAlloc / cudaHostRegister).  A decoder's Vec<u8> is pageable: cudaMemcpyAsync from it is staged by the
+// driver, synchronously and at a fraction of the link rate, so large batches of pageable buffers go through the
+// library's own pinned staging (run_on_device).
+bool is_pinned(fanlin_ctx *ctx, const void *p, size_t bytes) {
+    if (ctx->pinned.owns(p, bytes)) return true;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Copies `n` blocks on up to `threads` host threads (a single thread moves ~10 GB/s, the link five times that).
+struct CopyOp { void *dst; const void *src; size_t bytes; };
+void parallel_copy(const std::vector<CopyOp> &ops, unsigned threads) {
+    size_t total = 0;
+    for (const CopyOp &o : ops) total += o.bytes;
+    threads = unsigned(std::min<size_t>(threads, std::max<size_t>(1, total >> 22)));  // at least 4 MB per thread
+    if (threads <= 1 || ops.size() < 2) {
+        for (const CopyOp &o : ops) std::memcpy(o.dst, o.src, o.bytes);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    auto work = [&] {
+        for (size_t i = next++; i < ops.size(); i = next++) std::memcpy(ops[i].dst, ops[i].src, ops[i].bytes);
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < threads; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+// One sub-batch in flight on one stream: device staging buffers, pinned staging for pageable callers, the prepared batch.
 struct Flight {
     uint8_t *d_in = nullptr, *d_out = nullptr;
+    uint8_t *h_in = nullptr, *h_out = nullptr;  // pinned staging (from the context's pool) when the caller's buffers are pageable
+    std::vector<CopyOp> out_ops;                // h_out -> caller dst, once the stream has drained
+    fanlin_ctx *ctx = nullptr;
     fanlin_batch *batch = nullptr;
     cudaStream_t st = nullptr;
+    void finish_outputs(unsigned threads) {  // call after the stream has been synchronised
+        if (!out_ops.empty()) parallel_copy(out_ops, threads);
+        out_ops.clear();
+    }
     void release() {
         if (batch) fanlin_batch_free(batch);
         if (d_in) cudaFreeAsync(d_in, st);
         if (d_out) cudaFreeAsync(d_out, st);
+        if (h_in) ctx->pinned.free(h_in);
+        if (h_out) ctx->pinned.free(h_out);
         batch = nullptr;
         d_in = d_out = nullptr;
+        h_in = h_out = nullptr;
     }
 };
 
@@ -875,11 +918,19 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
         if (jobs[i].dst_capacity < pl[i].out_bytes) { set_error("fanlin: dst_capacity smaller than the planned output"); return FANLIN_ECAPACITY; }
     }
-    const uint32_t per = std::max<uint32_t>(64, (n + 15) / 16);  // <= 16 sub-batches, each at least 64 jobs
-    const size_t max_bytes = size_t(2) << 30;
+    const uint32_t per = std::max<uint32_t>(64, (n + 15) / 16);  // <= 16 sub-batches, each at least 64 jobs (fewer where max_bytes cuts them)
+    size_t max_bytes = size_t(2) << 30;
     Flight fl[2];
     fl[0].st = dev->copy_in;
     fl[1].st = dev->copy_out;
+    fl[0].ctx = fl[1].ctx = ctx;
+    // Pageable callers (the Vec<u8> of a decoder, src/handler.rs:219): batches stage through pinned buffers of the context's
+    // pool -- the host copy of sub-batch k + 1 runs while sub-batch k is on the link.  Judged on the first job (a batch comes
+    // from one producer); single requests keep the driver's own staging, which costs the same as ours for one image.
+    const unsigned copy_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / unsigned(std::max<size_t>(1, ctx->devs.size()))));
+    const bool stage_in = n >= BATCH_STAGING_MIN_JOBS && !is_pinned(ctx, jobs[0].src, 1);
+    const bool stage_out = n >= BATCH_STAGING_MIN_JOBS && !is_pinned(ctx, jobs[0].dst, 1);
+    if (stage_in) max_bytes = size_t(256) << 20;  // staged sub-batches: small enough that two of them stay in the pinned pool's cache
     int rc = FANLIN_OK;
     uint32_t begin = 0, k = 0;
     std::vector<fanlin_job> djobs;
@@ -888,6 +939,7 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         Flight &f = fl[k & 1];
         if (f.batch || f.d_in) {  // the sub-batch that used this slot two rounds ago must have drained
             if (cudaStreamSynchronize(f.st) != cudaSuccess) { set_error("fanlin: CUDA error in a sub-batch"); rc = FANLIN_ECUDA; break; }
+            f.finish_outputs(copy_threads);
             f.release();
         }
         uint32_t end = begin;
@@ -913,11 +965,33 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
             break;
         }
         djobs.assign(jobs + begin, jobs + end);
+        if (stage_in || stage_out) {
+            if (stage_in) f.h_in = static_cast<uint8_t *>(ctx->pinned.alloc(in_bytes + 256));
+            if (stage_out) f.h_out = static_cast<uint8_t *>(ctx->pinned.alloc(out_bytes + 256));
+            if ((stage_in && !f.h_in) || (stage_out && !f.h_out)) { set_error("fanlin: pinned staging allocation failed"); rc = FANLIN_ENOMEM; break; }
+        }
+        if (stage_in) {  // caller rows -> pinned staging, in the layout of the device buffer (rows on a 16-byte stride)
+            std::vector<CopyOp> ops;
+            for (uint32_t i = 0; i < m; i++) {
+                const fanlin_job &j = jobs[begin + i];
+                const size_t row = size_t(j.src_w) * j.src_channels;
+                const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
+                if (pitch == row && dpitch == row) {
+                    ops.push_back(CopyOp{f.h_in + in_off[i], j.src, row * j.src_h});
+                } else {
+                    for (uint32_t y = 0; y < j.src_h; y++) ops.push_back(CopyOp{f.h_in + in_off[i] + y * dpitch, j.src + y * pitch, row});
+                }
+            }
+            parallel_copy(ops, copy_threads);
+            const cudaError_t e = cudaMemcpyAsync(f.d_in, f.h_in, in_bytes, cudaMemcpyHostToDevice, f.st);  // one copy per sub-batch
+            if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; break; }
+        }
         for (uint32_t i = 0; i < m && rc == FANLIN_OK; i++) {
             const fanlin_job &j = jobs[begin + i];
             const size_t row = size_t(j.src_w) * j.src_channels;
             const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
-            const cudaError_t e = pitch == row && dpitch == row
+            const cudaError_t e = stage_in ? cudaSuccess
+                                  : pitch == row && dpitch == row
                                       ? cudaMemcpyAsync(f.d_in + in_off[i], j.src, row * j.src_h, cudaMemcpyHostToDevice, f.st)
                                       : cudaMemcpy2DAsync(f.d_in + in_off[i], dpitch, j.src, pitch, row, j.src_h, cudaMemcpyHostToDevice, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; }
@@ -932,10 +1006,19 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         if (rc != FANLIN_OK) break;
         rc = fanlin_batch_launch(f.batch, f.st);
         if (rc != FANLIN_OK) break;
-        for (uint32_t i = 0; i < m; i++) {
-            const cudaError_t e = cudaMemcpyAsync(jobs[begin + i].dst, f.d_out + out_off[i], pl[begin + i].out_bytes, cudaMemcpyDeviceToHost, f.st);
+        if (stage_out) {  // one copy per sub-batch into pinned staging; handed to the caller's buffers when the stream has drained
+            const cudaError_t e = cudaMemcpyAsync(f.h_out, f.d_out, out_bytes, cudaMemcpyDeviceToHost, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: D2H failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; break; }
-            ctx->d2h_bytes += pl[begin + i].out_bytes;
+            for (uint32_t i = 0; i < m; i++) {
+                f.out_ops.push_back(CopyOp{jobs[begin + i].dst, f.h_out + out_off[i], size_t(pl[begin + i].out_bytes)});
+                ctx->d2h_bytes += pl[begin + i].out_bytes;
+            }
+        } else {
+            for (uint32_t i = 0; i < m; i++) {
+                const cudaError_t e = cudaMemcpyAsync(jobs[begin + i].dst, f.d_out + out_off[i], pl[begin + i].out_bytes, cudaMemcpyDeviceToHost, f.st);
+                if (e != cudaSuccess) { set_error(std::string("fanlin: D2H failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; break; }
+                ctx->d2h_bytes += pl[begin + i].out_bytes;
+            }
         }
         begin = end;
         k++;
@@ -946,6 +1029,7 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
             set_error(std::string("fanlin: CUDA error: ") + cudaGetErrorString(se));
             rc = FANLIN_ECUDA;
         }
+        if (rc == FANLIN_OK) f.finish_outputs(copy_threads);
         f.release();
     }
     if (rc == FANLIN_OK && plans) std::copy(pl.begin(), pl.end(), plans);
