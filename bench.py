@@ -414,15 +414,15 @@ def main():
 
     # dominant kernel and its roofline
     def ncu_traffic(kernel, images):
-        """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of
-        this workload, scaled from the captured launch's image count to this launch's (the kernel
-        streams every image once: traffic is per image)."""
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01", "ncu_traffic_c2.json")
+        """DRAM bytes per launch of the dominant kernel from this round's committed `ncu --set full` capture of the
+        same workload (profiles/r02/ncu_traffic.json), scaled from the captured launch's image count to this launch's:
+        the kernel streams every image once, traffic is per image.  ncu cannot run inside a timed bench."""
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02", "ncu_traffic.json")
         try:
-            t = json.load(open(path))
+            t = json.load(open(path)).get(kernel)
         except OSError:
             return None
-        if t.get("kernel") != kernel:
+        if not t or not t["workload"].startswith("C2"):
             return None
         return (t["dram_bytes_read"] + t["dram_bytes_write"]) / t["images"] * images
 
@@ -432,7 +432,9 @@ def main():
         avg_ms = sum(ktimes[dom]) / len(ktimes[dom])
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None if args.exact else ncu_traffic(dom, n), "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": None if args.exact else ncu_traffic(dom, n),
+                    "traffic_source": "profiles/r02/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full launch of this kernel on this workload, per image x images",
+                    "peak_source": peak_src,
                     "kernel_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                     "kernel_share_of_step": avg_ms / ms_per_step,
                     "all_kernels_ms": {k: sum(v) / len(v) for k, v in ktimes.items()}}
