@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <tuple>
 
@@ -15,6 +16,7 @@ namespace {
 
 struct TcBand {
     uint32_t r0, rows, grp_off, n_groups, kg_max, grp_rows;
+    uint32_t inv_off;  // u32 offset of the band's per-row constants 255 * (sum of the row's quantised weights) * 2^-s as f32 bits
 };
 struct TcGeom {
     bool ok = false;
@@ -136,7 +138,10 @@ bool fused_tc_eligible(const StagePlan &s, const fanlin_job &job) {
     if (!s.present || !s.separable || !s.vtab || !s.htab) return false;
     if (s.n_rows == 0 || s.n_cols == 0) return false;
     if (s.v_kind != KIND_LANCZOS3) return false;  // Nearest is a gather (bit-exact on the CUDA-core path); blur has its own kernel
-    if (s.color_op != COLOR_NONE || s.c_mem != s.c) return false;
+    // Inverse rides on the vertical pass: sum q (255 - x) = 255 sum q - sum q x, exact in the integer contraction, so the
+    // consumers subtract the vertical result from a per-row constant (colour channels only) instead of a pass over the
+    // source inverting its bytes.  Grayscale changes the channel count and keeps its pass.
+    if ((s.color_op != COLOR_NONE && s.color_op != COLOR_INVERT) || s.c_mem != s.c) return false;
     const uint32_t pitch = s.src_is_input ? (job.src_pitch ? job.src_pitch : job.src_w * job.src_channels) : (s.in_pitch ? s.in_pitch : s.in_w * s.c_mem);
     if (pitch % 16 != 0) return false;  // TMA: the row stride is a multiple of 16 bytes
     if (s.src_is_input && (reinterpret_cast<uintptr_t>(job.src) & 15)) return false;
@@ -210,6 +215,17 @@ static bool build_band(const AxisTable &vt, uint32_t oy0, uint32_t r0, uint32_t 
         }
         uint32_t *gw = &tabs->info[bt.grp_off + size_t(gi) * 4];
         gw[0] = k0; gw[1] = kg; gw[2] = uint32_t(b_off); gw[3] = rb - ra;
+    }
+    // inverse on load: per band row, 255 * sum of its quantised weights, at the scale of the recombined vertical result
+    bt.inv_off = uint32_t(tabs->info.size());
+    for (uint32_t r = 0; r < bt.rows; r++) {
+        const TapEntry &e = vt.entries[oy0 + bt.r0 + r];
+        double sq = 0.0;
+        for (uint32_t t = 0; t < e.count; t++) sq += double(std::lround(std::ldexp(double(vt.weights[e.woff + t]), sh)));
+        const float k = float(std::ldexp(255.0 * sq, -sh));
+        uint32_t bits;
+        std::memcpy(&bits, &k, 4);
+        tabs->info.push_back(bits);
     }
     *out = bt;
     return true;
@@ -582,6 +598,7 @@ int fused_tc_build(const StagePlan &s, const fanlin_job &job, const uint8_t *src
         f.dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; f.c_out = s.c_out; f.canvas_w = s.canvas_w; f.canvas_h = s.canvas_h;
         f.dst_x = s.dst_x; f.dst_y = s.dst_y; f.epi = s.epi; f.fill = s.fill;
         f.first_band = b == 0; f.last_band = b + 1 == g.bands.size();
+        f.inv_off = s.color_op == COLOR_INVERT ? bt.inv_off : 0xffffffffu;
         if (g.ring) {
             f.hmma = 2; f.hrec_off = g.hrec_off;
             f.ring_cols = g.ring_cols; f.stage_stride = g.stage_stride; f.wh_bytes = g.wh_bytes;

@@ -58,6 +58,7 @@ struct FusedTcItem {
     // stage_stride words per row of a consumer warp's output staging tile; per-chunk records of 8 words
     // {tile offset, first output finished, outputs finished, window column, window columns, ring slot of the first finished, 0, 0}
     uint32_t ring_cols, n_vr, stage_stride, wh_bytes;
+    uint32_t inv_off;  // inverse on load: u32 offset of the band's per-row constants (f32 bits), 0xffffffff = no colour op
 };
 
 // Tensor-core horizontal stage: the chunk's 128 tile columns (K) are contracted with an f16 weight

@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
         // ================= consumer warps =================
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
         const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        // inverse on load applies to the colour channels of this thread's tile column (byte b0 + 128 chunk + m of the row)
+        const bool inv_on = it.inv_off != 0xffffffffu && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
         const uint32_t grp_rows = it.grp_rows;
         const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows, h_epi = it.epi, h_fill = it.fill;
         const uint32_t RP = ring_cols / C;
@@ -442,6 +444,11 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     float2 r = make_float2(0.f, 0.f);
                     ffma2(r, fl, scale);
                     ffma2(r, fh, scale_hi);
+                    if (inv_on) {  // inverse on load: 255 sum q - sum q x (colour channels; alpha columns pass)
+                        const uint32_t ri = g * grp_rows + half * 16 + e, rmax = it.band_rows - 1;  // (rows past the band are never stored)
+                        r.x = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri, rmax))) - r.x;
+                        r.y = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri + 1, rmax))) - r.y;
+                    }
                     const uint32_t h2 = pack_f16x2(r.x, r.y);
                     const float2 back = unpack_f16x2(h2);
                     ph[e / 2] = h2;

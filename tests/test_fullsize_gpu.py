@@ -172,3 +172,37 @@ def test_concurrent_prepares_share_the_table_generation(fanlin):
             assert np.array_equal(got[key], w), key
     finally:
         d.close()
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 4])
+def test_inverse_rides_on_the_vertical_pass(fanlin, c):
+    """inverse=true on the tensor-core resample: sum q (255 - x) = 255 sum q - sum q x in the exact integer contraction, so
+    no pass over the source inverts its bytes (the launch list holds no colour pass), alpha is left alone, and the
+    result is what inverting first gives (handler.rs:226-228 inverts BEFORE the resize)."""
+    import torch
+
+    d = fanlin.Device([0])
+    try:
+        h, w = 1080, 1920
+        img = synth_image(70 + c + (7 - (70 + c) % 8 if c in (2, 4) else 0), h, w, c)  # LA / RGBA: a seed with random alpha
+        if c in (2, 4):
+            assert (img[..., c - 1] != 255).any()
+        want = O.process(img, w=300, h=200, inverse=True, rgb=(9, 8, 7))
+        got = fanlin.process_image(d, img, fanlin.Query("w=300&h=200&inverse=true&rgb=9,8,7"))
+        hh = hist(got, want)
+        assert got.shape == want.shape and hh[">=2"] == 0, hh
+        src = torch.from_numpy(img).cuda()
+        dst = torch.zeros(want.shape, dtype=torch.uint8, device="cuda")
+        j = fanlin.make_job(img, fanlin.Query("w=300&h=200&inverse=true&rgb=9,8,7"))
+        j.src, j.dst, j.dst_capacity = src.data_ptr(), dst.data_ptr(), want.size
+        torch.cuda.synchronize()
+        b = d.prepare([j], 0)
+        b.set_timing(True)
+        b.launch(None)
+        torch.cuda.synchronize()
+        names = [k for k, _ in b.kernel_times()]
+        b.free()
+        assert names and all("color_pass" not in k for k in names), names
+        assert np.array_equal(dst.cpu().numpy(), got)
+    finally:
+        d.close()
