@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -350,8 +351,20 @@ static bool build_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
         if (fin != o_end) return false;
     }
     const uint32_t al = ring_slot_align(C);
-    const uint32_t RP = (std::max(live_max, 1u) + al - 1) / al * al, RINGC = RP * C;
-    if (RINGC > 256) return false;
+    uint32_t RP = (std::max(live_max, 1u) + al - 1) / al * al, RINGC = RP * C;
+    // the window of a chunk starts on a multiple of 16 columns: with that padding it must still fit the ring
+    for (;; RP += al, RINGC = RP * C) {
+        if (RINGC > 256) return false;
+        uint32_t fin = o0, touch = o0, widest = 0;
+        for (uint32_t ch = 0; ch < g.n_chunks; ch++) {
+            const uint32_t b1 = g.b0 + TC_M * (ch + 1), x_hi = (b1 - 1) / C;
+            while (touch < o_end && t.entries[touch].left <= x_hi) touch++;
+            const uint32_t u0 = ((fin - o0) % RP) * C, len = (touch - fin) * C;
+            widest = std::max(widest, (u0 + len - (u0 & ~15u) + 15) & ~15u);
+            while (fin < touch && (t.entries[fin].left + t.entries[fin].count) * C <= b1) fin++;
+        }
+        if (widest <= RINGC) break;
+    }
     g.ring_cols = RINGC;
     // words per staged row, == 4 (mod 8): 16-byte aligned rows whose four-word stores (lanes = rows) fall on distinct banks
     g.stage_stride = (fin_max * s.c_out + 3) / 4 + 1;
@@ -454,6 +467,9 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
     g.n_chunks = (xe * C - g.b0 + TC_M - 1) / TC_M;
     // Horizontal stage on the tensor cores where the output ring and the shared-memory budget allow it: the band
     // keeps its rows as f16 hi / lo tiles (32 rows per group, <= 8 groups = two M = 128 tiles) next to >= 2 source slots.
+    // FANLIN_PREFER_RING=1 (experiments): the ring variant also where the register-ring kernel fits
+    static const bool prefer_ring = [] { const char *e = std::getenv("FANLIN_PREFER_RING"); return e && e[0] == '1'; }();
+    if (cache->allow_hmma && prefer_ring && try_ring(s, g, tabs, tct)) return cache->geoms.emplace(key, std::move(g)).first->second;
     if (cache->allow_hmma) {
         const int sh = weight_shift(*s.vtab);
         uint32_t hm_out_stride = 1;

@@ -271,8 +271,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                 mbar_wait(smem_u32(&mbar[region]), (gg / NR) & 1);  // the MMAs of group gg have retired
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t half = warp >> 2, m = (warp & 3) * 32 + lane;
-                // inverse on load applies to the colour channels of this thread's tile column (byte b0 + 128 chunk + m of the row)
-                const bool inv_on = it.inv_off != 0xffffffffu && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
                 const uint32_t taddr = tmem_base + region * TC_N + (((warp & 3) * 32u) << 16) + half * 16;
                 uint32_t hi[16], mid[16], lo[16];
                 tmem_ld16(taddr, hi);
@@ -292,11 +290,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_resample_tc_kernel(const Fuse
                     float2 r = make_float2(0.f, 0.f);
                     ffma2(r, fl, scale);
                     ffma2(r, fh, scale_hi);
-                    if (inv_on) {  // inverse on load: 255 sum q - sum q x (colour channels; alpha columns pass)
-                        const uint32_t ri = g * grp_rows + half * 16 + e, rmax = it.band_rows - 1;  // (rows past the band are never stored)
-                        r.x = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri, rmax))) - r.x;
-                        r.y = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri + 1, rmax))) - r.y;
-                    }
                     v2[e / 2] = r;
                 }
                 if (nv >= 16) {  // lanes = consecutive columns, r_pad odd: conflict-free
@@ -671,7 +664,9 @@ __device__ __forceinline__ void tc2_v_role(const TcPipe &p) {
 #endif
 }
 
-template <int C>
+// INV: inverse on load (a template parameter: the consumers' conversion loop is what bounds them, and a runtime test in
+// it cost the plain kernel 17 %)
+template <int C, bool INV = false>
 __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const FusedTcItem *__restrict__ items, const CUtensorMap *__restrict__ tmaps,
                                                                     const uint8_t *__restrict__ tb, const uint32_t *__restrict__ tinfo) {
     constexpr uint32_t N2 = C == 3 ? 48 : 64, RP = N2 / C, HP = RP / 2;  // accumulator columns, ring of outputs, ring positions per thread
@@ -764,7 +759,7 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
         const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
         // inverse on load applies to the colour channels of this thread's tile column (byte b0 + 128 chunk + m of the row)
-        const bool inv_on = it.inv_off != 0xffffffffu && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
+        const bool inv_on = INV && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
         const uint32_t grp_rows = it.grp_rows, n_mt = hp.n_mt;
         const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows, h_epi = it.epi, h_fill = it.fill;
         const uint32_t out_stride = it.out_stride, out_u = smem_u32(out_s);
@@ -901,7 +896,7 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
                     float2 r = make_float2(0.f, 0.f);
                     ffma2(r, fl, scale);
                     ffma2(r, fh, scale_hi);
-                    if (inv_on) {  // inverse on load: 255 sum q - sum q x (colour channels; alpha columns pass)
+                    if (INV && inv_on) {  // inverse on load: 255 sum q - sum q x (colour channels; alpha columns pass)
                         const uint32_t ri = g * grp_rows + half * 16 + e, rmax = h_rows - 1;  // (rows past the band are never stored)
                         r.x = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri, rmax))) - r.x;
                         r.y = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri + 1, rmax))) - r.y;
@@ -947,10 +942,10 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
 #endif
 }
 
-template <int C>
+template <int C, bool INV>
 void launch_tc2_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b, const uint32_t *d_info,
                         LaunchCtx &lc) {
-    auto kern = fused_resample_tc2_kernel<C>;
+    auto kern = fused_resample_tc2_kernel<C, INV>;
     ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);  // a failure surfaces as the launch error
     lc.begin("fused_resample_tc2_kernel");
     kern<<<n_items, NT_ALL2, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
@@ -972,13 +967,17 @@ void launch_tc_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t
 int launch_fused_tc(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                     const float *d_w, const uint32_t *d_info, LaunchCtx &lc) {
     if (n_items == 0) return 0;
-    if (c & 16) return launch_fused_tc3(d_items, d_tmaps, n_items, c & 7, smem, d_b, d_info, lc);  // ... with the horizontal sums kept in TMEM
-    if (c & 8) {  // both passes on the tensor cores
-        switch (c & 7) {
-        case 1: launch_tc2_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
-        case 2: launch_tc2_variant<2>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
-        case 3: launch_tc2_variant<3>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
-        case 4: launch_tc2_variant<4>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    if (c & 16) return launch_fused_tc3(d_items, d_tmaps, n_items, c & 39, smem, d_b, d_info, lc);  // ... with the horizontal sums kept in TMEM
+    if (c & 8) {  // both passes on the tensor cores; bit 5: inverse on load
+        switch (c & 39) {
+        case 1: launch_tc2_variant<1, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 2: launch_tc2_variant<2, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 3: launch_tc2_variant<3, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 4: launch_tc2_variant<4, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 33: launch_tc2_variant<1, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 34: launch_tc2_variant<2, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 35: launch_tc2_variant<3, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+        case 36: launch_tc2_variant<4, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
         }
         return -1;
     }
@@ -1016,8 +1015,8 @@ size_t fused_tc_smem_limit() {
         size_t stat = 0;
         const void *kerns[8] = {reinterpret_cast<const void *>(fused_resample_tc_kernel<1>), reinterpret_cast<const void *>(fused_resample_tc_kernel<2>),
                                 reinterpret_cast<const void *>(fused_resample_tc_kernel<3>), reinterpret_cast<const void *>(fused_resample_tc_kernel<4>),
-                                reinterpret_cast<const void *>(fused_resample_tc2_kernel<1>), reinterpret_cast<const void *>(fused_resample_tc2_kernel<2>),
-                                reinterpret_cast<const void *>(fused_resample_tc2_kernel<3>), reinterpret_cast<const void *>(fused_resample_tc2_kernel<4>)};
+                                reinterpret_cast<const void *>(fused_resample_tc2_kernel<1, false>), reinterpret_cast<const void *>(fused_resample_tc2_kernel<2, false>),
+                                reinterpret_cast<const void *>(fused_resample_tc2_kernel<3, false>), reinterpret_cast<const void *>(fused_resample_tc2_kernel<4, false>)};
         bool ok = true;
         for (const void *k : kerns) {
             cudaFuncAttributes fa{};

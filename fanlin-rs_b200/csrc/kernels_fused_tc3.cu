@@ -41,7 +41,7 @@ constexpr uint32_t T3_NA_MAX = 4;
 
 __device__ __forceinline__ void t3_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
-template <int C>
+template <int C, bool INV = false>  // INV: inverse on load, a template parameter (see fused_resample_tc2_kernel)
 __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const FusedTcItem *__restrict__ items, const CUtensorMap *__restrict__ tmaps,
                                                                           const uint8_t *__restrict__ tb, const uint32_t *__restrict__ tinfo) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
         const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
         // inverse on load applies to the colour channels of this thread's tile column (byte b0 + 128 chunk + m of the row)
-        const bool inv_on = it.inv_off != 0xffffffffu && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
+        const bool inv_on = INV && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
         const uint32_t grp_rows = it.grp_rows;
         const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows, h_epi = it.epi, h_fill = it.fill;
         const uint32_t RP = ring_cols / C;
@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     float2 r = make_float2(0.f, 0.f);
                     ffma2(r, fl, scale);
                     ffma2(r, fh, scale_hi);
-                    if (inv_on) {  // inverse on load: 255 sum q - sum q x (colour channels; alpha columns pass)
+                    if (INV && inv_on) {  // inverse on load: 255 sum q - sum q x (colour channels; alpha columns pass)
                         const uint32_t ri = g * grp_rows + half * 16 + e, rmax = it.band_rows - 1;  // (rows past the band are never stored)
                         r.x = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri, rmax))) - r.x;
                         r.y = __uint_as_float(__ldg(tinfo + it.inv_off + min(ri + 1, rmax))) - r.y;
@@ -483,10 +483,10 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
-template <int C>
+template <int C, bool INV>
 void launch_tc3_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, size_t smem, const uint8_t *d_b, const uint32_t *d_info,
                         LaunchCtx &lc) {
-    auto kern = fused_resample_tc3_kernel<C>;
+    auto kern = fused_resample_tc3_kernel<C, INV>;
     ensure_dynamic_smem(reinterpret_cast<const void *>(kern), smem);
     lc.begin("fused_resample_tc3_kernel");
     kern<<<n_items, T3_NT_ALL, smem, lc.st>>>(d_items, static_cast<const CUtensorMap *>(d_tmaps), d_b, d_info);
@@ -498,11 +498,15 @@ void launch_tc3_variant(const FusedTcItem *d_items, const void *d_tmaps, uint32_
 int launch_fused_tc3(const FusedTcItem *d_items, const void *d_tmaps, uint32_t n_items, uint32_t c, size_t smem, const uint8_t *d_b,
                      const uint32_t *d_info, LaunchCtx &lc) {
     if (n_items == 0) return 0;
-    switch (c) {
-    case 1: launch_tc3_variant<1>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
-    case 2: launch_tc3_variant<2>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
-    case 3: launch_tc3_variant<3>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
-    case 4: launch_tc3_variant<4>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    switch (c) {  // bit 5: inverse on load
+    case 1: launch_tc3_variant<1, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 2: launch_tc3_variant<2, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 3: launch_tc3_variant<3, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 4: launch_tc3_variant<4, false>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 33: launch_tc3_variant<1, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 34: launch_tc3_variant<2, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 35: launch_tc3_variant<3, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
+    case 36: launch_tc3_variant<4, true>(d_items, d_tmaps, n_items, smem, d_b, d_info, lc); return 1;
     }
     return -1;
 }

@@ -390,7 +390,10 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         fused_a[i] = 0;
         gather_a[i] = p.a.present && p.a.separable && p.a.v_kind == KIND_NEAREST && p.a.h_kind == KIND_NEAREST;  // one tap per output: a gather
         if (!exact && use_tc && !gather_a[i]) {
-            if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache_p, &ftabs, &tctabs)) {
+            // (inverse rides on the vertical pass of the both-passes kernels only: the kernel with the CUDA-core horizontal
+            // stage keeps the colour pass in front of it)
+            if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache_p, &ftabs, &tctabs) &&
+                (p.a.color_op == COLOR_NONE || fused_tc_uses_hmma(p.a, tcache_p, &ftabs, &tctabs) || fused_tc_uses_ring(p.a, tcache_p, &ftabs, &tctabs))) {
                 fused_a[i] = 2;
             } else if (p.a.present && p.a.separable && p.a.color_op != COLOR_NONE && p.a.src_is_input) {
                 // Grayscale / inverse keep the tensor-core path: the source bytes reach the tensor core
@@ -475,7 +478,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (fused_a[i] == 2) {  // key: channels | 8 when the horizontal stage runs on the tensor cores too (another kernel)
                 const StagePlan &ta = a_pre[i].present ? a_pre[i] : b->plans[i].a;
                 tc_by_c[ta.c | (fused_tc_uses_hmma(ta, tcache_p, &ftabs, &tctabs) ? 8u : 0u) |
-                        (fused_tc_uses_ring(ta, tcache_p, &ftabs, &tctabs) ? 16u : 0u)].push_back(i);
+                        (fused_tc_uses_ring(ta, tcache_p, &ftabs, &tctabs) ? 16u : 0u) | (ta.color_op == COLOR_INVERT ? 32u : 0u)].push_back(i);
             }
         }
         {  // orientation passes: the stored image turned (and its colour op applied) into scratch, in front of everything
