@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
     const uint32_t sy = !row_in ? 0u : gather ? tab[d.v_tab + d.oy0 + (cy - dst_y)].left : d.oy0 + (cy - dst_y);
     const uint8_t *srow = d.src + size_t(sy) * d.src_pitch;
     const uint32_t ox0 = d.ox0, h_tab = d.h_tab;
+    // orient >= 2 (orientation applied after the resample, runtime.cpp): the source is a small image AS STORED and pixel
+    // (ox0 + lx, oy0 + ly) of its oriented view is wanted -- the index map of orient_pass_kernel below
+    const uint32_t orient = gather ? 0u : d.orient, SW = d.src_w, SH = d.src_h, yo = d.oy0 + (cy - dst_y);
     uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx0) * c_out;
     uint32_t out[4];
 #pragma unroll
@@ -116,6 +119,18 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
         if (cx < cw && row_in && cx >= dst_x && lx < n_cols) {
             const uint32_t sx = gather ? tab[h_tab + ox0 + lx].left : ox0 + lx;
             const uint8_t *p = srow + size_t(sx) * c_mem;
+            if (orient >= 2) {
+                const uint32_t xo = ox0 + lx;
+                uint32_t ux, uy;
+                if (orient >= 5) {
+                    ux = (orient == 5 || orient == 6) ? yo : SW - 1 - yo;
+                    uy = (orient == 5 || orient == 8) ? xo : SH - 1 - xo;
+                } else {
+                    ux = (orient == 2 || orient == 3) ? SW - 1 - xo : xo;
+                    uy = (orient == 3 || orient == 4) ? SH - 1 - yo : yo;
+                }
+                p = d.src + size_t(uy) * d.src_pitch + size_t(ux) * c_mem;
+            }
             const uint32_t v = c_mem == 4 ? fetch_packed<4>(p, color_op) : c_mem == 3 ? fetch_packed<3>(p, color_op)
                              : c_mem == 1 ? fetch_packed<1>(p, color_op) : fetch_packed<2>(p, color_op);
             if (epi == EPI_PLAIN) {

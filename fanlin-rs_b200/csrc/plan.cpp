@@ -147,6 +147,62 @@ std::shared_ptr<const AxisTable> build_axis_table(uint32_t kind, float sigma, ui
     return t;
 }
 
+std::shared_ptr<const AxisTable> mirror_axis_table(const std::shared_ptr<const AxisTable> &t) {
+    static std::mutex mu;
+    static std::map<const AxisTable *, std::pair<std::shared_ptr<const AxisTable>, std::shared_ptr<const AxisTable>>> cache;  // original (kept alive) -> mirrored
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(t.get());
+    if (it != cache.end()) return it->second.second;
+    if (cache.size() > 4096) cache.clear();
+    auto m = std::make_shared<AxisTable>();
+    m->kind = t->kind; m->n_in = t->n_in; m->n_out = t->n_out; m->sigma = t->sigma; m->max_taps = t->max_taps;
+    m->entries.resize(t->entries.size());
+    m->weights.reserve(t->weights.size());
+    const uint32_t n_out = uint32_t(t->entries.size());
+    for (uint32_t o2 = 0; o2 < n_out; o2++) {
+        const TapEntry &e = t->entries[n_out - 1 - o2];
+        m->entries[o2] = TapEntry{t->n_in - e.left - e.count, e.count, uint32_t(m->weights.size())};
+        for (uint32_t k = 0; k < e.count; k++) m->weights.push_back(t->weights[e.woff + e.count - 1 - k]);
+    }
+    cache[t.get()] = std::make_pair(t, std::shared_ptr<const AxisTable>(m));
+    return cache[t.get()].second;
+}
+
+StagePlan stored_axes_stage(const StagePlan &a, const fanlin_job &stored, uint32_t e) {
+    StagePlan in;
+    in.present = true; in.separable = true; in.src_is_input = true;
+    in.in_w = stored.src_w; in.in_h = stored.src_h; in.c_mem = stored.src_channels; in.c = stored.src_channels; in.color_op = COLOR_NONE;
+    if (stored.flags & FANLIN_GRAYSCALE) {
+        if (stored.src_channels >= 3) { in.color_op = COLOR_GRAY; in.c = stored.src_channels - 2; }
+    } else if (stored.flags & FANLIN_INVERSE) {
+        in.color_op = COLOR_INVERT;
+    }
+    in.v_kind = a.v_kind; in.h_kind = a.h_kind;
+    const bool swap = e >= 5;
+    // oriented (xo, yo) = stored (sx, sy) (Orientation::from_exif + apply_orientation, handler.rs:221-223):
+    //   e < 5: sx = xo, mirrored for 2 and 3; sy = yo, mirrored for 3 and 4
+    //   e >= 5: sx = yo, mirrored for 7 and 8; sy = xo, mirrored for 6 and 7
+    const bool mx = swap ? (e == 7 || e == 8) : (e == 2 || e == 3);  // the stored x axis runs against its oriented axis
+    const bool my = swap ? (e == 6 || e == 7) : (e == 3 || e == 4);
+    const std::shared_ptr<const AxisTable> &tx = swap ? a.vtab : a.htab, &ty = swap ? a.htab : a.vtab;  // oriented tables of the stored x / y axes
+    const uint32_t x_out = swap ? a.v_out : a.h_out, y_out = swap ? a.h_out : a.v_out;
+    const uint32_t x0 = swap ? a.oy0 : a.ox0, xn = swap ? a.n_rows : a.n_cols, y0 = swap ? a.ox0 : a.oy0, yn = swap ? a.n_cols : a.n_rows;
+    in.htab = tx ? (mx ? mirror_axis_table(tx) : tx) : nullptr;
+    in.vtab = ty ? (my ? mirror_axis_table(ty) : ty) : nullptr;
+    in.h_out = x_out; in.v_out = y_out;
+    in.ox0 = mx ? x_out - x0 - xn : x0; in.n_cols = xn;
+    in.oy0 = my ? y_out - y0 - yn : y0; in.n_rows = yn;
+    auto window = [](const AxisTable &t, uint32_t o0, uint32_t n, uint32_t *s0, uint32_t *ns) {
+        uint32_t lo = ~0u, hi = 0;
+        for (uint32_t o = o0; o < o0 + n; o++) { lo = std::min(lo, t.entries[o].left); hi = std::max(hi, t.entries[o].left + t.entries[o].count); }
+        *s0 = lo; *ns = hi - lo;
+    };
+    if (in.htab) window(*in.htab, in.ox0, in.n_cols, &in.sx0, &in.n_sx);
+    if (in.vtab) window(*in.vtab, in.oy0, in.n_rows, &in.sy0, &in.n_sy);
+    in.canvas_w = in.n_cols; in.canvas_h = in.n_rows; in.c_out = in.c; in.dst_x = in.dst_y = 0; in.epi = EPI_PLAIN; in.fill = 0;
+    return in;
+}
+
 static void axis_window(uint32_t kind, float sigma, uint32_t n_in, uint32_t n_out, uint32_t o0, uint32_t n,
                         uint32_t *s0, uint32_t *s1) {
     const FilterFn f{kind, sigma};

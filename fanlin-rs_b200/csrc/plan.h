@@ -28,6 +28,10 @@ using TableKey = std::tuple<uint32_t, uint32_t, uint32_t, uint32_t>;  // kind, s
 TableKey table_key(uint32_t kind, float sigma, uint32_t n_in, uint32_t n_out);
 std::shared_ptr<const AxisTable> build_axis_table(uint32_t kind, float sigma, uint32_t n_in, uint32_t n_out);
 
+// The same taps seen from the other end of both axes: entry n_out - 1 - o reads source [n_in - left - count, n_in - left) with
+// the weights of entry o reversed -- the table of an axis that is stored mirrored (EXIF flips, cached per table).
+std::shared_ptr<const AxisTable> mirror_axis_table(const std::shared_ptr<const AxisTable> &t);
+
 // resize_dimensions of image-0.25.6 math/utils.rs.
 void resize_dimensions(uint32_t w, uint32_t h, uint32_t nw, uint32_t nh, bool fill, uint32_t *ow, uint32_t *oh);
 
@@ -65,6 +69,13 @@ struct JobPlan {
     StagePlan a;  // colour op + resample + letterbox (+ to_rgba8), or compose
     StagePlan b;  // blur
 };
+
+// EXIF orientation applied AFTER the resample (fast paths): the Lanczos3 stage `a` of a job planned for the oriented image,
+// restated on the image AS STORED -- the oriented axes' tables on the stored axes they run along, mirrored where the
+// axis is stored mirrored, the produced rectangle mapped likewise, plain output.  Orienting its (small) output with the
+// same EXIF value gives the oriented stage's pixels up to the order of the f32 additions: a separable filter commutes
+// with flips and transposition, and the pass over the stored source at full resolution disappears.
+StagePlan stored_axes_stage(const StagePlan &a, const fanlin_job &stored, uint32_t exif);
 
 // Returns FANLIN_OK or FANLIN_EINVAL (message via set_error).  with_tables: also
 // build the axis tables (not needed for fanlin_plan_job).

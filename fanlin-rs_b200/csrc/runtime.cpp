@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -253,8 +254,8 @@ extern "C" void fanlin_host_free(fanlin_ctx *ctx, void *p) {
 namespace {
 
 struct JobScratch {
-    size_t pre = 0, inter = 0, tmp = 0, fin = 0;                  // bytes
-    size_t pre_off = 0, inter_off = 0, tmp_off = 0, fin_off = 0;  // offsets inside the chunk's scratch
+    size_t pre = 0, inter = 0, tmp = 0, fin = 0, lor = 0;                     // bytes
+    size_t pre_off = 0, inter_off = 0, tmp_off = 0, fin_off = 0, lor_off = 0;  // offsets inside the chunk's scratch
 };
 
 void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t *inter, float *tmp,
@@ -347,6 +348,12 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     std::vector<uint8_t> fused_a(n_jobs, 0);  // stage A: 1 = fused resample kernel, 2 = its tensor-core variant
     std::vector<uint8_t> gather_a(n_jobs, 0); // stage A is a Nearest resample: the compose kernel gathers through the tap tables
     std::vector<StagePlan> a_pre(n_jobs);     // present: stage A as the tensor-core kernel sees it behind a colour-op pass
+    // EXIF orientation AFTER the resample (plan.h stored_axes_stage): stage A runs on the image as stored and writes a small
+    // plain image to scratch; that image is oriented (the pass that used to run over the full-resolution source) and, where
+    // the oriented stage had a letterbox / to_rgba8 epilogue, composed onto the canvas.  late_a = the oriented stage A.
+    std::vector<uint8_t> late(n_jobs, 0);
+    std::vector<StagePlan> late_a(n_jobs);
+    static const bool late_orient_on = [] { const char *e = std::getenv("FANLIN_LATE_ORIENT"); return !(e && e[0] == '0'); }();
     FusedTcCache *const tcache_p = gen->tcache;
     FusedTcTables &tctabs = gen->tctabs;
     const bool use_tc = ctx->cfg.vertical_path != 1;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
@@ -384,6 +391,22 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             return FANLIN_ECAPACITY;
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
+        if (late_orient_on && !exact && use_tc && b->plans[i].pre.present && b->plans[i].a.present && b->plans[i].a.separable &&
+            b->plans[i].a.v_kind == KIND_LANCZOS3 && b->plans[i].a.n_rows && b->plans[i].a.n_cols) {
+            const StagePlan in = stored_axes_stage(b->plans[i].a, jobs[i], jobs[i].orientation);
+            StagePlan probe = in;  // as the tensor-core kernel would see it (behind the colour pass when grayscale is asked for)
+            if (probe.color_op == COLOR_GRAY) { probe.color_op = COLOR_NONE; probe.c_mem = probe.c; probe.src_is_input = false; probe.in_pitch = uint32_t(align_up(size_t(probe.in_w) * probe.c, 16)); }
+            // only where the stage on the stored image keeps the tensor-core kernels (rows on a 16-byte stride: the oriented
+            // scratch image of the orientation pass always has them, a caller's device batch may not)
+            if (fused_tc_eligible(probe, jobs[i])) {
+                late[i] = 1;
+                late_a[i] = b->plans[i].a;
+                b->plans[i].a = in;
+                b->plans[i].pre.present = false;  // no orientation pass over the source
+                ej[i] = jobs[i];
+                ej[i].orientation = 0;
+            }
+        }
         const JobPlan &p = b->plans[i];
         for (const auto &t : {p.a.vtab, p.a.htab, p.b.vtab, p.b.htab})
             if (t) gen->keep.insert(t);
@@ -434,13 +457,17 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             const JobPlan &p = b->plans[i];
             if (a_pre[i].present) js[i].pre = align_up(size_t(a_pre[i].in_pitch) * a_pre[i].in_h, 256);
             if (p.pre.present) js[i].pre = align_up(size_t(p.pre.job.src_pitch) * p.pre.job.src_h, 256);
-            if (p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_pitch) * p.a.canvas_h, 256);
+            if (late[i]) {  // the stored-axes stage's plain output, and its oriented copy where a compose step follows
+                js[i].lor = align_up(size_t(p.a.n_cols) * p.a.n_rows * p.a.c, 256);
+                if (p.a.present && p.b.present) js[i].inter = align_up(size_t(late_a[i].canvas_pitch) * late_a[i].canvas_h, 256);
+            }
+            if (!late[i] && p.a.present && p.b.present) js[i].inter = align_up(size_t(p.a.canvas_pitch) * p.a.canvas_h, 256);
             size_t ta = 0, tb = 0;
             if (p.a.present && p.a.separable && !fused_a[i] && !gather_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
             if (p.b.present && !tc_b[i]) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of the two-kernel blur paths
             js[i].tmp = align_up(std::max(ta, tb), 256);
             if (p.post_c_in) js[i].fin = align_up(size_t(p.pub.out_w) * p.pub.out_h * p.post_c_in, 256);  // the final image before to_rgb8
-            const size_t need = js[i].pre + js[i].inter + js[i].tmp + js[i].fin;
+            const size_t need = js[i].pre + js[i].inter + js[i].tmp + js[i].fin + js[i].lor;
             if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
                 chunk_end.push_back(i);
                 cur = 0;
@@ -449,6 +476,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             js[i].inter_off = cur + js[i].pre;
             js[i].tmp_off = cur + js[i].pre + js[i].inter;
             js[i].fin_off = js[i].tmp_off + js[i].tmp;
+            js[i].lor_off = js[i].fin_off + js[i].fin;
             cur += need;
             scratch_bytes = std::max(scratch_bytes, cur);
         }
@@ -460,6 +488,12 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         if (b->plans[i].pre.present) ej[i].src = static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off;
     for (uint32_t i = 0; i < n_jobs; i++)  // FANLIN_TO_RGB8: the stages write the final image to scratch, a last pass converts it into dst
         if (b->plans[i].post_c_in) ej[i].dst = static_cast<uint8_t *>(b->d_scratch) + js[i].fin_off;
+
+    // where stage A of job i writes: its scratch image when the orientation follows, the canvas in front of the blur, the output
+    auto a_dst = [&](uint32_t i) -> uint8_t * {
+        if (late[i]) return static_cast<uint8_t *>(b->d_scratch) + js[i].lor_off;
+        return b->plans[i].b.present ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : ej[i].dst;
+    };
 
     // 3. descriptors per chunk and stage kind
     std::vector<StageDesc> descs;
@@ -528,7 +562,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const bool pre = a_pre[i].present;
                 const uint8_t *tsrc = pre ? static_cast<const uint8_t *>(b->d_scratch) + js[i].pre_off : ej[i].src;
                 const uint32_t pitch = pre ? a_pre[i].in_pitch : ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
-                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, p.b.present ? inter : ej[i].dst, tcache_p, &ftabs,
+                const int rc = fused_tc_build(pre ? a_pre[i] : p.a, ej[i], tsrc, pitch, a_dst(i), tcache_p, &ftabs,
                                               &tctabs, &tcitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: tensor-core tables"); return rc; }
             }
@@ -543,7 +577,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 const JobPlan &p = b->plans[i];
                 uint8_t *inter = js[i].inter ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : nullptr;
                 const uint32_t pitch = ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels;
-                const int rc = fused_build(p.a, ej[i].src, pitch, p.b.present ? inter : ej[i].dst, fcache_p, &ftabs, &fitems);
+                const int rc = fused_build(p.a, ej[i].src, pitch, a_dst(i), fcache_p, &ftabs, &fitems);
                 if (rc != FANLIN_OK) { set_error("fanlin: internal: fused tables"); return rc; }
             }
             hs.n_items = uint32_t(fitems.size() - hs.first);
@@ -551,6 +585,48 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (hs.n_items) hsteps.push_back(hs);
         }
         for (int pass = 0; pass < 3; pass++) {  // 0: A separable (generic), 1: A compose, 2: B separable
+            if (pass == 2) {
+                // orientation after the resample: the stored-axes stage's small image turned into the oriented one -- by the
+                // orientation pass straight onto the canvas where the oriented stage's epilogue is plain, else by a compose step
+                // that reads its source through the orientation (letterbox / to_rgba8 in the same kernel)
+                HostStep ho{6, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+                for (uint32_t i = begin; i < end; i++) {
+                    if (!late[i] || late_a[i].epi != EPI_PLAIN) continue;
+                    const JobPlan &p = b->plans[i];
+                    const StagePlan &oa = late_a[i];
+                    uint8_t *lo = static_cast<uint8_t *>(b->d_scratch) + js[i].lor_off;
+                    uint8_t *final_dst = p.b.present ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : ej[i].dst;
+                    const uint32_t cpitch = oa.canvas_pitch ? oa.canvas_pitch : oa.canvas_w * oa.c_out;
+                    StageDesc d;
+                    std::memset(&d, 0, sizeof(d));
+                    d.src = lo; d.src_pitch = p.a.n_cols * p.a.c; d.src_w = p.a.n_cols; d.src_h = p.a.n_rows;
+                    d.c_mem = d.c = d.c_out = p.a.c; d.color_op = COLOR_NONE; d.orient = jobs[i].orientation;
+                    d.v_tab = d.h_tab = NO_TABLE;
+                    d.oy0 = 0; d.n_rows = oa.n_rows; d.ox0 = 0; d.n_cols = oa.n_cols; d.canvas_w = oa.n_cols; d.canvas_h = oa.n_rows; d.epi = EPI_PLAIN;
+                    d.dst = final_dst + size_t(oa.dst_y) * cpitch + size_t(oa.dst_x) * oa.c_out;
+                    d.dst_pitch = cpitch;
+                    geom_add(&ho.g, d);
+                    descs.push_back(d);
+                }
+                if (ho.g.n_jobs) hsteps.push_back(ho);
+                HostStep hc{1, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+                for (uint32_t i = begin; i < end; i++) {
+                    if (!late[i] || late_a[i].epi == EPI_PLAIN) continue;
+                    const JobPlan &p = b->plans[i];
+                    StagePlan cs = late_a[i];  // the oriented stage's canvas, placement, epilogue and fill; its input is the oriented small image
+                    cs.separable = false; cs.src_is_input = false; cs.vtab = nullptr; cs.htab = nullptr; cs.color_op = COLOR_NONE;
+                    cs.in_w = p.a.n_cols; cs.in_h = p.a.n_rows; cs.c_mem = cs.c = p.a.c; cs.in_pitch = p.a.n_cols * p.a.c;  // the small image as stored
+                    cs.ox0 = cs.oy0 = 0; cs.sx0 = cs.sy0 = 0; cs.n_sx = cs.n_cols; cs.n_sy = cs.n_rows;
+                    uint8_t *lo = static_cast<uint8_t *>(b->d_scratch) + js[i].lor_off;
+                    StageDesc d;
+                    fill_desc(&d, cs, ej[i], lo, nullptr, tab_base, true);
+                    d.orient = jobs[i].orientation;
+                    d.dst = p.b.present ? static_cast<uint8_t *>(b->d_scratch) + js[i].inter_off : ej[i].dst;
+                    geom_add(&hc.g, d);
+                    descs.push_back(d);
+                }
+                if (hc.g.n_jobs) hsteps.push_back(hc);
+            }
             HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
             for (uint32_t i = begin; i < end; i++) {
                 const JobPlan &p = b->plans[i];
@@ -564,6 +640,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 StageDesc d;
                 const bool last = pass == 2 || !p.b.present;
                 fill_desc(&d, s, ej[i], inter, tmp, tab_base, last);
+                if (pass < 2 && late[i]) d.dst = a_dst(i);
                 geom_add(&hs.g, d);
                 descs.push_back(d);
             }

@@ -26,6 +26,9 @@ CONFIGS = [
     # EXIF orientation on the device (stored portrait 1080x1920 shown as 1920x1080)
     ("C2 stored rotated, EXIF 6 (rotate 90)", 1920, 1080, 3, "w=300&h=200", False, 592, 6),
     ("C2 EXIF 3 (rotate 180)", 1080, 1920, 3, "w=300&h=200", False, 592, 3),
+    # rows on a 16-byte stride (what fanlin_run's device staging gives every image): the orientation moves behind the resample
+    ("C2-like stored rotated 1072x1920, EXIF 6, 16-byte rows", 1920, 1072, 3, "w=300&h=200", False, 592, 6),
+    ("C2-like stored 1072x1920 unrotated", 1920, 1072, 3, "w=200&h=300", False, 592, 1),
 ]
 
 
