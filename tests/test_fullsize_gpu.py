@@ -206,3 +206,23 @@ def test_inverse_rides_on_the_vertical_pass(fanlin, c):
         assert np.array_equal(dst.cpu().numpy(), got)
     finally:
         d.close()
+
+
+@pytest.mark.parametrize("exif,h,w,c,qs,kw", [
+    (6, 1920, 1080, 3, "w=300&h=200", dict(w=300, h=200)),                                                  # C2 stored rotated (a phone's portrait frame)
+    (3, 1080, 1920, 3, "w=300&h=200&rgb=1,2,3", dict(w=300, h=200, rgb=(1, 2, 3))),
+    (8, 2160, 3840, 4, "w=1000&h=1618&crop=true&blur=10", dict(w=1000, h=1618, crop=True, blur=10.0)),       # odd crop difference, mirrored axis
+    (5, 1500, 2001, 3, "w=333&h=251&crop=true&grayscale=true", dict(w=333, h=251, crop=True, grayscale=True)),
+    (7, 1001, 1333, 4, "w=400&h=300&inverse=true", dict(w=400, h=300, inverse=True)),
+    (2, 1080, 1920, 1, "w=301&h=170&crop=true", dict(w=301, h=170, crop=True)),
+    (4, 777, 1234, 2, "w=200&h=200", dict(w=200, h=200)),
+])
+def test_orientation_behind_the_resample_full_size(fanlin, dev, exif, h, w, c, qs, kw):
+    """EXIF orientation 2..8 at BASELINE sizes: on the fast paths the Lanczos3 stage runs on the image as stored and the small
+    output is oriented (plan.h stored_axes_stage); the oracle orients first (handler.rs:221-223)."""
+    img = synth_image(600 + exif + (7 - (600 + exif) % 8 if c in (2, 4) else 0), h, w, c)
+    want = O.process(img, orientation=exif, **kw)
+    got = fanlin.process_image(dev, img, fanlin.Query(qs), orientation=exif)
+    hh = hist(got, want)
+    assert got.shape == want.shape and hh[">=2"] == 0, (exif, hh)
+    assert hh[1] <= max(64, got.size // 100), hh
