@@ -341,7 +341,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     // it has grown past a bound; batches in flight keep their TableBuf.
     std::unique_lock<std::mutex> tab_lock(dev->tab_mu);
     const bool allow_hmma = ctx->cfg.vertical_path == 3 || ctx->cfg.vertical_path == 0;  // both Lanczos3 passes on the tensor cores where the geometry allows
-    if (!dev->gen || dev->gen->host_bytes() > (size_t(768) << 20)) dev->gen = std::make_shared<TableGen>(allow_hmma);
+    // (FANLIN_TABLE_GEN_LIMIT_MB: the bound, for tests of the roll-over)
+    static const size_t gen_limit = [] { const char *e = std::getenv("FANLIN_TABLE_GEN_LIMIT_MB"); const long v = e ? std::atol(e) : 0; return size_t(v > 0 ? v : 768) << 20; }();
+    if (!dev->gen || dev->gen->host_bytes() > gen_limit) dev->gen = std::make_shared<TableGen>(allow_hmma);
     std::shared_ptr<TableGen> gen = dev->gen;
     FusedCache *const fcache_p = gen->fcache;
     FusedTables &ftabs = gen->ftabs;

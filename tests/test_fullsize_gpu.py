@@ -226,3 +226,45 @@ def test_orientation_behind_the_resample_full_size(fanlin, dev, exif, h, w, c, q
     hh = hist(got, want)
     assert got.shape == want.shape and hh[">=2"] == 0, (exif, hh)
     assert hh[1] <= max(64, got.size // 100), hh
+
+
+def test_table_generation_rolls_over(fanlin):
+    """The per-device table generation is REPLACED, never edited, once it has grown past its bound (768 MB; 4 MB here through
+    FANLIN_TABLE_GEN_LIMIT_MB, read once per process -- so this runs in a process of its own): geometries keep working
+    across the roll-over, results stay what a fresh context gives, and batches prepared before it still launch from the
+    tables they were built with."""
+    import os
+    import subprocess
+    import sys
+
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import __graft_entry__ as G
+from synth import synth_image
+import torch
+pkg = G.load_package()
+d = pkg.Device([0])
+ref = pkg.Device([0])
+img = synth_image(5, 1080, 1920, 3)
+src = torch.from_numpy(img).cuda(); dst = torch.zeros((200, 300, 4), dtype=torch.uint8, device='cuda')
+j = pkg.make_job(img, pkg.Query('w=300&h=200')); j.src, j.dst, j.dst_capacity = src.data_ptr(), dst.data_ptr(), 240000
+torch.cuda.synchronize()
+old_batch = d.prepare([j], 0)   # holds the first generation's device tables
+t_prev, rolled = 0, 0
+for k in range(12):             # ~1 MB of tiles per geometry: the 4 MB bound is passed several times
+    q = pkg.Query(f'w={300 + 4 * k}&h=200')
+    a = pkg.process_image(d, img, q)
+    t = d.stats()['table_bytes']
+    assert t > t_prev, 'a new geometry must upload tables'
+    t_prev = t
+    assert np.array_equal(a, pkg.process_image(ref, img, q)), k
+old_batch.launch(None); torch.cuda.synchronize()
+assert np.array_equal(dst.cpu().numpy(), pkg.process_image(ref, img, pkg.Query('w=300&h=200')))
+old_batch.free(); d.close(); ref.close()
+print('ROLLOVER_OK')
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FANLIN_TABLE_GEN_LIMIT_MB="4")
+    r = subprocess.run([sys.executable, "-c", code % (root, os.path.join(root, "tests"))], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ROLLOVER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
