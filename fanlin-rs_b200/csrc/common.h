@@ -10,6 +10,13 @@ enum ColorOp : uint32_t { COLOR_NONE = 0, COLOR_GRAY = 1, COLOR_INVERT = 2 };
 enum Epilogue : uint32_t { EPI_PLAIN = 0, EPI_BLEND_FILL = 1, EPI_TO_RGBA = 2 };
 enum FilterKind : uint32_t { KIND_NEAREST = 0, KIND_LANCZOS3 = 1, KIND_GAUSSIAN = 100 };
 
+// Subpixel types (enum fanlin_sample) and their size in bytes.
+enum Sample : uint32_t { SAMPLE_U8 = 0, SAMPLE_U16 = 1, SAMPLE_F32 = 2 };
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t sample_bytes(uint32_t s) { return s == SAMPLE_U8 ? 1u : s == SAMPLE_U16 ? 2u : 4u; }
+
 // One entry of an axis table: output index o reads source [left, left+count) with
 // weights tab_w[woff .. woff+count).
 struct TapEntry {
@@ -40,6 +47,7 @@ struct StageDesc {
     uint32_t fill;          // r | g<<8 | b<<16 | 255<<24
     uint32_t v_max_taps, h_max_taps;
     uint32_t orient;        // orientation pass only: EXIF orientation (2..8) of the stored image
+    uint32_t s_in, s_out;   // subpixel types at src and dst (Sample); everything but the kernels of kernels_deep.cu sees u8 only
 };
 
 }  // namespace fanlin

@@ -46,6 +46,12 @@ struct LaunchGeom {
 // intermediate in HBM, then horizontal pass + epilogue.  Returns kernels launched.
 int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const float *d_w, const LaunchGeom &g,
                      LaunchCtx &lc);
+// The same stages for 16-bit / f32 subpixels (kernels_deep.cu): separable stage in the crate's operation order, compose-only
+// stage, orientation pass, to_rgb8 -- StageDesc::s_in / s_out name the subpixel types.
+int launch_sep_deep(const StageDesc *d_descs, const TapEntry *d_tab, const float *d_w, const LaunchGeom &g, LaunchCtx &lc);
+int launch_compose_deep(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+int launch_orient_deep(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
+int launch_to_rgb8_deep(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc);
 // Fused separable resample (kernels_fused.cu); items of one (c, c_mem, colour op) variant.
 struct FusedItem;
 int launch_fused(const FusedItem *d_items, uint32_t n_items, uint32_t variant, uint32_t max_band_rows,

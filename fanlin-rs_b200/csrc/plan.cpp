@@ -225,17 +225,19 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
     if (job.orientation >= 2) {
         // Orientation::from_exif + apply_orientation: 5..8 swap width and height.  Plan the request as it
         // looks behind the orientation pass, which also applies the colour op.
-        if (job.src_w == 0 || job.src_h == 0 || job.src_channels < 1 || job.src_channels > 4) {
+        if (job.src_w == 0 || job.src_h == 0 || job.src_channels < 1 || job.src_channels > 4 || job.src_sample > SAMPLE_F32) {
             set_error("fanlin: bad source image");
             return FANLIN_EINVAL;
         }
+        if (reinterpret_cast<uintptr_t>(job.src) % sample_bytes(job.src_sample) != 0) { set_error("fanlin: src / dst not aligned to the subpixel size"); return FANLIN_EINVAL; }
         OrientPlan pre;
         pre.present = true;
         pre.orient = job.orientation;
         pre.c_mem = pre.c = job.src_channels;
+        pre.sample = job.src_sample;
         pre.color_op = COLOR_NONE;
-        if (job.flags & FANLIN_GRAYSCALE) {
-            if (job.src_channels >= 3) { pre.color_op = COLOR_GRAY; pre.c = job.src_channels - 2; }
+        if (job.flags & FANLIN_GRAYSCALE) {  // (Rgb32F / Rgba32F keep their channels: the luma is replicated)
+            if (job.src_channels >= 3) { pre.color_op = COLOR_GRAY; pre.c = job.src_sample == SAMPLE_F32 ? job.src_channels : job.src_channels - 2; }
         } else if (job.flags & FANLIN_INVERSE) {
             pre.color_op = COLOR_INVERT;
         }
@@ -245,20 +247,25 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
         ej.flags &= ~uint32_t(FANLIN_GRAYSCALE | FANLIN_INVERSE);
         if (job.orientation >= 5) { ej.src_w = job.src_h; ej.src_h = job.src_w; }
         ej.src_channels = pre.c;
-        ej.src_pitch = (ej.src_w * pre.c + 15u) & ~15u;
+        ej.src_pitch = (ej.src_w * pre.c * sample_bytes(pre.sample) + 15u) & ~15u;
         ej.src = nullptr;
         const int rc = plan_job(ej, out, with_tables);
         if (rc != FANLIN_OK) return rc;
         out->pre = pre;
         out->pub.stages |= pre.color_op != COLOR_NONE ? 1u : 0u;
-        out->pub.algorithmic_bytes = uint64_t(out->pub.src_x1 - out->pub.src_x0) * (out->pub.src_y1 - out->pub.src_y0) * job.src_channels + out->pub.out_bytes;
+        out->pub.algorithmic_bytes = uint64_t(out->pub.src_x1 - out->pub.src_x0) * (out->pub.src_y1 - out->pub.src_y0) * job.src_channels * sample_bytes(pre.sample) + out->pub.out_bytes;
         return FANLIN_OK;
     }
     JobPlan p;
     const uint32_t W = job.src_w, H = job.src_h, c0 = job.src_channels;
     if (W == 0 || H == 0) { set_error("fanlin: empty source image"); return FANLIN_EINVAL; }
-    if (c0 < 1 || c0 > 4) { set_error("fanlin: src_channels must be 1..4 (u8 L/La/Rgb/Rgba)"); return FANLIN_EINVAL; }
-    if (job.src_pitch != 0 && job.src_pitch < W * c0) { set_error("fanlin: src_pitch smaller than a row"); return FANLIN_EINVAL; }
+    if (c0 < 1 || c0 > 4) { set_error("fanlin: src_channels must be 1..4 (L/La/Rgb/Rgba)"); return FANLIN_EINVAL; }
+    const uint32_t s0 = job.src_sample;
+    if (s0 > SAMPLE_F32) { set_error("fanlin: src_sample must be 0 (u8), 1 (u16) or 2 (f32)"); return FANLIN_EINVAL; }
+    if (s0 == SAMPLE_F32 && c0 < 3) { set_error("fanlin: f32 images are Rgb32F or Rgba32F (src_channels 3 or 4)"); return FANLIN_EINVAL; }
+    const uint32_t bp0 = sample_bytes(s0);
+    if (job.src_pitch != 0 && (job.src_pitch < W * c0 * bp0 || job.src_pitch % bp0 != 0)) { set_error("fanlin: src_pitch smaller than a row (or not a multiple of the subpixel size)"); return FANLIN_EINVAL; }
+    if (s0 != SAMPLE_U8 && (reinterpret_cast<uintptr_t>(job.src) % bp0 != 0 || reinterpret_cast<uintptr_t>(job.dst) % bp0 != 0)) { set_error("fanlin: src / dst not aligned to the subpixel size"); return FANLIN_EINVAL; }
     if (job.filter != FANLIN_FILTER_NEAREST && job.filter != FANLIN_FILTER_LANCZOS3) {
         set_error("fanlin: unknown filter");
         return FANLIN_EINVAL;
@@ -269,7 +276,7 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
     // handler.rs:224-228 -- grayscale wins over inverse
     uint32_t op = COLOR_NONE, c1 = c0;
     if (job.flags & FANLIN_GRAYSCALE) {
-        if (c0 >= 3) { op = COLOR_GRAY; c1 = c0 - 2; }
+        if (c0 >= 3) { op = COLOR_GRAY; c1 = s0 == SAMPLE_F32 ? c0 : c0 - 2; }  // grayscale_with_type: Rgb32F / Rgba32F keep their type
     } else if (job.flags & FANLIN_INVERSE) {
         op = COLOR_INVERT;
     }
@@ -319,7 +326,7 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
     pub.overlay_y = ov_y;
     pub.stages = (op != COLOR_NONE ? 1u : 0u) | (resample ? 2u : 0u) | (letterbox ? 4u : 0u) | (blur ? 8u : 0u) | (want_rgba ? 16u : 0u);
 
-    uint32_t img_w = cur_w, img_h = cur_h, img_c = c1;  // running image description
+    uint32_t img_w = cur_w, img_h = cur_h, img_c = c1, img_s = s0;  // running image description
     const bool subrect = !resample && (cur_w != W || cur_h != H);
     StagePlan &a = p.a;
     const bool need_a = resample || letterbox || subrect || !blur;
@@ -328,6 +335,7 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
         a.separable = resample;
         a.src_is_input = true;
         a.in_w = W; a.in_h = H; a.c_mem = c0; a.c = c1; a.color_op = op;
+        a.s_in = a.s_out = s0;
         a.v_kind = a.h_kind = kind;
         a.v_out = full_h; a.h_out = full_w;
         a.oy0 = ry; a.n_rows = cur_h; a.ox0 = rx; a.n_cols = cur_w;
@@ -337,9 +345,10 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
             a.n_cols = std::min(a.n_cols, a.canvas_w - std::min(a.dst_x, a.canvas_w));
             a.n_rows = std::min(a.n_rows, a.canvas_h - std::min(a.dst_y, a.canvas_h));
             img_w = a.canvas_w; img_h = a.canvas_h; img_c = 4;
+            a.s_out = img_s = SAMPLE_U8;  // the canvas is Rgba<u8> whatever the image (handler.rs:240)
         } else {
             a.canvas_w = cur_w; a.canvas_h = cur_h; a.dst_x = a.dst_y = 0;
-            if (want_rgba && !blur) { a.epi = EPI_TO_RGBA; a.c_out = 4; img_c = 4; }
+            if (want_rgba && !blur) { a.epi = EPI_TO_RGBA; a.c_out = 4; img_c = 4; a.s_out = img_s = SAMPLE_U8; }
             else { a.epi = EPI_PLAIN; a.c_out = c1; }
         }
         if (resample) {
@@ -366,29 +375,33 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
         b.in_w = img_w; b.in_h = img_h;
         if (a.present) { b.c_mem = img_c; b.c = img_c; b.color_op = COLOR_NONE; }
         else { b.c_mem = c0; b.c = c1; b.color_op = op; img_c = c1; }
+        b.s_in = b.s_out = img_s;
         b.v_kind = b.h_kind = KIND_GAUSSIAN;
         b.sigma = job.blur_sigma;
         b.v_out = img_h; b.h_out = img_w;
         b.oy0 = 0; b.n_rows = img_h; b.ox0 = 0; b.n_cols = img_w;
         b.sx0 = 0; b.n_sx = img_w; b.sy0 = 0; b.n_sy = img_h;
         b.canvas_w = img_w; b.canvas_h = img_h; b.dst_x = b.dst_y = 0;
-        if (want_rgba) { b.epi = EPI_TO_RGBA; b.c_out = 4; img_c = 4; }
+        if (want_rgba) { b.epi = EPI_TO_RGBA; b.c_out = 4; img_c = 4; b.s_out = img_s = SAMPLE_U8; }
         else { b.epi = EPI_PLAIN; b.c_out = b.c; }
         if (with_tables) {
             b.vtab = build_axis_table(KIND_GAUSSIAN, b.sigma, img_h, img_h);
             b.htab = build_axis_table(KIND_GAUSSIAN, b.sigma, img_w, img_w);
         }
     }
-    if ((job.flags & FANLIN_TO_RGB8) && img_c != 3) {  // DynamicImage::to_rgb8 as a last pass over the (small) output
+    if ((job.flags & FANLIN_TO_RGB8) && (img_c != 3 || img_s != SAMPLE_U8)) {  // DynamicImage::to_rgb8 as a last pass over the (small) output
         p.post_c_in = img_c;
+        p.post_s_in = img_s;
         img_c = 3;
+        img_s = SAMPLE_U8;
         pub.stages |= 32u;
     }
     pub.out_w = img_w;
     pub.out_h = img_h;
     pub.out_channels = img_c;
-    pub.out_bytes = uint64_t(img_w) * img_h * img_c;
-    pub.algorithmic_bytes = uint64_t(pub.src_x1 - pub.src_x0) * (pub.src_y1 - pub.src_y0) * c0 + pub.out_bytes;
+    pub.out_sample = img_s;
+    pub.out_bytes = uint64_t(img_w) * img_h * img_c * sample_bytes(img_s);
+    pub.algorithmic_bytes = uint64_t(pub.src_x1 - pub.src_x0) * (pub.src_y1 - pub.src_y0) * c0 * bp0 + pub.out_bytes;
     *out = std::move(p);
     return FANLIN_OK;
 }

@@ -42,6 +42,7 @@ struct StagePlan {
     bool src_is_input = true;  // else reads the previous stage's canvas
     uint32_t in_pitch = 0;     // bytes per row of that canvas when it is not tightly packed (0: in_w * c_mem)
     uint32_t in_w = 0, in_h = 0, c_mem = 0, c = 0, color_op = COLOR_NONE;
+    uint32_t s_in = SAMPLE_U8, s_out = SAMPLE_U8;  // subpixel type read / written (u16 / f32 stages take the kernels of kernels_deep.cu)
     uint32_t v_kind = 0, h_kind = 0;
     float sigma = 0.f;
     uint32_t v_out = 0, h_out = 0;  // full filtered size (table n_out) per axis
@@ -59,6 +60,7 @@ struct OrientPlan {
     bool present = false;
     uint32_t orient = 0;                    // 2..8
     uint32_t c_mem = 0, c = 0, color_op = 0;  // the stored image's channels, after the colour op, the op
+    uint32_t sample = SAMPLE_U8;            // subpixel type of the stored and of the oriented image
     fanlin_job job{};                       // oriented size, c channels, 16-byte aligned pitch, no colour flags; src unset
 };
 
@@ -66,6 +68,7 @@ struct JobPlan {
     fanlin_plan pub{};
     OrientPlan pre;
     uint32_t post_c_in = 0;  // FANLIN_TO_RGB8: channels of the final image before to_rgb8 (0: no conversion pass)
+    uint32_t post_s_in = SAMPLE_U8;  // ... and its subpixel type
     StagePlan a;  // colour op + resample + letterbox (+ to_rgba8), or compose
     StagePlan b;  // blur
 };

@@ -263,11 +263,12 @@ void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t 
     std::memset(d, 0, sizeof(*d));
     if (s.src_is_input) {
         d->src = job.src;
-        d->src_pitch = job.src_pitch ? job.src_pitch : job.src_w * job.src_channels;
+        d->src_pitch = job.src_pitch ? job.src_pitch : job.src_w * job.src_channels * sample_bytes(job.src_sample);
     } else {
         d->src = inter;
-        d->src_pitch = s.in_pitch ? s.in_pitch : s.in_w * s.c_mem;
+        d->src_pitch = s.in_pitch ? s.in_pitch : s.in_w * s.c_mem * sample_bytes(s.s_in);
     }
+    d->s_in = s.s_in; d->s_out = s.s_out;
     d->dst = last_stage ? job.dst : inter;
     d->tmp = tmp;
     d->src_w = s.in_w; d->src_h = s.in_h;
@@ -279,7 +280,7 @@ void fill_desc(StageDesc *d, const StagePlan &s, const fanlin_job &job, uint8_t 
     d->oy0 = s.oy0; d->n_rows = s.n_rows; d->ox0 = s.ox0; d->n_cols = s.n_cols;
     d->sx0 = s.sx0; d->n_sx = s.n_sx; d->sy0 = s.sy0; d->n_sy = s.n_sy;
     d->tmp_pitch = s.n_sx * s.c;
-    d->dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out; d->c_out = s.c_out;
+    d->dst_pitch = s.canvas_pitch ? s.canvas_pitch : s.canvas_w * s.c_out * sample_bytes(s.s_out); d->c_out = s.c_out;
     d->canvas_w = s.canvas_w; d->canvas_h = s.canvas_h;
     d->dst_x = s.dst_x; d->dst_y = s.dst_y; d->epi = s.epi; d->fill = s.fill;
 }
@@ -359,6 +360,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     FusedTcCache *const tcache_p = gen->tcache;
     FusedTcTables &tctabs = gen->tctabs;
     const bool use_tc = ctx->cfg.vertical_path != 1;  // 2: tensor-core vertical pass, CUDA-core horizontal stage
+    // 16-bit / f32 subpixels (fanlin_job.src_sample): the stages that read them take the generic kernels of kernels_deep.cu
+    // (crate operation order); a blur behind a letterbox reads the Rgba<u8> canvas and is an ordinary u8 stage
+    std::vector<uint8_t> deep_a(n_jobs, 0), deep_b(n_jobs, 0);
     std::vector<uint8_t> fast_b(n_jobs, 0);  // stage B takes the fast blur kernels
     std::vector<uint8_t> tc_b(n_jobs, 0);    // ... both passes on the tensor cores, no f32 intermediate (kernels_blur_tc.cu)
     BlurTables &btabs = gen->btabs;
@@ -384,7 +388,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         if (b->plans[i].pre.present) ej[i] = b->plans[i].pre.job;  // src: its scratch image, set once the scratch is laid out
         if (b->plans[i].a.present && b->plans[i].b.present) {  // the canvas between the stages: rows on a 16-byte stride (TMA reads it)
             StagePlan &sa = b->plans[i].a;
-            sa.canvas_pitch = uint32_t(align_up(size_t(sa.canvas_w) * sa.c_out, 16));
+            sa.canvas_pitch = uint32_t(align_up(size_t(sa.canvas_w) * sa.c_out * sample_bytes(sa.s_out), 16));
             b->plans[i].b.in_pitch = sa.canvas_pitch;
         }
         if (!jobs[i].src || !jobs[i].dst) { set_error("fanlin: null src or dst"); return FANLIN_EINVAL; }
@@ -393,7 +397,9 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             return FANLIN_ECAPACITY;
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
-        if (late_orient_on && !exact && use_tc && b->plans[i].pre.present && b->plans[i].a.present && b->plans[i].a.separable &&
+        deep_a[i] = b->plans[i].a.present && b->plans[i].a.s_in != SAMPLE_U8;
+        deep_b[i] = b->plans[i].b.present && b->plans[i].b.s_in != SAMPLE_U8;
+        if (late_orient_on && !exact && use_tc && jobs[i].src_sample == SAMPLE_U8 && b->plans[i].pre.present && b->plans[i].a.present && b->plans[i].a.separable &&
             b->plans[i].a.v_kind == KIND_LANCZOS3 && b->plans[i].a.n_rows && b->plans[i].a.n_cols) {
             const StagePlan in = stored_axes_stage(b->plans[i].a, jobs[i], jobs[i].orientation);
             StagePlan probe = in;  // as the tensor-core kernel would see it (behind the colour pass when grayscale is asked for)
@@ -413,8 +419,8 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         for (const auto &t : {p.a.vtab, p.a.htab, p.b.vtab, p.b.htab})
             if (t) gen->keep.insert(t);
         fused_a[i] = 0;
-        gather_a[i] = p.a.present && p.a.separable && p.a.v_kind == KIND_NEAREST && p.a.h_kind == KIND_NEAREST;  // one tap per output: a gather
-        if (!exact && use_tc && !gather_a[i]) {
+        gather_a[i] = !deep_a[i] && p.a.present && p.a.separable && p.a.v_kind == KIND_NEAREST && p.a.h_kind == KIND_NEAREST;  // one tap per output: a gather
+        if (!exact && use_tc && !gather_a[i] && !deep_a[i]) {
             // (inverse rides on the vertical pass of the both-passes kernels only: the kernel with the CUDA-core horizontal
             // stage keeps the colour pass in front of it)
             if (fused_tc_eligible(p.a, ej[i]) && fused_tc_geometry_ok(p.a, tcache_p, &ftabs, &tctabs) &&
@@ -434,16 +440,16 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 }
             }
         }
-        if (!fused_a[i] && !gather_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache_p, &ftabs);
+        if (!fused_a[i] && !gather_a[i] && !deep_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache_p, &ftabs);
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
-        fast_b[i] = !exact && blur_eligible(p.b);
+        fast_b[i] = !exact && !deep_b[i] && blur_eligible(p.b);
         if (fast_b[i] && use_tc && ctx->cfg.blur_path != 1) {
             // rows of the blur's input: the caller's image, or scratch (orientation pass / the canvas of stage A: 256-byte
             // aligned blocks, rows on a 16-byte stride)
             const bool from_caller = p.b.src_is_input && !p.pre.present;
             const uint8_t *bsrc = from_caller ? jobs[i].src : nullptr;
             const uint32_t bpitch = p.b.src_is_input ? (ej[i].src_pitch ? ej[i].src_pitch : ej[i].src_w * ej[i].src_channels)
-                                                     : (p.b.in_pitch ? p.b.in_pitch : p.b.in_w * p.b.c);
+                                                     : (p.b.in_pitch ? p.b.in_pitch : p.b.in_w * p.b.c);  // (u8 here: fast_b excludes deep_b)
             tc_b[i] = blur_tc_eligible(p.b, bpitch, bsrc);
         }
         if (!fast_b[i]) { add_table(p.b.vtab); add_table(p.b.htab); }
@@ -468,7 +474,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             if (p.a.present && p.a.separable && !fused_a[i] && !gather_a[i]) ta = size_t(p.a.n_rows) * p.a.n_sx * p.a.c * 4;
             if (p.b.present && !tc_b[i]) tb = size_t(p.b.n_rows) * p.b.n_sx * p.b.c * 4;  // f32 intermediate of the two-kernel blur paths
             js[i].tmp = align_up(std::max(ta, tb), 256);
-            if (p.post_c_in) js[i].fin = align_up(size_t(p.pub.out_w) * p.pub.out_h * p.post_c_in, 256);  // the final image before to_rgb8
+            if (p.post_c_in) js[i].fin = align_up(size_t(p.pub.out_w) * p.pub.out_h * p.post_c_in * sample_bytes(p.post_s_in), 256);  // the final image before to_rgb8
             const size_t need = js[i].pre + js[i].inter + js[i].tmp + js[i].fin + js[i].lor;
             if (cur && cur + need > ctx->cfg.device_scratch_bytes) {
                 chunk_end.push_back(i);
@@ -518,15 +524,17 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             }
         }
         {  // orientation passes: the stored image turned (and its colour op applied) into scratch, in front of everything
-            HostStep hs{6, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+          for (int deep = 0; deep < 2; deep++) {  // (the passes of 16-bit / f32 images: kind 12)
+            HostStep hs{deep ? 12 : 6, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
             for (uint32_t i = begin; i < end; i++) {
                 const JobPlan &p = b->plans[i];
-                if (!p.pre.present) continue;
+                if (!p.pre.present || (p.pre.sample != SAMPLE_U8) != (deep != 0)) continue;
                 StageDesc d;
                 std::memset(&d, 0, sizeof(d));
                 d.src = jobs[i].src;
-                d.src_pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels;
+                d.src_pitch = jobs[i].src_pitch ? jobs[i].src_pitch : jobs[i].src_w * jobs[i].src_channels * sample_bytes(jobs[i].src_sample);
                 d.src_w = jobs[i].src_w; d.src_h = jobs[i].src_h;
+                d.s_in = d.s_out = p.pre.sample;
                 d.c_mem = p.pre.c_mem; d.c = p.pre.c; d.color_op = p.pre.color_op; d.orient = p.pre.orient;
                 d.v_tab = d.h_tab = NO_TABLE;
                 d.oy0 = p.pub.src_y0; d.n_rows = p.pub.src_y1 - p.pub.src_y0; d.ox0 = 0; d.n_cols = ej[i].src_w;
@@ -536,6 +544,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 descs.push_back(d);
             }
             if (hs.g.n_jobs) hsteps.push_back(hs);
+          }
         }
         {  // colour-op passes in front of the tensor-core resample: the needed source rows, op applied, into scratch
             HostStep hs{5, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
@@ -629,11 +638,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 }
                 if (hc.g.n_jobs) hsteps.push_back(hc);
             }
-            HostStep hs{pass == 1 ? 1 : 0, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+          for (int deep = 0; deep < 2; deep++) {  // (stages on 16-bit / f32 subpixels: kinds 10 / 11)
+            HostStep hs{(pass == 1 ? 1 : 0) + (deep ? 10 : 0), descs.size(), LaunchGeom{}, 0, 0, 0, 0};
             for (uint32_t i = begin; i < end; i++) {
                 const JobPlan &p = b->plans[i];
                 const StagePlan &s = pass == 2 ? p.b : p.a;
                 if (!s.present) continue;
+                if ((pass == 2 ? deep_b[i] : deep_a[i]) != deep) continue;
                 if (pass == 0 && (!s.separable || fused_a[i] || gather_a[i])) continue;
                 if (pass == 1 && s.separable && !gather_a[i]) continue;
                 if (pass == 2 && fast_b[i]) continue;
@@ -647,6 +658,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 descs.push_back(d);
             }
             if (hs.g.n_jobs) hsteps.push_back(hs);
+          }
         }
         // stage B through the fast blur kernels, one launch pair per (channels, sigma); the vertical pass
         // on the tensor cores where the rows allow TMA (16-byte stride), else on the CUDA cores
@@ -711,13 +723,15 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             hsteps.push_back(hs);
         }
         {  // FANLIN_TO_RGB8: the last pass, scratch -> dst
-            HostStep hs{8, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
+          for (int deep = 0; deep < 2; deep++) {
+            HostStep hs{deep ? 13 : 8, descs.size(), LaunchGeom{}, 0, 0, 0, 0};
             for (uint32_t i = begin; i < end; i++) {
                 const JobPlan &p = b->plans[i];
-                if (!p.post_c_in) continue;
+                if (!p.post_c_in || (p.post_s_in != SAMPLE_U8) != (deep != 0)) continue;
                 StageDesc d;
                 std::memset(&d, 0, sizeof(d));
                 d.src = ej[i].dst; d.dst = jobs[i].dst;
+                d.s_in = p.post_s_in; d.s_out = SAMPLE_U8;
                 d.c_mem = p.post_c_in; d.c = 3; d.c_out = 3;
                 d.canvas_w = p.pub.out_w; d.canvas_h = p.pub.out_h;
                 d.v_tab = d.h_tab = NO_TABLE;
@@ -725,6 +739,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 descs.push_back(d);
             }
             if (hs.g.n_jobs) hsteps.push_back(hs);
+          }
         }
         begin = end;
     }
@@ -856,7 +871,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             st.geom = hs.g;
             st.geom.n_jobs = std::min<uint32_t>(65535, hs.g.n_jobs - o);
             b->steps.push_back(st);
-            b->launches_per_run += st.kind == 0 ? 2 : 1;
+            b->launches_per_run += (st.kind == 0 || st.kind == 10) ? 2 : 1;
         }
     }
     *out = b.release();
@@ -890,7 +905,11 @@ extern "C" int fanlin_batch_launch(fanlin_batch *b, void *cuda_stream) {
             const int k = launch_fused(s.items, s.n_items, s.variant, s.max_band, b->d_fw, b->d_finfo, lc);
             if (k < 0) { set_error("fanlin: internal: no fused kernel variant"); return FANLIN_EINVAL; }
             n += k;
-        } else if (s.kind == 8) n += launch_to_rgb8(s.descs, s.geom, lc);
+        } else if (s.kind == 10) n += launch_sep_deep(s.descs, b->d_tab, b->d_w, s.geom, lc);
+        else if (s.kind == 11) n += launch_compose_deep(s.descs, s.geom, lc);
+        else if (s.kind == 12) n += launch_orient_deep(s.descs, s.geom, lc);
+        else if (s.kind == 13) n += launch_to_rgb8_deep(s.descs, s.geom, lc);
+        else if (s.kind == 8) n += launch_to_rgb8(s.descs, s.geom, lc);
         else if (s.kind == 6) n += launch_orient_pass(s.descs, s.geom, lc);
         else if (s.kind == 5) n += launch_color_pass(s.descs, s.geom, lc);
         else if (s.kind == 1) n += launch_compose(s.descs, b->d_tab, s.geom, lc);
@@ -1030,7 +1049,7 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         out_off.clear();
         while (end < n && end - begin < per) {
             // device rows start every 16 bytes whatever the width: the tensor-core path (TMA) needs that stride
-            const size_t ib = align_up(align_up(size_t(jobs[end].src_w) * jobs[end].src_channels, 16) * jobs[end].src_h, 256);
+            const size_t ib = align_up(align_up(size_t(jobs[end].src_w) * jobs[end].src_channels * sample_bytes(jobs[end].src_sample), 16) * jobs[end].src_h, 256);
             if (end > begin && in_bytes + ib > max_bytes) break;
             in_off.push_back(in_bytes);
             out_off.push_back(out_bytes);
@@ -1056,7 +1075,7 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
             std::vector<CopyOp> ops;
             for (uint32_t i = 0; i < m; i++) {
                 const fanlin_job &j = jobs[begin + i];
-                const size_t row = size_t(j.src_w) * j.src_channels;
+                const size_t row = size_t(j.src_w) * j.src_channels * sample_bytes(j.src_sample);
                 const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
                 if (pitch == row && dpitch == row) {
                     ops.push_back(CopyOp{f.h_in + in_off[i], j.src, row * j.src_h});
@@ -1070,7 +1089,7 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
         }
         for (uint32_t i = 0; i < m && rc == FANLIN_OK; i++) {
             const fanlin_job &j = jobs[begin + i];
-            const size_t row = size_t(j.src_w) * j.src_channels;
+            const size_t row = size_t(j.src_w) * j.src_channels * sample_bytes(j.src_sample);
             const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
             const cudaError_t e = stage_in ? cudaSuccess
                                   : pitch == row && dpitch == row

@@ -111,7 +111,7 @@ struct fanlin_batch {
     uint32_t n_jobs = 0;
     std::vector<fanlin::JobPlan> plans;
     struct Step {
-        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores), 4 blur, 5 colour pass, 6 orientation pass, 7 vertical blur (tensor cores), 8 to_rgb8, 9 blur with both passes on the tensor cores
+        int kind;  // 0 separable generic (exact), 1 compose, 2 fused resample, 3 fused resample (tensor cores), 4 blur, 5 colour pass, 6 orientation pass, 7 vertical blur (tensor cores), 8 to_rgb8, 9 blur with both passes on the tensor cores; 10 / 11 / 12 / 13 = 0 / 1 / 6 / 8 for 16-bit and f32 subpixels (kernels_deep.cu)
         const fanlin::BlurItem *blur_items;
         uint32_t max_w, max_h, c, radius, taps_pad;
         const fanlin::FusedTcItem *tc_items;

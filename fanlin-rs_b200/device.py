@@ -11,6 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 FILTER_NEAREST, FILTER_LANCZOS3 = 0, 1
 GRAYSCALE, INVERSE, HAS_DIMS, CROP, TO_RGBA8 = 1, 2, 4, 8, 16
+SAMPLE_U8, SAMPLE_U16, SAMPLE_F32 = 0, 1, 2  # enum fanlin_sample
+SAMPLE_DTYPES = {SAMPLE_U8: np.uint8, SAMPLE_U16: np.uint16, SAMPLE_F32: np.float32}
 
 
 class FanlinError(RuntimeError):
@@ -29,6 +31,7 @@ class Job(C.Structure):
         ("blur_sigma", C.c_float),
         ("dst", C.c_void_p),
         ("dst_capacity", C.c_uint64),
+        ("src_sample", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -41,6 +44,7 @@ class Plan(C.Structure):
         ("src_x0", C.c_uint32), ("src_y0", C.c_uint32), ("src_x1", C.c_uint32), ("src_y1", C.c_uint32),
         ("stages", C.c_uint32),
         ("out_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
+        ("out_sample", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -121,7 +125,7 @@ def lib():
         L.fanlin_query_unsupported_scale_size.argtypes = [P(QueryStruct)]
         L.fanlin_job_from_query.argtypes = [P(QueryStruct), C.c_int, P(Job)]
         L.fanlin_job_from_query.restype = None
-        assert L.fanlin_abi_version() == 1
+        assert L.fanlin_abi_version() == 2
         _lib = L
     return _lib
 

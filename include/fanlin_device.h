@@ -6,9 +6,12 @@
  * repository).  A Rust `extern "C"` block binding exactly these symbols is shown
  * in INTEGRATION.md.  Plain pointers and sizes only; no CUDA or torch types.
  *
- * Pixel buffers are u8, row-major, interleaved channels (1 = L8, 2 = La8,
- * 3 = Rgb8, 4 = Rgba8), i.e. image::ImageBuffer::as_raw() (tight) unless a pitch
- * is given.
+ * Pixel buffers are row-major, interleaved channels (1 = Luma, 2 = LumaA,
+ * 3 = Rgb, 4 = Rgba), i.e. image::ImageBuffer::as_raw() (tight) unless a pitch
+ * is given.  Subpixels are u8 (the north_star's path: every tensor-core kernel)
+ * or, for the DynamicImage variants a 16-bit PNG / TIFF or an HDR / EXR file
+ * decodes to (src/handler.rs:219), u16 / f32 in native byte order
+ * (fanlin_job.src_sample; generic kernels in the crate's operation order).
  */
 #ifndef FANLIN_DEVICE_H
 #define FANLIN_DEVICE_H
@@ -20,7 +23,7 @@
 extern "C" {
 #endif
 
-#define FANLIN_ABI_VERSION 1
+#define FANLIN_ABI_VERSION 2 /* 2: fanlin_job.src_sample, fanlin_plan.out_sample (16-bit and f32 DynamicImage variants) */
 
 #if defined(__GNUC__)
 #define FANLIN_API __attribute__((visibility("default")))
@@ -44,6 +47,10 @@ enum fanlin_status {
 /* image::imageops::FilterType as used by the reference: Lanczos3 for stills
  * (src/handler.rs:233,235), Nearest for GIF frames (src/handler.rs:338,340). */
 enum fanlin_filter { FANLIN_FILTER_NEAREST = 0, FANLIN_FILTER_LANCZOS3 = 1 };
+
+/* Subpixel type of a DynamicImage variant: ImageLuma8 .. ImageRgba8, ImageLuma16 .. ImageRgba16, ImageRgb32F /
+ * ImageRgba32F (f32 has no Luma variants: src_channels 3 or 4). */
+enum fanlin_sample { FANLIN_SAMPLE_U8 = 0, FANLIN_SAMPLE_U16 = 1, FANLIN_SAMPLE_F32 = 2 };
 
 enum fanlin_flags {
     FANLIN_GRAYSCALE = 1u << 0, /* Query::grayscale()  src/query.rs:64-66; wins over INVERSE (handler.rs:224-228) */
@@ -74,6 +81,10 @@ typedef struct fanlin_job {
     float blur_sigma;      /* Query::blur(): 0 = off, else already clamped to [10,20]  src/query.rs:59-62 */
     uint8_t *dst;          /* host (fanlin_run) or device (fanlin_batch_*) pointer, tight rows */
     uint64_t dst_capacity; /* bytes available at dst */
+    uint32_t src_sample;   /* enum fanlin_sample of src (0 = u8).  src_pitch stays in bytes; src must be aligned to the
+                              subpixel size.  The result keeps the subpixel type except behind a letterbox (the reference's
+                              canvas is Rgba<u8>, handler.rs:240-247) and TO_RGBA8 / TO_RGB8: fanlin_plan.out_sample says which */
+    uint32_t reserved;     /* 0 */
 } fanlin_job;
 
 /* What the stage will produce for a job: lets the caller allocate dst and pick
@@ -87,6 +98,8 @@ typedef struct fanlin_plan {
     uint32_t stages;               /* bit0 colour op, bit1 resample, bit2 letterbox, bit3 blur, bit4 to_rgba8, bit5 to_rgb8 */
     uint64_t out_bytes;
     uint64_t algorithmic_bytes;    /* src window bytes + out_bytes */
+    uint32_t out_sample;           /* enum fanlin_sample of the output (out_bytes = out_w * out_h * out_channels * its size) */
+    uint32_t reserved;
 } fanlin_plan;
 
 typedef struct fanlin_config {

@@ -38,9 +38,32 @@ class Job(C.Structure):
     ]
 
 
+class DeepJob(C.Structure):
+    """fod_job of fanlin_oracle_deep.c: the request on a DynamicImage variant of any subpixel type."""
+    _fields_ = [
+        ("src", C.c_void_p),
+        ("src_w", C.c_uint32), ("src_h", C.c_uint32), ("src_c", C.c_uint32), ("sample", C.c_uint32),
+        ("flags", C.c_uint32),
+        ("req_w", C.c_uint32), ("req_h", C.c_uint32),
+        ("fill", C.c_uint8 * 3), ("orientation", C.c_uint8),
+        ("blur_sigma", C.c_float),
+        ("dst", C.c_void_p),
+        ("dst_cap", C.c_uint64),
+        ("out_w", C.c_uint32), ("out_h", C.c_uint32), ("out_c", C.c_uint32), ("out_sample", C.c_uint32),
+    ]
+
+
+TO_RGBA8 = 64  # fod_process only: DynamicImage::into_rgba8 of a still (the WebP branch, handler.rs:287)
+SAMPLE_DTYPES = {0: np.uint8, 1: np.uint16, 2: np.float32}
+
+
+def sample_kind(dtype) -> int:
+    return {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[np.dtype(dtype)]
+
+
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "fanlin_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("fanlin_oracle.c", "fanlin_oracle_deep.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
     return _SO
 
@@ -74,6 +97,8 @@ def lib():
         L.fo_ycck_to_cmyk.argtypes = [C.c_void_p, C.c_size_t]
         L.fo_ycck_to_cmyk.restype = None
         L.fo_apply_orientation.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        assert L.fod_job_size() == C.sizeof(DeepJob), "fod_job layout mismatch"
+        L.fod_process.argtypes = [C.POINTER(DeepJob)]
         _lib = L
     return _lib
 
@@ -244,3 +269,35 @@ def process_batch(imgs, n_threads=1, **kw):
         j = jobs[i]
         outs.append(bufs[i][: j.out_w * j.out_h * j.out_c].reshape(j.out_h, j.out_w, j.out_c))
     return outs
+
+
+def process_deep(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0, grayscale=False, inverse=False, gif=False,
+                 orientation=1, to_rgb8=False, to_rgba8=False) -> np.ndarray:
+    """One image of any subpixel type (u8 / u16 / f32 array, (H, W) or (H, W, C)) through the stage as restated in
+    fanlin_oracle_deep.c; returns (H, W, C) in the subpixel type the reference would hold (u8 behind a letterbox or
+    to_rgb8 / to_rgba8)."""
+    a = np.ascontiguousarray(img)
+    if a.ndim == 2:
+        a = a[:, :, None]
+    j = DeepJob()
+    j.src = a.ctypes.data
+    j.src_h, j.src_w, j.src_c = a.shape
+    j.sample = sample_kind(a.dtype)
+    fl = (GRAYSCALE if grayscale else 0) | (INVERSE if inverse else 0) | (CROP if crop else 0) | (GIF_FRAME if gif else 0)
+    fl |= (TO_RGB8 if to_rgb8 else 0) | (TO_RGBA8 if to_rgba8 else 0)
+    if w is not None and h is not None:
+        fl |= HAS_DIMS
+        j.req_w, j.req_h = int(w), int(h)
+    j.flags = fl
+    j.fill[0], j.fill[1], j.fill[2] = rgb
+    j.blur_sigma = float(blur)
+    j.orientation = int(orientation)
+    cap = max(j.req_w * j.req_h if fl & HAS_DIMS else 0, j.src_w * j.src_h, 1) * 4 * 4
+    buf = np.empty(cap, np.uint8)
+    j.dst, j.dst_cap = buf.ctypes.data, cap
+    rc = lib().fod_process(C.byref(j))
+    if rc:
+        raise ValueError(f"fod_process rc={rc}")
+    dt = SAMPLE_DTYPES[j.out_sample]
+    n = j.out_w * j.out_h * j.out_c
+    return buf[: n * np.dtype(dt).itemsize].view(dt).reshape(j.out_h, j.out_w, j.out_c).copy()

@@ -22,3 +22,24 @@ def synth_image(seed: int, h: int, w: int, c: int) -> np.ndarray:
         else:
             img[..., c - 1] = 255
     return img
+
+
+def synth_deep(seed: int, h: int, w: int, c: int, dtype) -> np.ndarray:
+    """The same picture with 16-bit or f32 subpixels (ImageLuma16 .. ImageRgba16, ImageRgb32F / ImageRgba32F): u16 =
+    257 x the u8 value plus low-order noise (so that the samples are not multiples of 257), f32 = the u8 value scaled to
+    [-0.1, 1.2] (HDR-like: resize and blur clamp to [0, 1], the colour ops do not).  Alpha as in synth_image."""
+    a = synth_image(seed, h, w, c)
+    dt = np.dtype(dtype)
+    if dt == np.uint8:
+        return a
+    rng = np.random.default_rng(seed + 7919)
+    if dt == np.uint16:
+        b = (a.astype(np.int32) * 257 + rng.integers(-120, 121, a.shape)).clip(0, 65535).astype(np.uint16)
+        if c in (2, 4) and seed % 8 != 7:
+            b[..., c - 1] = 65535
+        return b
+    assert dt == np.float32
+    f = (a.astype(np.float32) / np.float32(255)) * np.float32(1.3) - np.float32(0.1)
+    if c == 4:
+        f[..., 3] = np.float32(1.0) if seed % 8 != 7 else a[..., 3].astype(np.float32) / np.float32(255)
+    return np.ascontiguousarray(f, dtype=np.float32)

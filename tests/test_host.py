@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(fanlin):
     L = C.CDLL(fanlin.lib_path())
     for n in names:
         assert hasattr(L, n), n
-    assert L.fanlin_abi_version() == 1
+    assert L.fanlin_abi_version() == 2
 
 
 def test_no_device_is_an_error_not_a_fallback(fanlin):
