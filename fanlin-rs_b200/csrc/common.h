@@ -8,6 +8,12 @@ namespace fanlin {
 
 enum ColorOp : uint32_t { COLOR_NONE = 0, COLOR_GRAY = 1, COLOR_INVERT = 2 };
 enum Epilogue : uint32_t { EPI_PLAIN = 0, EPI_BLEND_FILL = 1, EPI_TO_RGBA = 2 };
+// Flag on EPI_BLEND_FILL / EPI_TO_RGBA: the Rgba<u8> pixel leaves without its alpha byte (c_out = 3) -- DynamicImage::to_rgb8
+// of the result folded into the last kernel (FANLIN_TO_RGB8, the JPEG branch handler.rs:274-278).  Understood by the
+// both-passes tensor-core kernels, the compose kernel and the generic (exact / deep) horizontal passes; the planner in
+// runtime.cpp sets it only where one of them writes the final image.
+constexpr uint32_t EPI_RGB8 = 4u;
+constexpr uint32_t EPI_MASK = 3u;
 enum FilterKind : uint32_t { KIND_NEAREST = 0, KIND_LANCZOS3 = 1, KIND_GAUSSIAN = 100 };
 
 // Subpixel types (enum fanlin_sample) and their size in bytes.

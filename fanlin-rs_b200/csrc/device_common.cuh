@@ -91,13 +91,29 @@ __device__ __forceinline__ void store_px(const StageDesc &d, uint32_t cx, uint32
         for (uint32_t k = 0; k < d.c; k++) q[k] = uint8_t(v[k]);
     } else {
         uint32_t px = to_rgba_packed(v, d.c);
-        if (d.epi == EPI_BLEND_FILL) px = blend_rgba(d.fill, px);
-        store_rgba(q, px);
+        if ((d.epi & EPI_MASK) == EPI_BLEND_FILL) px = blend_rgba(d.fill, px);
+        if (d.epi & EPI_RGB8) { q[0] = uint8_t(px); q[1] = uint8_t(px >> 8); q[2] = uint8_t(px >> 16); }
+        else store_rgba(q, px);
     }
+}
+
+// image-0.25.6 codecs/jpeg/encoder.rs rgb_to_ycbcr for u8 subpixels (max = 255): f32, the coefficients divided by max
+// first, products summed left to right, truncating (saturating) casts -- every operation rounded separately.
+__device__ __forceinline__ void rgb_to_ycbcr_u8(uint32_t r8, uint32_t g8, uint32_t b8, uint8_t *y, uint8_t *cb, uint8_t *cr) {
+    const float r = float(r8), g = float(g8), b = float(b8), m = 255.0f;
+    const float yy = __fadd_rn(__fadd_rn(__fmul_rn(__fdiv_rn(76.245f, m), r), __fmul_rn(__fdiv_rn(149.685f, m), g)), __fmul_rn(__fdiv_rn(29.07f, m), b));
+    const float cbv = __fadd_rn(__fadd_rn(__fsub_rn(__fmul_rn(__fdiv_rn(-43.0185f, m), r), __fmul_rn(__fdiv_rn(84.4815f, m), g)), __fmul_rn(__fdiv_rn(127.5f, m), b)), 128.0f);
+    const float crv = __fadd_rn(__fsub_rn(__fsub_rn(__fmul_rn(__fdiv_rn(127.5f, m), r), __fmul_rn(__fdiv_rn(106.7685f, m), g)), __fmul_rn(__fdiv_rn(20.7315f, m), b)), 128.0f);
+    *y = uint8_t(trunc_u8(yy)); *cb = uint8_t(trunc_u8(cbv)); *cr = uint8_t(trunc_u8(crv));
 }
 
 // Letterbox bars: canvas pixels outside the placed rect get the fill colour.
 __device__ __forceinline__ void store_fill(const StageDesc &d, uint32_t cx, uint32_t cy) {
+    if (d.epi & EPI_RGB8) {
+        uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx) * 3;
+        q[0] = uint8_t(d.fill); q[1] = uint8_t(d.fill >> 8); q[2] = uint8_t(d.fill >> 16);
+        return;
+    }
     store_rgba(d.dst + size_t(cy) * d.dst_pitch + size_t(cx) * 4, d.fill);
 }
 

@@ -96,7 +96,12 @@ __device__ __forceinline__ void store_px_deep(const StageDesc &d, uint32_t cx, u
 #pragma unroll
     for (int k = 0; k < 4; k++) b[k] = sub_to_u8(d.s_in, v[k]);
     uint32_t px = to_rgba_packed(b, d.c);  // missing alpha: MAX -> 255
-    if (d.epi == EPI_BLEND_FILL) px = blend_rgba(d.fill, px);
+    if ((d.epi & EPI_MASK) == EPI_BLEND_FILL) px = blend_rgba(d.fill, px);
+    if (d.epi & EPI_RGB8) {
+        uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx) * 3;
+        q[0] = uint8_t(px); q[1] = uint8_t(px >> 8); q[2] = uint8_t(px >> 16);
+        return;
+    }
     store_rgba(d.dst + size_t(cy) * d.dst_pitch + size_t(cx) * 4, px);
 }
 
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(256) to_rgb8_deep_kernel(const StageDesc *__re
                  : s == SAMPLE_U16 ? float(reinterpret_cast<const uint16_t *>(d.src)[idx]) : float(d.src[idx]);
         }
         uint8_t *o = d.dst + size_t(i) * 3;
+        if (d.epi) { rgb_to_ycbcr_u8(sub_to_u8(s, v[0]), sub_to_u8(s, v[1]), sub_to_u8(s, v[2]), d.dst + i, d.dst + n + i, d.dst + 2 * size_t(n) + i); continue; }
         o[0] = uint8_t(sub_to_u8(s, v[0])); o[1] = uint8_t(sub_to_u8(s, v[1])); o[2] = uint8_t(sub_to_u8(s, v[2]));
     }
 }

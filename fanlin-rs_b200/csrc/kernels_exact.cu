@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
     const uint32_t cy = blockIdx.x / xtiles;
     const uint32_t cx0 = ((blockIdx.x % xtiles) * TX + threadIdx.x) * 4;
     if (cx0 >= cw) return;
-    const uint32_t c_mem = d.c_mem, C = d.c, c_out = d.c_out, epi = d.epi, fill = d.fill, color_op = d.color_op;
+    const uint32_t c_mem = d.c_mem, C = d.c, c_out = d.c_out, epi = d.epi & EPI_MASK, fill = d.fill, color_op = d.color_op;  // (EPI_RGB8: c_out = 3 bytes of the packed pixel leave)
     const uint32_t dst_x = d.dst_x, dst_y = d.dst_y, n_cols = d.n_cols, n_rows = d.n_rows;
     const bool row_in = cy >= dst_y && cy - dst_y < n_rows;
     const bool gather = d.v_tab != NO_TABLE;
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restric
         const uint8_t *p = d.src + size_t(i) * c;
         uint8_t *o = d.dst + size_t(i) * 3;
         const uint8_t r = p[0], g = c <= 2 ? r : p[1], b = c <= 2 ? r : p[2];
+        if (d.epi) { rgb_to_ycbcr_u8(r, g, b, d.dst + i, d.dst + n + i, d.dst + 2 * size_t(n) + i); continue; }  // FANLIN_TO_YCBCR: planes
         o[0] = r; o[1] = g; o[2] = b;
     }
 }

@@ -849,8 +849,11 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
                             for (int c = 0; c < C; c++) sts8(sq + c, u[c]);
                         } else {
                             uint32_t px = to_rgba_packed(u, C);
-                            if (h_epi == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
-                            if (h_words) {
+                            if ((h_epi & EPI_MASK) == EPI_BLEND_FILL) px = blend_rgba(h_fill, px);
+                            if (h_epi & EPI_RGB8) {  // to_rgb8 of the result: the alpha byte stays behind (h_cout = 3)
+#pragma unroll
+                                for (int c = 0; c < 3; c++) sts8(sq + c, px >> (8 * c));
+                            } else if (h_words) {
                                 asm volatile("st.shared.b32 [%0], %1;" ::"r"(sq), "r"(px) : "memory");
                             } else {
 #pragma unroll

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                         px[i] = u[0] | u[1] << 8 | u[2] << 16 | u[3] << 24;  // the pixel's c bytes, low byte first
                     } else {
                         px[i] = to_rgba_packed(u, C);
-                        if (h_epi == EPI_BLEND_FILL) px[i] = blend_rgba(h_fill, px[i]);
+                        if ((h_epi & EPI_MASK) == EPI_BLEND_FILL) px[i] = blend_rgba(h_fill, px[i]);
                     }
                 }
                 // zero exactly the columns of the np pixels read: the neighbouring columns belong to live outputs, or to the
@@ -345,12 +345,13 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                         for (uint32_t i = 0; i < PB; i++)
                             if (i < np) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sp + 4 * i), "r"(px[i]) : "memory");
                     }
-                } else {  // plain output of 1..3 channels: byte by byte
+                } else {  // plain output of 1..3 channels, or RGB8 (EPI_RGB8: the packed pixel without its alpha byte): byte by byte
 #pragma unroll
                     for (uint32_t i = 0; i < PB; i++)
                         if (i < np) {
 #pragma unroll
-                            for (int c = 0; c < C; c++) sts8(sp + i * C + c, px[i] >> (8 * c));
+                            for (uint32_t c = 0; c < 3; c++)
+                                if (c < h_cout) sts8(sp + i * h_cout + c, px[i] >> (8 * c));
                         }
                 }
                 pb += np;

@@ -221,7 +221,7 @@ static uint32_t absdiff(uint32_t a, uint32_t b) { return a > b ? a - b : b - a; 
 
 int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
     if (job.orientation > 8) { set_error("fanlin: orientation must be an EXIF value 0..8"); return FANLIN_EINVAL; }
-    if ((job.flags & FANLIN_TO_RGBA8) && (job.flags & FANLIN_TO_RGB8)) { set_error("fanlin: TO_RGBA8 and TO_RGB8 exclude each other"); return FANLIN_EINVAL; }
+    if (((job.flags & FANLIN_TO_RGBA8) != 0) + ((job.flags & FANLIN_TO_RGB8) != 0) + ((job.flags & FANLIN_TO_YCBCR) != 0) > 1) { set_error("fanlin: TO_RGBA8, TO_RGB8 and TO_YCBCR exclude each other"); return FANLIN_EINVAL; }
     if (job.orientation >= 2) {
         // Orientation::from_exif + apply_orientation: 5..8 swap width and height.  Plan the request as it
         // looks behind the orientation pass, which also applies the colour op.
@@ -395,6 +395,14 @@ int plan_job(const fanlin_job &job, JobPlan *out, bool with_tables) {
         img_c = 3;
         img_s = SAMPLE_U8;
         pub.stages |= 32u;
+    }
+    if (job.flags & FANLIN_TO_YCBCR) {  // the JPEG encoder's rgb_to_ycbcr of to_rgb8() of the result, as three planes
+        p.post_c_in = img_c;
+        p.post_s_in = img_s;
+        p.post_ycbcr = true;
+        img_c = 3;
+        img_s = SAMPLE_U8;
+        pub.stages |= 64u;
     }
     pub.out_w = img_w;
     pub.out_h = img_h;

@@ -356,6 +356,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     // the oriented stage had a letterbox / to_rgba8 epilogue, composed onto the canvas.  late_a = the oriented stage A.
     std::vector<uint8_t> late(n_jobs, 0);
     std::vector<StagePlan> late_a(n_jobs);
+    static const bool no_rgb8_epilogue = [] { const char *e = std::getenv("FANLIN_RGB8_EPILOGUE"); return e && e[0] == '0'; }();  // (A/B switch: 0 keeps the to_rgb8 pass)
     static const bool late_orient_on = [] { const char *e = std::getenv("FANLIN_LATE_ORIENT"); return !(e && e[0] == '0'); }();
     FusedTcCache *const tcache_p = gen->tcache;
     FusedTcTables &tctabs = gen->tctabs;
@@ -415,9 +416,23 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 ej[i].orientation = 0;
             }
         }
-        const JobPlan &p = b->plans[i];
-        for (const auto &t : {p.a.vtab, p.a.htab, p.b.vtab, p.b.htab})
+        for (const auto &t : {b->plans[i].a.vtab, b->plans[i].a.htab, b->plans[i].b.vtab, b->plans[i].b.htab})
             if (t) gen->keep.insert(t);
+        // FANLIN_TO_RGB8 as an epilogue: where stage A writes the final image and its kernel can leave
+        // the alpha byte behind, the to_rgb8 pass over the output disappears -- tried first, taken back when the stage
+        // then falls to a kernel that cannot (the CUDA-core fused kernel, the tensor-core kernel with the CUDA-core
+        // horizontal stage).  With a blur behind it, or the orientation applied after the resample, the pass stays.
+        const bool rgb8_try = !no_rgb8_epilogue && b->plans[i].post_c_in && !b->plans[i].post_ycbcr && b->plans[i].post_s_in == SAMPLE_U8 && b->plans[i].a.present &&
+                              !b->plans[i].b.present && !late[i] && b->plans[i].a.s_out == SAMPLE_U8;
+        const StagePlan a_keep = b->plans[i].a;
+        if (rgb8_try) {
+            StagePlan &ta = b->plans[i].a;
+            ta.epi = (ta.epi == EPI_PLAIN ? uint32_t(EPI_TO_RGBA) : ta.epi) | EPI_RGB8;
+            ta.c_out = 3;
+        }
+      for (int attempt = 0; attempt < 2; attempt++) {
+        const JobPlan &p = b->plans[i];
+        a_pre[i] = StagePlan();
         fused_a[i] = 0;
         gather_a[i] = !deep_a[i] && p.a.present && p.a.separable && p.a.v_kind == KIND_NEAREST && p.a.h_kind == KIND_NEAREST;  // one tap per output: a gather
         if (!exact && use_tc && !gather_a[i] && !deep_a[i]) {
@@ -441,6 +456,16 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             }
         }
         if (!fused_a[i] && !gather_a[i] && !deep_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache_p, &ftabs);
+        if (attempt == 0 && rgb8_try) {
+            const StagePlan &ta = a_pre[i].present ? a_pre[i] : p.a;
+            const bool both_passes_tc = fused_a[i] == 2 && (fused_tc_uses_hmma(ta, tcache_p, &ftabs, &tctabs) || fused_tc_uses_ring(ta, tcache_p, &ftabs, &tctabs));
+            if (fused_a[i] == 0 || both_passes_tc) { b->plans[i].post_c_in = 0; break; }  // compose / generic / deep / both-passes kernels: folded
+            b->plans[i].a = a_keep;  // the kernel it fell to has no such epilogue: plan A as it was, the pass stays
+            continue;
+        }
+        break;
+      }
+        const JobPlan &p = b->plans[i];
         if (!fused_a[i]) { add_table(p.a.vtab); add_table(p.a.htab); }
         fast_b[i] = !exact && !deep_b[i] && blur_eligible(p.b);
         if (fast_b[i] && use_tc && ctx->cfg.blur_path != 1) {
@@ -733,6 +758,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 d.src = ej[i].dst; d.dst = jobs[i].dst;
                 d.s_in = p.post_s_in; d.s_out = SAMPLE_U8;
                 d.c_mem = p.post_c_in; d.c = 3; d.c_out = 3;
+                d.epi = p.post_ycbcr ? 1u : 0u;  // (this pass only: 1 = planar Y, Cb, Cr instead of interleaved RGB)
                 d.canvas_w = p.pub.out_w; d.canvas_h = p.pub.out_h;
                 d.v_tab = d.h_tab = NO_TABLE;
                 geom_add(&hs.g, d);

@@ -26,10 +26,11 @@ def _as_img(a) -> np.ndarray:
 
 TO_RGB8 = 1 << 5  # enum fanlin_flags FANLIN_TO_RGB8
 TO_RGBA8 = 1 << 4
+TO_YCBCR = 1 << 6  # FANLIN_TO_YCBCR: the JPEG encoder's planes of the result, (3, H, W)
 
 
 def make_job(img: np.ndarray, params: Query, *, gif: bool = False, orientation: int = 1, to_rgb8: bool = False,
-             to_rgba8: bool = False) -> Job:
+             to_rgba8: bool = False, to_ycbcr: bool = False) -> Job:
     """orientation: the EXIF value decoder.orientation() reported for a still (src/handler.rs:206);
     the device turns the image instead of img.apply_orientation(o) on the host (:221-223).
     to_rgb8: the caller will encode JPEG (:274-278) and wants the RGB8 the encoder works on;
@@ -42,6 +43,8 @@ def make_job(img: np.ndarray, params: Query, *, gif: bool = False, orientation: 
         j.flags |= TO_RGB8
     if to_rgba8:
         j.flags |= TO_RGBA8
+    if to_ycbcr:
+        j.flags |= TO_YCBCR
     j.src = a.ctypes.data
     j.src_h, j.src_w, j.src_channels = a.shape
     j.src_sample = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[a.dtype]
@@ -53,7 +56,8 @@ def _run(dev: Device, jobs):
     outs = []
     for j in jobs:
         p = plan_job(j)
-        o = np.empty((p.out_h, p.out_w, p.out_channels), SAMPLE_DTYPES[p.out_sample])
+        planar = bool(p.stages & 64)  # FANLIN_TO_YCBCR: (3, H, W)
+        o = np.empty((3, p.out_h, p.out_w) if planar else (p.out_h, p.out_w, p.out_channels), SAMPLE_DTYPES[p.out_sample])
         j.dst, j.dst_capacity = o.ctypes.data, o.nbytes
         outs.append(o)
     arr = (Job * len(jobs))()
@@ -64,11 +68,11 @@ def _run(dev: Device, jobs):
 
 
 def process_image(dev: Device, img: np.ndarray, params: Query, *, orientation: int = 1, to_rgb8: bool = False,
-                  to_rgba8: bool = False) -> np.ndarray:
+                  to_rgba8: bool = False, to_ycbcr: bool = False) -> np.ndarray:
     """Pixel section of State::process_image: decoded pixels (as stored, with their EXIF
     orientation) in, transformed pixels out (RGB8 when the JPEG encoder follows, RGBA8 for WebP).
     The array's dtype is the DynamicImage variant's subpixel type (u8, u16, f32)."""
-    return _run(dev, [make_job(img, params, orientation=orientation, to_rgb8=to_rgb8, to_rgba8=to_rgba8)])[0]
+    return _run(dev, [make_job(img, params, orientation=orientation, to_rgb8=to_rgb8, to_rgba8=to_rgba8, to_ycbcr=to_ycbcr)])[0]
 
 
 def process_images(dev: Device, imgs, params: Query):

@@ -58,8 +58,14 @@ enum fanlin_flags {
     FANLIN_HAS_DIMS = 1u << 2,  /* Query::dimensions() is Some((req_w, req_h))  src/query.rs:28-33 */
     FANLIN_CROP = 1u << 3,      /* Query::cropping()   src/query.rs:55-57 -> resize_to_fill */
     FANLIN_TO_RGBA8 = 1u << 4,  /* GIF frames end with img.to_rgba8()  src/handler.rs:355; also the WebP branch's into_rgba8() (:287) */
-    FANLIN_TO_RGB8 = 1u << 5    /* the JPEG branch: the encoder works on RGB8 (src/handler.rs:274-278), DynamicImage::to_rgb8 --
-                                   alpha dropped, luma replicated; not together with FANLIN_TO_RGBA8 */
+    FANLIN_TO_RGB8 = 1u << 5,   /* the JPEG branch: the encoder works on RGB8 (src/handler.rs:274-278), DynamicImage::to_rgb8 --
+                                   alpha dropped, luma replicated; not together with FANLIN_TO_RGBA8.  Folded into the last
+                                   kernel's epilogue where that kernel writes the final image (no extra pass) */
+    FANLIN_TO_YCBCR = 1u << 6   /* the JPEG branch, one step further: the result as the three full-resolution
+                                   planes Y, Cb, Cr the JPEG encoder derives from it -- image-0.25.6 codecs/jpeg/encoder.rs
+                                   rgb_to_ycbcr on to_rgb8() of the result (f32, JFIF coefficients x 255, truncating cast);
+                                   dst holds [3][out_h][out_w] u8, out_channels = 3, fanlin_plan.stages bit 6.  For a host
+                                   encoder that accepts planar input; excludes TO_RGBA8 / TO_RGB8 */
 };
 
 /* One image (still) or one composited GIF frame and the request parameters the
@@ -95,7 +101,7 @@ typedef struct fanlin_plan {
     uint32_t crop_x, crop_y;       /* resize_to_fill crop origin inside the resized image */
     uint32_t overlay_x, overlay_y; /* letterbox offset (handler.rs:244-245) */
     uint32_t src_x0, src_y0, src_x1, src_y1; /* source window the output depends on (in the oriented image) */
-    uint32_t stages;               /* bit0 colour op, bit1 resample, bit2 letterbox, bit3 blur, bit4 to_rgba8, bit5 to_rgb8 */
+    uint32_t stages;               /* bit0 colour op, bit1 resample, bit2 letterbox, bit3 blur, bit4 to_rgba8, bit5 to_rgb8, bit6 planar YCbCr */
     uint64_t out_bytes;
     uint64_t algorithmic_bytes;    /* src window bytes + out_bytes */
     uint32_t out_sample;           /* enum fanlin_sample of the output (out_bytes = out_w * out_h * out_channels * its size) */

@@ -47,8 +47,32 @@ enum {
     FO_CROP = 1u << 3,
     FO_GIF_FRAME = 1u << 4, /* Nearest, no blur, to_rgba8 (handler.rs:329-355; GIF frames are RGBA8, kept for the u8 cross-check) */
     FO_TO_RGB8 = 1u << 5,   /* DynamicImage::to_rgb8 of the result */
-    FO_TO_RGBA8 = 1u << 6   /* DynamicImage::into_rgba8 of the result (the WebP branch, handler.rs:287) */
+    FO_TO_RGBA8 = 1u << 6,  /* DynamicImage::into_rgba8 of the result (the WebP branch, handler.rs:287) */
+    FO_TO_YCBCR = 1u << 7   /* the planes Y, Cb, Cr the JPEG encoder derives from the result (codecs/jpeg/encoder.rs rgb_to_ycbcr on
+                               to_rgb8() of it): [3][h][w] u8 */
 };
+
+/* image-0.25.6 codecs/jpeg/encoder.rs:
+ *   fn rgb_to_ycbcr<P: Pixel>(pixel: P) -> (u8, u8, u8) {
+ *       let [r, g, b] = pixel.to_rgb().0;  let max: f32 = P::Subpixel::DEFAULT_MAX_VALUE.to_f32().unwrap();  (r, g, b as f32)
+ *       // Coefficients from JPEG File Interchange Format (Version 1.02), multiplied for 255 maximum.
+ *       let y  =   76.245  / max * r + 149.685  / max * g +  29.07   / max * b;
+ *       let cb = - 43.0185 / max * r -  84.4815 / max * g + 127.5    / max * b + 128.;
+ *       let cr =  127.5    / max * r - 106.7685 / max * g -  20.7315 / max * b + 128.;
+ *       (y as u8, cb as u8, cr as u8) }                       -- restated from memory, like the rest (version-sensitive) */
+static uint8_t sat_u8(float v) { return v != v ? 0 : (v <= 0.0f ? 0 : (v >= 255.0f ? 255 : (uint8_t)v)); }
+static void rgb_to_ycbcr(const uint8_t p[3], uint8_t *y, uint8_t *cb, uint8_t *cr) {
+    const float max = 255.0f, r = (float)p[0], g = (float)p[1], b = (float)p[2];
+    float yy = 76.245f / max * r + 149.685f / max * g;
+    yy = yy + 29.07f / max * b;
+    float c1 = -43.0185f / max * r - 84.4815f / max * g;
+    c1 = c1 + 127.5f / max * b;
+    c1 = c1 + 128.0f;
+    float c2 = 127.5f / max * r - 106.7685f / max * g;
+    c2 = c2 - 20.7315f / max * b;
+    c2 = c2 + 128.0f;
+    *y = sat_u8(yy); *cb = sat_u8(c1); *cr = sat_u8(c2);
+}
 
 /* exported by fanlin_oracle.c */
 uint32_t fo_weight_table(int kind, float sigma, uint32_t n_in, uint32_t n_out, uint32_t *lefts, uint32_t *counts, float *weights,
@@ -351,7 +375,8 @@ int fod_process(fod_job *job) {
         if (rc != FO_OK) return rc;
         img = bl;
     }
-    const int to4 = gif || (job->flags & FO_TO_RGBA8), to3 = !to4 && (job->flags & FO_TO_RGB8);
+    const int ycc = !gif && (job->flags & FO_TO_YCBCR);
+    const int to4 = gif || (job->flags & FO_TO_RGBA8), to3 = !to4 && ((job->flags & FO_TO_RGB8) || ycc);
     if ((to4 && !(img.c == 4 && img.sk == FOD_U8)) || (to3 && !(img.c == 3 && img.sk == FOD_U8))) {
         img_t r;
         const uint32_t oc = to4 ? 4 : 3;
@@ -363,6 +388,15 @@ int fod_process(fod_job *job) {
         }
         img_free(&img);
         img = r;
+    }
+    if (ycc) { /* img is RGB8 here */
+        img_t pl;
+        const size_t n = (size_t)img.w * img.h;
+        if (img_alloc(&pl, img.w, img.h, 3, FOD_U8) != FO_OK) { img_free(&img); return FO_ENOMEM; }
+        uint8_t *o = pl.px;
+        for (size_t i = 0; i < n; i++) rgb_to_ycbcr((const uint8_t *)img.px + 3 * i, o + i, o + n + i, o + 2 * n + i);
+        img_free(&img);
+        img = pl;
     }
     job->out_w = img.w; job->out_h = img.h; job->out_c = img.c; job->out_sample = img.sk;
     const uint64_t need = img_bytes(&img);

@@ -54,6 +54,7 @@ class DeepJob(C.Structure):
 
 
 TO_RGBA8 = 64  # fod_process only: DynamicImage::into_rgba8 of a still (the WebP branch, handler.rs:287)
+TO_YCBCR = 128  # fod_process only: the JPEG encoder's Y, Cb, Cr planes of the result ([3][h][w])
 SAMPLE_DTYPES = {0: np.uint8, 1: np.uint16, 2: np.float32}
 
 
@@ -272,7 +273,7 @@ def process_batch(imgs, n_threads=1, **kw):
 
 
 def process_deep(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0, grayscale=False, inverse=False, gif=False,
-                 orientation=1, to_rgb8=False, to_rgba8=False) -> np.ndarray:
+                 orientation=1, to_rgb8=False, to_rgba8=False, to_ycbcr=False) -> np.ndarray:
     """One image of any subpixel type (u8 / u16 / f32 array, (H, W) or (H, W, C)) through the stage as restated in
     fanlin_oracle_deep.c; returns (H, W, C) in the subpixel type the reference would hold (u8 behind a letterbox or
     to_rgb8 / to_rgba8)."""
@@ -284,7 +285,7 @@ def process_deep(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0,
     j.src_h, j.src_w, j.src_c = a.shape
     j.sample = sample_kind(a.dtype)
     fl = (GRAYSCALE if grayscale else 0) | (INVERSE if inverse else 0) | (CROP if crop else 0) | (GIF_FRAME if gif else 0)
-    fl |= (TO_RGB8 if to_rgb8 else 0) | (TO_RGBA8 if to_rgba8 else 0)
+    fl |= (TO_RGB8 if to_rgb8 else 0) | (TO_RGBA8 if to_rgba8 else 0) | (TO_YCBCR if to_ycbcr else 0)
     if w is not None and h is not None:
         fl |= HAS_DIMS
         j.req_w, j.req_h = int(w), int(h)
@@ -300,4 +301,6 @@ def process_deep(img, *, w=None, h=None, rgb=(32, 32, 32), crop=False, blur=0.0,
         raise ValueError(f"fod_process rc={rc}")
     dt = SAMPLE_DTYPES[j.out_sample]
     n = j.out_w * j.out_h * j.out_c
+    if to_ycbcr:  # planar: (3, H, W)
+        return buf[:n].reshape(3, j.out_h, j.out_w).copy()
     return buf[: n * np.dtype(dt).itemsize].view(dt).reshape(j.out_h, j.out_w, j.out_c).copy()

@@ -290,3 +290,54 @@ def test_deep_fuzz(fanlin, dev):
             assert np.abs(got.astype(np.int16) - want.astype(np.int16)).max() <= 1, (it, p)
         else:
             assert got.tobytes() == want.tobytes(), (it, c, dt, h, w, p)
+
+
+# ---- FANLIN_TO_YCBCR: the JPEG encoder's planes of the result ---------------------------------
+
+def _ycbcr_np(rgb):
+    """codecs/jpeg/encoder.rs rgb_to_ycbcr, vectorised in f32 (a second restatement): (..., 3) u8 -> three u8 arrays."""
+    f = np.float32
+    r, g, b = (rgb[..., k].astype(f) for k in range(3))
+    m = f(255.0)
+    y = (f(76.245) / m) * r + (f(149.685) / m) * g + (f(29.07) / m) * b
+    cb = (f(-43.0185) / m) * r - (f(84.4815) / m) * g + (f(127.5) / m) * b + f(128.0)
+    cr = (f(127.5) / m) * r - (f(106.7685) / m) * g - (f(20.7315) / m) * b + f(128.0)
+    return tuple(np.clip(np.trunc(v), 0, 255).astype(np.uint8) for v in (y, cb, cr))
+
+
+def _all_rgb():
+    v = np.arange(1 << 24, dtype=np.uint32)
+    return np.stack([v & 255, (v >> 8) & 255, v >> 16], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+
+
+def test_ycbcr_oracle_all_triples():
+    img = _all_rgb()
+    got = O.process_deep(img, to_ycbcr=True)
+    assert got.shape == (3, 4096, 4096)
+    for plane, want in zip(got, _ycbcr_np(img)):
+        assert (plane == want).all()
+    # known answers: black, white (f32: 76.245/255*255 + ... rounds just below 255), the primaries of JFIF
+    px = np.array([[[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255]]], np.uint8)
+    y, cb, cr = O.process_deep(px, to_ycbcr=True)
+    assert y[0].tolist()[:1] == [0] and cb[0, 0] == 128 and cr[0, 0] == 128
+    assert y[0, 2] == 76 and y[0, 3] == 149 and y[0, 4] == 29 and cb[0, 4] == 255 and cr[0, 2] == 255
+    # the request runs first, the planes come from to_rgb8() of its result
+    a = synth_image(9, 40, 60, 4)
+    rgb = O.process_deep(a, w=50, h=50, to_rgb8=True)
+    assert (np.stack(_ycbcr_np(rgb)) == O.process_deep(a, w=50, h=50, to_ycbcr=True)).all()
+
+
+@pytest.mark.gpu
+def test_ycbcr_planes_on_device(fanlin, dev, dev_exact):
+    img = _all_rgb()  # every (R, G, B): bit-exact
+    got = fanlin.process_image(dev, img, fanlin.Query(""), to_ycbcr=True)
+    assert got.shape == (3, 4096, 4096) and (got == O.process_deep(img, to_ycbcr=True)).all()
+    for (seed, h, w, c, dt), p in [((1, 90, 120, 3, np.uint8), dict(w=64, h=64, rgb=(3, 4, 5))), ((7, 90, 120, 4, np.uint8), dict(w=64, h=40, crop=True)),
+                                   ((2, 90, 120, 1, np.uint8), dict(w=50, h=50, crop=True, blur=10)), ((3, 60, 80, 2, np.uint8), dict(inverse=True)),
+                                   ((4, 70, 90, 3, np.uint16), dict(w=40, h=30, crop=True, orientation=6)), ((5, 70, 90, 4, np.float32), dict(w=60, h=60))]:
+        img = synth_deep(seed, h, w, c, dt)
+        want = O.process_deep(img, to_ycbcr=True, **_okw(p))
+        e = fanlin.process_image(dev_exact, img, fanlin.Query(_qs(p)), orientation=p.get("orientation", 1), to_ycbcr=True)
+        assert e.shape == want.shape and (e == want).all(), p
+        g = fanlin.process_image(dev, img, fanlin.Query(_qs(p)), orientation=p.get("orientation", 1), to_ycbcr=True)
+        assert g.shape == want.shape and np.abs(g.astype(np.int16) - want.astype(np.int16)).max() <= 2, p  # a 1-LSB RGB difference moves a plane by <= 1 (+ truncation)

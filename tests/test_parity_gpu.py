@@ -283,6 +283,47 @@ def test_to_rgb8_output(fanlin, dev, dev_exact, h, w, c, qs):
     assert got.shape == want.shape and hh[">=2"] == 0 and hh[1] <= 0.002 * want.size + 2, hh
 
 
+# FANLIN_TO_RGB8 folded into the last kernel: h, w, c, request, kernel launches expected on a default context
+RGB8_EPILOGUE_CASES = [
+    (1080, 1920, 3, "w=300&h=200&rgb=32,32,32", 1),   # C2 shape: both-passes kernel, letterbox blend, alpha byte left behind
+    (512, 512, 3, "w=300&h=200", 1),                  # C1 shape: ring kernel
+    (540, 960, 4, "w=404&h=250&crop=true", 1),        # RGBA (random alpha, seed 615 -> 7 mod 8): dropped, not blended
+    (540, 960, 4, "w=404&h=300&rgb=9,8,7", 1),        # RGBA letterboxed: blended onto the fill colour, then RGB
+    (700, 900, 1, "w=100&h=100&rgb=1,2,3", 1),        # L8 letterboxed -> (l, l, l)
+    (300, 400, 2, "w=90&h=90&crop=true", 1),          # La8 -> (l, l, l)
+    (50, 100, 3, "w=100&h=100", 1),                   # letterbox without a resample: compose kernel
+    (60, 80, 2, "inverse=true", 1),                   # colour op only
+    (37, 53, 4, "w=20&h=31&crop=true", None),         # tiny: whatever kernel takes it
+]
+
+
+@pytest.mark.parametrize("h,w,c,qs,launches", RGB8_EPILOGUE_CASES, ids=[f"{p[0]}x{p[1]}x{p[2]}-{p[3]}" for p in RGB8_EPILOGUE_CASES])
+def test_to_rgb8_is_an_epilogue(fanlin, dev, dev_exact, h, w, c, qs, launches):
+    img = synth_image(611 + c, h, w, c)
+    q = fanlin.Query(qs)
+    kw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+    if q.dimensions() is not None:
+        kw["w"], kw["h"] = q.dimensions()
+    want = O.process(img, to_rgb8=True, **kw)
+    assert want.shape[2] == 3
+    exact = fanlin.process_image(dev_exact, img, q, to_rgb8=True)
+    assert exact.shape == want.shape and np.array_equal(exact, want)
+    n0 = dev.stats()["kernel_launches"]
+    got = fanlin.process_image(dev, img, q, to_rgb8=True)
+    n1 = dev.stats()["kernel_launches"]
+    hh = hist(got, want)
+    assert got.shape == want.shape and hh[">=2"] == 0 and hh[1] <= 0.002 * want.size + 2, hh
+    if launches is not None:
+        assert n1 - n0 == launches, (n1 - n0, "the to_rgb8 pass was not folded into the last kernel")
+    # contexts whose resample kernels have no such epilogue keep the pass and give the same pixels within the bar
+    for vp in (1, 2):
+        d = fanlin.Device([0], vertical_path=vp)
+        g2 = fanlin.process_image(d, img, q, to_rgb8=True)
+        d.close()
+        h2 = hist(g2, want)
+        assert g2.shape == want.shape and h2[">=2"] == 0, (vp, h2)
+
+
 # ---- same-shaped images in one launch --------------------------------------------------------
 
 @pytest.mark.parametrize("h,w,c,qs", [(1080, 1920, 3, "w=300&h=200&rgb=32,32,32"), (600, 800, 3, "w=200&h=200&crop=true"),
