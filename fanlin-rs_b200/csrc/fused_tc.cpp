@@ -2,6 +2,9 @@
 // s8 digit tiles of the vertical weights and the horizontal scatter table.
 #include "fused_tc.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -368,7 +371,10 @@ static bool build_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
     g.ring_cols = RINGC;
     // words per staged row, == 4 (mod 8): 16-byte aligned rows whose four-word stores (lanes = rows) fall on distinct banks
     g.stage_stride = (fin_max * s.c_out + 3) / 4 + 1;
-    g.stage_stride += (4 + 8 - (g.stage_stride & 7)) & 7;
+    // (RGBA in, RGBA out stages four pixels per 16-byte store; everything else stages words or bytes, for which an ODD stride
+    // is conflict-free and up to seven words per row shorter -- the 7 KB that let a whole C1 image be ONE band of two row tiles)
+    if (C == 4 && s.c_out == 4) g.stage_stride += (4 + 8 - (g.stage_stride & 7)) & 7;
+    else g.stage_stride |= 1u;
     std::vector<uint16_t> w_hi(t.weights.size()), w_lo(t.weights.size());
     for (uint32_t o = o0; o < o_end; o++) {
         const TapEntry &e = t.entries[o];
@@ -435,6 +441,9 @@ static bool try_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTa
             const uint32_t n_mt = (ng + 3) / 4;
             fits = n_mt * g.ring_cols + 2 * TC_N <= 512 &&
                    fused_tc3_smem_bytes(ng, kgm, 2, 1, g.wh_bytes, g.stage_stride) <= TC_SMEM_LIMIT;
+            if (std::getenv("FANLIN_TC_DEBUG"))
+                std::fprintf(stderr, "try_ring: %u bands of %u rows: %u groups, kg_max %u, ring %u, wh %u B, stage stride %u -> %zu B of %zu: %s\n", n_bands, band_rows, ng, kgm,
+                             g.ring_cols, g.wh_bytes, g.stage_stride, fused_tc3_smem_bytes(ng, kgm, 2, 1, g.wh_bytes, g.stage_stride), size_t(TC_SMEM_LIMIT), fits ? "fits" : "no");
         }
     }
     if (!fits) { tabs->info.resize(info_mark); tct->b.resize(b_mark); return false; }

@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
 
         // the pixels chunk `chunk` finished in row tile `mt`: ring -> registers -> rounded bytes -> staging -> canvas
         long long w_v = 0, w_d2 = 0, t_dr = 0, t_v = 0;
+        long long t_ld = 0, t_zs = 0, t_wo = 0;  // T3_PROF: inside the ring drain -- TMEM loads, the wait for the zeroing stores, write-out
         const long long t_start = clock64();
         auto drain_ring = [&](uint32_t chunk, uint32_t mt) {
             T3W(w_d2, smem_u32(&d2_full[mt]), chunk & 1);  // every warp: the tile's T rows may be overwritten from here on
@@ -288,8 +289,14 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                 const uint32_t np = min(min(PB, p1 - pb), RP - slot);
                 const uint32_t ta = tbase + slot * C;
                 uint32_t v[16];
+#ifdef T3_PROF
+                const long long tl0 = clock64();
+#endif
                 tmem_ld16(ta, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef T3_PROF
+                t_ld += clock64() - tl0;
+#endif
                 uint32_t px[PB];
 #pragma unroll
                 for (uint32_t i = 0; i < PB; i++) {
@@ -358,9 +365,17 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                 slot += np;
                 if (slot >= RP) slot -= RP;
             }
+#ifdef T3_PROF
+            const long long tz0 = clock64();
+#endif
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0) t3_arrive(smem_u32(&d2_free[mt]));
+#ifdef T3_PROF
+            t_zs += clock64() - tz0;
+            const long long tw0 = clock64();
+            struct AccW { long long &a; long long t0; __device__ ~AccW() { a += clock64() - t0; } } accw_{t_wo, tw0};
+#endif
             if (p1 <= p0) return;
             __syncwarp();
             // ---- write out: this group's rows x nb bytes at canvas byte (fin_first + p0) * c_out of each row
@@ -474,9 +489,9 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
         if (n_mt > 1) drain_ring(n_chunks - 1, 1);
 #ifdef T3_PROF
         if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 5))
-            printf("tc3 consumer warp %u: total %lld clk; waits: vertical results %lld, ring ready %lld; vertical drain %lld, ring drain + write-out %lld\n", warp, clock64() - t_start, w_v, w_d2, t_v, t_dr);
+            printf("tc3 consumer warp %u: total %lld clk; waits: vertical results %lld, ring ready %lld; vertical drain %lld, ring drain + write-out %lld (TMEM loads %lld, wait for zeroing stores %lld, write-out %lld)\n", warp, clock64() - t_start, w_v, w_d2, t_v, t_dr, t_ld, t_zs, t_wo);
 #else
-        (void)t_start; (void)w_v; (void)w_d2; (void)t_dr; (void)t_v;
+        (void)t_start; (void)w_v; (void)w_d2; (void)t_dr; (void)t_v; (void)t_ld; (void)t_zs; (void)t_wo;
 #endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
