@@ -127,7 +127,7 @@ size_t fused_tc2_smem_bytes(uint32_t c, uint32_t n_groups, uint32_t kg_max, uint
 size_t fused_tc3_smem_bytes(uint32_t n_groups, uint32_t kg_max, uint32_t n_a, uint32_t n_wh, uint32_t wh_bytes, uint32_t stage_stride) {
     const size_t a = size_t(n_a) * kg_max * TC_M, b = 2 * size_t(TC_N) * kg_max;  // source slots, two vertical weight-tile slots
     const size_t t = 2 * size_t(n_groups) * 32 * 256;                             // T hi + lo
-    const size_t stage = 8 * ((16 + size_t(32) * stage_stride * 4 + 15) & ~size_t(15));  // per consumer warp: guard + [32 rows][stage_stride words]
+    const size_t stage = 8 * ((16 + size_t(32) * stage_stride * 4 + 15) & ~size_t(15));  // per (row tile, lane quarter): guard + [32 rows][stage_stride words]
     return a + b + t + size_t(n_wh) * wh_bytes + stage;
 }
 

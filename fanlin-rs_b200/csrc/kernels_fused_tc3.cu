@@ -23,8 +23,9 @@ namespace fanlin {
 
 namespace {
 
-constexpr int T3_NT = 256;            // consumer threads
+constexpr int T3_NT = 384;            // consumer threads: 12 warps = 3 sets of one warp per TMEM lane quarter (the kernel needs ~100 registers)
 constexpr int T3_NT_ALL = T3_NT + 128;
+constexpr uint32_t T3_SETS = T3_NT / 128;
 constexpr uint32_t T3_NB = 2;         // vertical weight-tile slots
 constexpr uint32_t T3_NA_MAX = 4;
 #ifndef T3_PF_AHEAD
@@ -39,6 +40,18 @@ constexpr uint32_t T3_NA_MAX = 4;
 #define T3WR(acc, ...) mbar_wait_wd(__VA_ARGS__)  // role threads: with the watchdog
 #endif
 
+// Which of the three consumer sets converts group g (of 8 at most) of a chunk, cr = chunk mod 3.  In chunk k set cr drains
+// what chunk k - 1 finished in row tile 0 and set cr + 1 what it finished in tile 1; a tile's groups go to the OTHER two sets,
+// alternating, so that the tile is handed to the tensor core after max(drain, two conversions) and not after their sum.
+__device__ __forceinline__ uint32_t t3_owner(uint32_t cr, uint32_t g) {
+    const uint32_t b = cr == 2 ? 0u : cr + 1, c = cr == 0 ? 2u : cr - 1;
+    return (g & 1) ? c : (g < 4 ? b : cr);
+}
+// v_full barrier of a group: one per (owner set, vertical region) -- only the owner waits on it, and on every phase of it (a
+// set that skipped phases of a barrier shared with the other sets could not tell them apart by parity).  Waiters keep the
+// parities in a bit mask.
+__device__ __forceinline__ uint32_t t3_vbar(uint32_t owner, uint32_t region) { return owner * 4 + region; }
+
 __device__ __forceinline__ void t3_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 template <int C, bool INV = false>  // INV: inverse on load, a template parameter (see fused_resample_tc2_kernel)
@@ -47,7 +60,8 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ FusedTcItem it_s;
-    __shared__ __align__(8) uint64_t v_full[4], v_free[4], a_full[T3_NA_MAX], b_full[T3_NB];
+    // v_full: one barrier per (consumer set, vertical region), see t3_vbar
+    __shared__ __align__(8) uint64_t v_full[12], v_free[4], a_full[T3_NA_MAX], b_full[T3_NB];
     __shared__ __align__(8) uint64_t t_ready[2], d2_full[2], d2_free[2], wh_full[2], wh_free[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t grp[4 * 8];
@@ -56,13 +70,14 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
     if (tid == 0) {
         it_s = items[blockIdx.x];
         auto init = [](uint64_t *b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); };
-        for (uint32_t r = 0; r < 4; r++) { init(&v_full[r], 1); init(&v_free[r], 8); }
+        for (uint32_t r = 0; r < 12; r++) init(&v_full[r], 1);
+        for (uint32_t r = 0; r < 4; r++) init(&v_free[r], 4);  // a group's vertical results are read by the four warps of ONE set
         for (uint32_t r = 0; r < T3_NA_MAX; r++) init(&a_full[r], 1);
         for (uint32_t r = 0; r < T3_NB; r++) init(&b_full[r], 1);
         for (uint32_t r = 0; r < 2; r++) {
-            init(&t_ready[r], 8);
+            init(&t_ready[r], T3_NT / 32);
             init(&d2_full[r], 1);
-            init(&d2_free[r], it_s.n_groups > 4 ? 4 : 8);  // drained by the tile's own four warps when the band has two tiles, else by all eight
+            init(&d2_free[r], 4);  // what a chunk finished in a tile is drained by the four warps of one set
             init(&wh_full[r], 1);
             init(&wh_free[r], 1);
         }
@@ -103,7 +118,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
             const CUtensorMap *tmap = tmaps + blockIdx.x;
             asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(tmap) : "memory");
             uint32_t g = 0, chunk = 0, slot = 0, pg = 0, pchunk = 0;
-            uint32_t wreg = 0, wuse = 0;  // region / use count of the group whose MMAs free the slot being refilled (group gg - n_a)
+            uint32_t wg = 0, wcr = 0, wreg = 0, wph = 0;  // the group whose MMAs free the slot being refilled (group gg - n_a): index in its chunk, chunk mod 3, region; parities
             for (uint32_t k = 0; k < T3_PF_AHEAD && pchunk < n_chunks; k++)
                 if (++pg == n_groups) { pg = 0; pchunk++; }
             for (uint32_t gg = 0; gg < total; gg++) {
@@ -112,8 +127,11 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     if (++pg == n_groups) { pg = 0; pchunk++; }
                 }
                 if (gg >= n_a) {
-                    mbar_wait_wd(smem_u32(&v_full[wreg]), wuse & 1);
-                    if (++wreg == n_vr) { wreg = 0; wuse++; }
+                    const uint32_t vb = t3_vbar(t3_owner(wcr, wg), wreg);
+                    mbar_wait_wd(smem_u32(&v_full[vb]), (wph >> vb) & 1);
+                    wph ^= 1u << vb;
+                    if (++wreg == n_vr) wreg = 0;
+                    if (++wg == n_groups) { wg = 0; if (++wcr == 3) wcr = 0; }
                 }
                 const uint32_t bar = smem_u32(&a_full[slot]);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg_max * TC_M) : "memory");
@@ -127,11 +145,14 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
     } else if (warp == T3_NT / 32 + 2) {
         // ================= vertical-weight TMA thread =================
         if (elect_one()) {
-            uint32_t g = 0, wreg = 0, wuse = 0;
+            uint32_t g = 0, wg = 0, wcr = 0, wreg = 0, wph = 0;
             for (uint32_t gg = 0; gg < total; gg++) {
                 if (gg >= T3_NB) {
-                    mbar_wait_wd(smem_u32(&v_full[wreg]), wuse & 1);  // the slot's previous tile was read by the MMAs of group gg - 2
-                    if (++wreg == n_vr) { wreg = 0; wuse++; }
+                    const uint32_t vb = t3_vbar(t3_owner(wcr, wg), wreg);
+                    mbar_wait_wd(smem_u32(&v_full[vb]), (wph >> vb) & 1);  // the slot's previous tile was read by the MMAs of group gg - 2
+                    wph ^= 1u << vb;
+                    if (++wreg == n_vr) wreg = 0;
+                    if (++wg == n_groups) { wg = 0; if (++wcr == 3) wcr = 0; }
                 }
                 const uint32_t kg = grp[4 * g + 1], b_off = grp[4 * g + 2];
                 const uint32_t bar = smem_u32(&b_full[gg & 1]);
@@ -145,7 +166,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
     } else if (warp == T3_NT / 32) {
         // ================= vertical MMA thread =================
         if (elect_one()) {
-            uint32_t g = 0, slot = 0, suse = 0, region = 0, ruse = 0;
+            uint32_t g = 0, cr = 0, slot = 0, suse = 0, region = 0, ruse = 0;
             long long w_b = 0, w_a = 0, w_r = 0;
             const long long t_start = clock64();
             for (uint32_t gg = 0; gg < total; gg++) {
@@ -167,10 +188,10 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                                  "l"(da), "l"(db), "r"(UMMA_IDESC)
                                  : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&v_full[region])) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&v_full[t3_vbar(t3_owner(cr, g), region)])) : "memory");
                 if (++slot == n_a) { slot = 0; suse++; }
                 if (++region == n_vr) { region = 0; ruse++; }
-                if (++g == n_groups) g = 0;
+                if (++g == n_groups) { g = 0; if (++cr == 3) cr = 0; }
             }
 #ifdef T3_PROF
             if (blockIdx.x == 300) printf("tc3 vertical MMA thread: total %lld clk, %u chunks x %u groups; waits: weights %lld, source rows %lld, TMEM region %lld\n", clock64() - t_start, n_chunks, n_groups, w_b, w_a, w_r);
@@ -189,16 +210,80 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                              "l"(tb + __ldg(hrec + 8 * ch)), "r"(bytes), "r"(bar)
                              : "memory");
             };
-            load_wh(0);
             long long w_wh = 0, w_tr = 0, w_df = 0, w_wf = 0;
             const long long t_start = clock64();
+            // window piece: accumulator columns [col, col + n) += T . W[brow .. brow + n), combos [c_a, c_b) of hi x hi, lo x hi, hi x lo
+            auto piece = [&](uint32_t mt, uint32_t col, uint32_t n, uint32_t brow, uint32_t b_hi0, uint32_t b_lo0, int c_a, int c_b) {
+                const uint32_t idesc = (1u << 4) | (1u << 15) | ((n >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
+                const uint32_t d_tmem = tmem_base + mt * ring_cols + col;
+                const uint32_t a_hi = sT_u + mt * 32768u, a_lo = a_hi + t_bytes;
+#pragma unroll
+                for (int combo = 0; combo < 3; combo++) {
+                    if (combo < c_a || combo >= c_b) continue;
+                    uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);
+                    uint64_t db = umma_desc((combo == 2 ? b_lo0 : b_hi0) + (brow >> 3) * 2048u, 128, 2048);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+                                     "l"(da), "l"(db), "r"(idesc)
+                                     : "memory");
+                        da += 256 >> 4;
+                        db += 256 >> 4;
+                    }
+                }
+            };
+            auto commit = [](uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); };
+            if (n_wh == 1) {
+                // ONE slot for the chunk's weight tiles (they are up to 48 KB), but its hi and lo halves have lives of their own:
+                // the hi tile is read by the hi x hi and lo x hi series, the lo tile by hi x lo only.  The last row tile's series are
+                // issued hi x hi, lo x hi, hi x lo; when the first two have retired the next chunk's hi tile is fetched under the
+                // hi x lo series, and its lo tile under the next chunk's first series -- with the whole pair fetched only once a
+                // chunk's MMAs had retired, the copy (~1.2 k clk per chunk) was exposed: 134 k of a C3 CTA's 915 k clk.
+                auto load_half = [&](uint32_t ch, uint32_t half) {  // wh_full[0 / 1], wh_free[0 / 1]: hi / lo half
+                    const uint32_t bar = smem_u32(&wh_full[half]), n_total = __ldg(hrec + 8 * ch + 4), bytes = n_total * 256u;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                    // (fixed places for the halves: the tiles of consecutive chunks differ in size, and the next hi tile lands while this lo tile is read)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sWh_u + half * (wh_bytes >> 1)),
+                                 "l"(tb + __ldg(hrec + 8 * ch) + half * bytes), "r"(bytes), "r"(bar)
+                                 : "memory");
+                };
+                load_half(0, 0);
+                load_half(0, 1);
+                for (uint32_t ch = 0; ch < n_chunks; ch++) {
+                    const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
+                    const uint32_t n1 = min(n_total, ring_cols - w0);
+                    const uint32_t b_hi0 = sWh_u, b_lo0 = b_hi0 + (wh_bytes >> 1);
+                    for (uint32_t mt = 0; mt < n_mt; mt++) {
+                        const bool last = mt + 1 == n_mt;
+                        T3WR(w_tr, smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
+                        if (ch > 0) T3WR(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
+                        if (mt == 0) T3WR(w_wh, smem_u32(&wh_full[0]), ch & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        piece(mt, w0, n1, 0, b_hi0, b_lo0, 0, 2);
+                        if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 0, 2);
+                        if (last) commit(&wh_free[0]);
+                        if (mt == 0) { T3WR(w_wh, smem_u32(&wh_full[1]), ch & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                        piece(mt, w0, n1, 0, b_hi0, b_lo0, 2, 3);
+                        if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 2, 3);
+                        commit(&d2_full[mt]);
+                        if (last) commit(&wh_free[1]);
+                    }
+                    if (ch + 1 < n_chunks) {
+                        T3WR(w_wf, smem_u32(&wh_free[0]), ch & 1);  // hi x hi and lo x hi of the last tile have retired (hi x lo is still running)
+                        load_half(ch + 1, 0);
+                        T3WR(w_wf, smem_u32(&wh_free[1]), ch & 1);
+                        load_half(ch + 1, 1);
+                    }
+                }
+            } else {
+            load_wh(0);
             for (uint32_t ch = 0; ch < n_chunks; ch++) {
-                const uint32_t slot = n_wh == 2 ? (ch & 1) : 0u;
-                if (n_wh == 2 && ch + 1 < n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
+                const uint32_t slot = ch & 1;
+                if (ch + 1 < n_chunks) {  // the other slot: free once the horizontal MMAs of chunk ch - 1 have retired
                     if (ch >= 1) T3WR(w_wf, smem_u32(&wh_free[(ch + 1) & 1]), ((ch - 1) >> 1) & 1);
                     load_wh(ch + 1);
                 }
-                T3WR(w_wh, smem_u32(&wh_full[slot]), (n_wh == 2 ? (ch >> 1) : ch) & 1);
+                T3WR(w_wh, smem_u32(&wh_full[slot]), (ch >> 1) & 1);
                 const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
                 const uint32_t n1 = min(n_total, ring_cols - w0);
                 const uint32_t b_hi0 = sWh_u + slot * wh_bytes, b_lo0 = b_hi0 + n_total * 256u;
@@ -206,34 +291,12 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     T3WR(w_tr, smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
                     if (ch > 0) T3WR(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi = sT_u + mt * 32768u, a_lo = a_hi + t_bytes;
-                    // window piece: accumulator columns [col, col + n) += T . W[brow .. brow + n)
-                    auto piece = [&](uint32_t col, uint32_t n, uint32_t brow) {
-                        const uint32_t idesc = (1u << 4) | (1u << 15) | ((n >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
-                        const uint32_t d_tmem = tmem_base + mt * ring_cols + col;
-#pragma unroll
-                        for (int combo = 0; combo < 3; combo++) {
-                            uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);
-                            uint64_t db = umma_desc((combo == 2 ? b_lo0 : b_hi0) + (brow >> 3) * 2048u, 128, 2048);
-#pragma unroll
-                            for (int ks = 0; ks < 8; ks++) {
-                                asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-                                             "l"(da), "l"(db), "r"(idesc)
-                                             : "memory");
-                                da += 256 >> 4;
-                                db += 256 >> 4;
-                            }
-                        }
-                    };
-                    piece(w0, n1, 0);
-                    if (n1 < n_total) piece(0, n_total - n1, n1);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&d2_full[mt])) : "memory");
-                    if (mt + 1 == n_mt) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&wh_free[slot])) : "memory");
+                    piece(mt, w0, n1, 0, b_hi0, b_lo0, 0, 3);
+                    if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 0, 3);
+                    commit(&d2_full[mt]);
+                    if (mt + 1 == n_mt) commit(&wh_free[slot]);
                 }
-                if (n_wh == 1 && ch + 1 < n_chunks) {  // the only slot: its tiles were read once the chunk's MMAs have retired
-                    T3WR(w_wf, smem_u32(&wh_free[0]), ch & 1);
-                    load_wh(ch + 1);
-                }
+            }
             }
 #ifdef T3_PROF
             if (blockIdx.x == 300) printf("tc3 horizontal thread: total %lld clk, n_wh %u, n_a %u, n_vr %u, ring %u; waits: weight tile landed %lld, T tile %lld, ring drained %lld, weight slot free %lld\n", clock64() - t_start, n_wh, n_a, n_vr, ring_cols, w_wh, w_tr, w_df, w_wf);
@@ -244,45 +307,47 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
     } else {
         // ================= consumer warps =================
         const float scale = it.scale, scale_hi = it.scale * 16384.0f;
-        const uint32_t q = warp & 3, half = warp >> 2, m = q * 32 + lane;
+        // Work split (t3_owner): what chunk k - 1 finished in row tile t is drained by the four warps of set (k + t) mod 3, a
+        // tile's groups (both halves of their 32 rows) are converted by the other two sets.  (Eight warps -- two per scheduler -- left the consumers latency-bound at ~0.35 IPC each and
+        // the tensor pipe waiting for them; the kernel needs ~100 registers, so twelve fit.)
+        const uint32_t q = warp & 3, set = warp >> 2, m = q * 32 + lane;
         // inverse on load applies to the colour channels of this thread's tile column (byte b0 + 128 chunk + m of the row)
         const bool inv_on = INV && !((C == 2 || C == 4) && ((it.b0 + m) % C) == C - 1);
         const uint32_t grp_rows = it.grp_rows;
         const uint32_t h_cout = it.c_out, h_pitch = it.dst_pitch, h_rows = it.band_rows, h_epi = it.epi, h_fill = it.fill;
         const uint32_t RP = ring_cols / C;
         uint8_t *const h_row0 = it.dst + size_t(it.dst_y + it.band_r0) * it.dst_pitch + size_t(it.dst_x) * h_cout;  // first canvas byte of the band
-        const uint32_t my_stage = stage_u + warp * stage_warp + 16u;  // 16 bytes in front: "word -1" of row 0 is readable
         const uint32_t stride4 = it.stage_stride * 4u;
-        // the rings start at zero: warp (q, half) clears its lanes of the tiles' columns, half of them each
-        for (uint32_t c0 = half * 16; c0 < v0; c0 += 32) tmem_st16_zero(tmem_base + ((q * 32u) << 16) + c0);
+        // the rings start at zero: warp (q, set) clears its lanes of the tiles' columns, a third of them each
+        for (uint32_t c0 = set * 16; c0 < v0; c0 += 16 * T3_SETS) tmem_st16_zero(tmem_base + ((q * 32u) << 16) + c0);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        // drain duty of this warp: with two row tiles warp (q, half) owns tile `half`; with one tile the two warps of a
-        // lane quarter split the pixels a chunk finishes
-        const uint32_t my_mt = n_mt == 2 ? half : 0u;
         const bool words_ok = h_cout == 4 && ((reinterpret_cast<uintptr_t>(h_row0) | h_pitch) & 3) == 0;  // every row segment starts on a word
 
         // the pixels chunk `chunk` finished in row tile `mt`: ring -> registers -> rounded bytes -> staging -> canvas
         long long w_v = 0, w_d2 = 0, t_dr = 0, t_v = 0;
-        long long t_ld = 0, t_zs = 0, t_wo = 0;  // T3_PROF: inside the ring drain -- TMEM loads, the wait for the zeroing stores, write-out
+        long long t_ld = 0, t_zs = 0, t_wo = 0, t_cv = 0, t_z = 0, t_sg = 0;  // T3_PROF: inside the ring drain -- TMEM loads, the wait for the zeroing stores, write-out
         const long long t_start = clock64();
-        auto drain_ring = [&](uint32_t chunk, uint32_t mt) {
+        // (fin_first, n_fin, fin_slot: the chunk's record words 1, 2, 5 -- fetched a chunk ahead by the caller: a load from
+        // global memory inside the drain cost ~0.8 k of its ~3.2 k clk)
+        auto drain_ring = [&](uint32_t chunk, uint32_t mt, uint32_t drainer, uint32_t fin_first, uint32_t n_fin, uint32_t fin_slot) {
             T3W(w_d2, smem_u32(&d2_full[mt]), chunk & 1);  // every warp: the tile's T rows may be overwritten from here on
-            if (n_mt == 2 && mt != my_mt) return;          // ... but only the tile's own four warps drain it (and arrive)
+            if (drainer != set) return;  // ... the sets take turns at draining (a drain is latency-bound: splitting one does not shorten it)
+            // staging tile of (row tile, lane quarter): its previous user -- another set, a chunk ago -- finished its write-out
+            // before it arrived at t_ready for the chunk whose horizontal MMAs this drain waited for; 16 bytes in front: "word -1" of row 0 is readable
+            const uint32_t my_stage = stage_u + (mt * 4 + q) * stage_warp + 16u;
 #ifdef T3_PROF
             const long long td0 = clock64();
             struct Acc { long long &a; long long t0; __device__ ~Acc() { a += clock64() - t0; } } acc_{t_dr, td0};
 #endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t fin_first = __ldg(hrec + 8 * chunk + 1), n_fin = __ldg(hrec + 8 * chunk + 2), fin_slot = __ldg(hrec + 8 * chunk + 5);
-            uint32_t p0 = 0, p1 = n_fin;  // this warp's share of the finished pixels
-            if (n_mt == 1) { const uint32_t hsplit = (n_fin + 1) / 2; p0 = half ? hsplit : 0u; p1 = half ? n_fin : hsplit; }
+            constexpr uint32_t PB = 16 / C;
+            const uint32_t p0 = 0, p1 = n_fin;
             const uint32_t tbase = tmem_base + mt * ring_cols + ((q * 32u) << 16);
             const uint32_t sw = my_stage + lane * stride4;
             __syncwarp();  // the previous chunk's words have left the staging tile
             // Batches of PB = 16 / C pixels: ONE tcgen05.ld of 16 columns (what it reads past the batch is ignored) and one
             // to four stores that zero exactly the batch's columns, a batch ending where the ring wraps.  Per-pixel loads and stores cost an issue slot each next to a tensor core
             // that keeps the shared-memory and TMEM ports busy (measured: 6.4 k clk per chunk for 15 RGBA pixels).
-            constexpr uint32_t PB = 16 / C;
             uint32_t slot = fin_slot + p0;
             if (slot >= RP) slot -= RP;
             for (uint32_t pb = p0; pb < p1;) {
@@ -312,6 +377,10 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                         if ((h_epi & EPI_MASK) == EPI_BLEND_FILL) px[i] = blend_rgba(h_fill, px[i]);
                     }
                 }
+#ifdef T3_PROF
+                const long long tc1 = clock64();
+                t_cv += tc1 - tl0;
+#endif
                 // zero exactly the columns of the np pixels read: the neighbouring columns belong to live outputs, or to the
                 // pixels the other warp of this lane quarter drains
                 {
@@ -337,6 +406,10 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                         }
                     }
                 }
+#ifdef T3_PROF
+                const long long tc2 = clock64();
+                t_z += tc2 - tc1;
+#endif
                 const uint32_t sp = sw + (pb - p0) * h_cout;  // staged at its byte offset within this warp's segment
                 if (h_cout == 4) {
                     if constexpr (PB == 4) {
@@ -361,6 +434,9 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                                 if (c < h_cout) sts8(sp + i * h_cout + c, px[i] >> (8 * c));
                         }
                 }
+#ifdef T3_PROF
+                t_sg += clock64() - tc2;
+#endif
                 pb += np;
                 slot += np;
                 if (slot >= RP) slot -= RP;
@@ -432,26 +508,36 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
             }
         };
 
-        uint32_t gg = 0, region = 0, ruse = 0;
+        uint32_t gg = 0, region = 0, vph = 0, cr = 0;  // vph: parities of this set's v_full barriers; cr = chunk mod 3
+        uint32_t rc0 = 0, rc1 = 0, rc2 = 0, rn0 = 0, rn1 = 0, rn2 = 0;  // record of the chunk being drained (chunk - 1) / of this chunk
         for (uint32_t chunk = 0; chunk < n_chunks; chunk++) {
+            rc0 = rn0; rc1 = rn1; rc2 = rn2;
+            rn0 = __ldg(hrec + 8 * chunk + 1); rn1 = __ldg(hrec + 8 * chunk + 2); rn2 = __ldg(hrec + 8 * chunk + 5);
             for (uint32_t g = 0; g < n_groups; g++, gg++) {
                 // the tile's rows are about to be overwritten: its horizontal MMAs of the previous chunk must have retired --
                 // which is also when the pixels they finished can be drained
-                if ((g & 3) == 0 && chunk > 0) drain_ring(chunk - 1, g >> 2);
-                T3W(w_v, smem_u32(&v_full[region]), ruse & 1);  // the vertical MMAs of group gg have retired
+                if ((g & 3) == 0 && chunk > 0) drain_ring(chunk - 1, g >> 2, (g >> 2) ? (cr == 2 ? 0u : cr + 1) : cr, rc0, rc1, rc2);
+                const bool mine = t3_owner(cr, g) == set;
+                if (mine) {
+                const uint32_t vb = t3_vbar(set, region);
+                T3W(w_v, smem_u32(&v_full[vb]), (vph >> vb) & 1);  // the vertical MMAs of group gg have retired
+                vph ^= 1u << vb;
 #ifdef T3_PROF
                 const long long tv0 = clock64();
 #endif
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (uint32_t half = 0; half < 2; half++) {  // rows 0-15, 16-31 of the group
                 const uint32_t taddr = tmem_base + v0 + region * TC_N + ((q * 32u) << 16) + half * 16;
                 uint32_t hi[16], mid[16], lo[16];
                 tmem_ld16(taddr, hi);
                 tmem_ld16(taddr + 32, mid);
                 tmem_ld16(taddr + 64, lo);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                if (lane == 0) t3_arrive(smem_u32(&v_free[region]));
-                if (++region == n_vr) { region = 0; ruse++; }
+                if (half == 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0) t3_arrive(smem_u32(&v_free[region]));
+                }
                 uint32_t ph[8], pl[8];
 #pragma unroll
                 for (int e = 0; e < 16; e += 2) {  // value = (hi 2^14 + mid 2^7 + lo) 2^-s, two rows per f32x2 op
@@ -475,23 +561,27 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                 sts128(t0 + 2048, ph[4], ph[5], ph[6], ph[7]);
                 sts128(t0 + t_bytes, pl[0], pl[1], pl[2], pl[3]);
                 sts128(t0 + t_bytes + 2048, pl[4], pl[5], pl[6], pl[7]);
+                }
+#ifdef T3_PROF
+                t_v += clock64() - tv0;
+#endif
+                }
+                if (++region == n_vr) region = 0;
                 if ((g & 3) == 3 || g + 1 == n_groups) {  // the row tile is complete: hand it to the tensor core
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) t3_arrive(smem_u32(&t_ready[g >> 2]));
                 }
-#ifdef T3_PROF
-                t_v += clock64() - tv0;
-#endif
             }
+            if (++cr == 3) cr = 0;
         }
-        drain_ring(n_chunks - 1, 0);
-        if (n_mt > 1) drain_ring(n_chunks - 1, 1);
+        drain_ring(n_chunks - 1, 0, cr, rn0, rn1, rn2);  // (cr = n_chunks mod 3 here)
+        if (n_mt > 1) drain_ring(n_chunks - 1, 1, cr == 2 ? 0u : cr + 1, rn0, rn1, rn2);
 #ifdef T3_PROF
-        if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 5))
-            printf("tc3 consumer warp %u: total %lld clk; waits: vertical results %lld, ring ready %lld; vertical drain %lld, ring drain + write-out %lld (TMEM loads %lld, wait for zeroing stores %lld, write-out %lld)\n", warp, clock64() - t_start, w_v, w_d2, t_v, t_dr, t_ld, t_zs, t_wo);
+        if (blockIdx.x == 300 && lane == 0 && (warp == 0 || warp == 5 || warp == 10))
+            printf("tc3 consumer warp %u: total %lld clk; waits: vertical results %lld, ring ready %lld; vertical drain %lld, ring drain + write-out %lld (TMEM loads %lld, load + convert %lld, zeroing %lld, staging %lld, wait for zeroing stores %lld, write-out %lld)\n", warp, clock64() - t_start, w_v, w_d2, t_v, t_dr, t_ld, t_cv, t_z, t_sg, t_zs, t_wo);
 #else
-        (void)t_start; (void)w_v; (void)w_d2; (void)t_dr; (void)t_v; (void)t_ld; (void)t_zs; (void)t_wo;
+        (void)t_start; (void)w_v; (void)w_d2; (void)t_dr; (void)t_v; (void)t_ld; (void)t_zs; (void)t_wo; (void)t_cv; (void)t_z; (void)t_sg;
 #endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
