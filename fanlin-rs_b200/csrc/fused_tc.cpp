@@ -431,7 +431,7 @@ static bool try_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTa
     const int sh = weight_shift(*s.vtab);
     bool fits = false;
     uint32_t band_rows = s.n_rows;
-    for (uint32_t n_bands = 1; n_bands <= 64 && !fits; n_bands++) {
+    for (uint32_t n_bands = std::max(1u, s.min_bands); n_bands <= 64 && !fits; n_bands++) {
         band_rows = (s.n_rows + n_bands - 1) / n_bands;
         fits = true;
         for (uint32_t r0 = 0; r0 < s.n_rows && fits; r0 += band_rows) {
@@ -462,7 +462,7 @@ static bool try_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTa
 }
 
 static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTables *tabs, FusedTcTables *tct) {
-    const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c | (s.c_out << 8));
+    const TcKey key(s.vtab.get(), s.htab.get(), s.oy0 | (s.n_rows << 16), s.ox0 | (s.n_cols << 16), s.c | (s.c_out << 8) | (s.min_bands << 16));
     auto it = cache->geoms.find(key);
     if (it != cache->geoms.end()) return it->second;
     TcGeom g;
@@ -493,8 +493,8 @@ static const TcGeom &geom_of(const StagePlan &s, FusedTcCache *cache, FusedTable
             hm_out_stride = ((widest * s.c_out + 6) / 4) | 1u;
         }
         bool fits = false;
-        uint32_t n_bands = 1, band_rows = s.n_rows;
-        for (; n_bands <= 8 && !fits; n_bands++) {
+        uint32_t n_bands = std::max(1u, s.min_bands), band_rows = s.n_rows;
+        for (; n_bands <= std::max(8u, s.min_bands) && !fits; n_bands++) {
             band_rows = (s.n_rows + n_bands - 1) / n_bands;
             fits = true;
             for (uint32_t r0 = 0; r0 < s.n_rows && fits; r0 += band_rows) {

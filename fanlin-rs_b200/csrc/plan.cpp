@@ -200,6 +200,7 @@ StagePlan stored_axes_stage(const StagePlan &a, const fanlin_job &stored, uint32
     if (in.htab) window(*in.htab, in.ox0, in.n_cols, &in.sx0, &in.n_sx);
     if (in.vtab) window(*in.vtab, in.oy0, in.n_rows, &in.sy0, &in.n_sy);
     in.canvas_w = in.n_cols; in.canvas_h = in.n_rows; in.c_out = in.c; in.dst_x = in.dst_y = 0; in.epi = EPI_PLAIN; in.fill = 0;
+    in.min_bands = a.min_bands;
     return in;
 }
 

@@ -50,6 +50,8 @@ struct StagePlan {
     uint32_t sx0 = 0, n_sx = 0, sy0 = 0, n_sy = 0;
     uint32_t canvas_w = 0, canvas_h = 0, c_out = 0, dst_x = 0, dst_y = 0, epi = EPI_PLAIN, fill = 0;
     uint32_t canvas_pitch = 0;  // bytes per canvas row when the canvas is scratch with padded rows (0: canvas_w * c_out)
+    uint32_t min_bands = 1;     // tensor-core resample: cut the image into at least this many bands (CTAs) -- set for small batches, where
+                                // one CTA per image would leave the GPU to a handful of SMs (latency of a single request)
     std::shared_ptr<const AxisTable> vtab, htab;
 };
 

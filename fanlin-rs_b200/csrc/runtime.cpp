@@ -185,6 +185,7 @@ extern "C" int fanlin_init(const int *device_ids, int n_devices, const fanlin_co
     if (cfg) std::memcpy(&ctx->cfg, cfg, std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(*cfg), sizeof(*cfg)));
     if (!ctx->cfg.device_scratch_bytes) ctx->cfg.device_scratch_bytes = uint64_t(8) << 30;
     if (!ctx->cfg.pinned_bytes) ctx->cfg.pinned_bytes = uint64_t(2) << 30;
+    ctx->adaptive_window = ctx->cfg.batch_window_us == 0;  // default: no idle wait in the request batcher (batcher_main)
     if (!ctx->cfg.batch_window_us) ctx->cfg.batch_window_us = 200;
     if (!ctx->cfg.max_batch_jobs) ctx->cfg.max_batch_jobs = 4096;
     ctx->pinned.set_limit(ctx->cfg.pinned_bytes);
@@ -398,6 +399,12 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             return FANLIN_ECAPACITY;
         }
         if (plans_out) plans_out[i] = b->plans[i].pub;
+        if (n_jobs < 74 && b->plans[i].a.present && b->plans[i].a.separable && b->plans[i].a.v_kind == KIND_LANCZOS3) {
+            // a handful of requests: cut each image into bands, so that its resample runs on 148 / n_jobs SMs instead of one
+            // (a single C2 request spent 0.19 of its 0.86 ms in a one-CTA kernel); bands of >= 24 rows, so that a band is about a group
+            const uint32_t by_rows = std::max(1u, b->plans[i].a.n_rows / 24u);
+            b->plans[i].a.min_bands = std::max(1u, std::min({148u / n_jobs, by_rows, 48u}));
+        }
         deep_a[i] = b->plans[i].a.present && b->plans[i].a.s_in != SAMPLE_U8;
         deep_b[i] = b->plans[i].b.present && b->plans[i].b.s_in != SAMPLE_U8;
         if (late_orient_on && !exact && use_tc && jobs[i].src_sample == SAMPLE_U8 && b->plans[i].pre.present && b->plans[i].a.present && b->plans[i].a.separable &&
@@ -1253,6 +1260,10 @@ static void batcher_main(fanlin_ctx *ctx, int dev_index) {
                     dev->queue.pop_front();
                 }
                 if (jobs >= ctx->cfg.max_batch_jobs || dev->stop) break;
+                // default (batch_window_us left 0): no idle wait -- what is queued goes now, what arrives while this batch runs is
+                // merged into the next one (queues form exactly when the device is busy).  A lone client used to see the whole
+                // window, 200 us, on every request.  An explicit batch_window_us keeps the fixed window.
+                if (ctx->adaptive_window) break;
                 if (dev->qcv.wait_until(lk, deadline) == std::cv_status::timeout && dev->queue.empty()) break;
             }
         }

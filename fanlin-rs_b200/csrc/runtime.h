@@ -103,6 +103,7 @@ struct fanlin_ctx {
     std::atomic<uint64_t> kernel_launches{0}, jobs{0}, batches{0}, h2d_bytes{0}, d2h_bytes{0}, table_bytes{0};
     std::atomic<uint32_t> rr{0};
     std::atomic<bool> down{false};
+    bool adaptive_window = false;  // batch_window_us was left at its default: the request batcher does not wait when its queue is empty
 };
 
 struct fanlin_batch {

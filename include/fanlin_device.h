@@ -113,7 +113,9 @@ typedef struct fanlin_config {
     uint32_t exact;              /* 1: crate operation order, no FMA contraction (bit-exact to the CPU path, slower) */
     uint64_t device_scratch_bytes; /* per-device arena for staging + intermediates; 0 = default */
     uint64_t pinned_bytes;       /* per-device pinned staging ring; 0 = default */
-    uint32_t batch_window_us;    /* request batcher collection window; 0 = default */
+    uint32_t batch_window_us;    /* request batcher: 0 = default, no idle wait (what is queued is dispatched at once; requests that
+                                    arrive while a batch runs are merged into the next one); > 0: the collector waits this long
+                                    after the first arrival before it dispatches */
     uint32_t max_batch_jobs;     /* 0 = default */
     uint32_t vertical_path;      /* 0 = tensor cores, both Lanczos3 passes where the geometry allows (tables are cached per geometry in the context, so single requests take them too); 1 = CUDA cores only; 2 = tensor cores for the vertical pass only; 3 = same as 0 (kept from ABI 1, where 0 needed >= 256 jobs per batch) */
     uint32_t blur_path;          /* 0 = both blur passes on the tensor cores where eligible (no f32 intermediate in HBM); 1 = the two-kernel blur (vertical pass on the tensor cores, horizontal on the CUDA cores) */
