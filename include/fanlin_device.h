@@ -59,8 +59,8 @@ enum fanlin_flags {
     FANLIN_CROP = 1u << 3,      /* Query::cropping()   src/query.rs:55-57 -> resize_to_fill */
     FANLIN_TO_RGBA8 = 1u << 4,  /* GIF frames end with img.to_rgba8()  src/handler.rs:355; also the WebP branch's into_rgba8() (:287) */
     FANLIN_TO_RGB8 = 1u << 5,   /* the JPEG branch: the encoder works on RGB8 (src/handler.rs:274-278), DynamicImage::to_rgb8 --
-                                   alpha dropped, luma replicated; not together with FANLIN_TO_RGBA8.  Folded into the last
-                                   kernel's epilogue where that kernel writes the final image (no extra pass) */
+                                   alpha dropped, luma replicated; not together with FANLIN_TO_RGBA8.  For request-sized batches
+                                   folded into the epilogue of the kernel that writes the final image (no extra pass) */
     FANLIN_TO_YCBCR = 1u << 6   /* the JPEG branch, one step further: the result as the three full-resolution
                                    planes Y, Cb, Cr the JPEG encoder derives from it -- image-0.25.6 codecs/jpeg/encoder.rs
                                    rgb_to_ycbcr on to_rgb8() of the result (f32, JFIF coefficients x 255, truncating cast);

@@ -15,6 +15,7 @@ SHAPES = {"c1": (512, 512, 3, "w=300&h=200&rgb=32,32,32"), "c2": (1080, 1920, 3,
           "c5": (3000, 4000, 1, "w=1618&h=1000&crop=true")}
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 148
+rgb8 = "--rgb8" in sys.argv  # FANLIN_TO_RGB8: the JPEG branch's layout from the kernel's epilogue
 h, w, c, qs = SHAPES[which]
 pkg = G.load_package()
 dev = pkg.Device([0], vertical_path=3)
@@ -24,6 +25,8 @@ q = pkg.Query(qs)
 proto = pkg.Job()
 pkg.lib().fanlin_job_from_query(C.byref(q._q), 0, C.byref(proto))
 proto.src_w, proto.src_h, proto.src_channels = w, h, c
+if rgb8:
+    proto.flags |= 1 << 5
 plan = pkg.plan_job(proto)
 dst = torch.zeros((n, plan.out_h, plan.out_w, plan.out_channels), dtype=torch.uint8, device=device)
 jobs = (pkg.Job * n)()
@@ -41,6 +44,6 @@ torch.cuda.synchronize()
 per = {}
 for k, v in b.kernel_times():
     per.setdefault(k, []).append(v)
-print(which, f"batch {n}:", {k: round(min(v) * 1e3 / n, 2) for k, v in per.items()}, "us per image", flush=True)
+print(which + (" rgb8" if rgb8 else ""), f"batch {n}:", {k: round(min(v) * 1e3 / n, 2) for k, v in per.items()}, "us per image", flush=True)
 b.free()
 dev.close()
