@@ -92,18 +92,20 @@ __device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t colo
 // GIF frames (handler.rs:338,340), which is a gather: with tables (v_tab != NO_TABLE) the source
 // pixel of an output is (h_tab[x].left, v_tab[y].left), its single tap.  Four consecutive canvas
 // pixels of a row per thread; RGBA output leaves as one 16-byte store when the row allows.
+constexpr uint32_t CMP_ROWS = 4;
 __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs, const TapEntry *__restrict__ tab) {
     const StageDesc &d = descs[blockIdx.y];
     const uint32_t cw = d.canvas_w, ch = d.canvas_h;
     const uint32_t xtiles = (cw + 4 * TX - 1) / (4 * TX);
-    if (blockIdx.x >= ch * xtiles) return;
-    const uint32_t cy = blockIdx.x / xtiles;
+    if (blockIdx.x >= ((ch + CMP_ROWS - 1) / CMP_ROWS) * xtiles) return;
+    const uint32_t cy0 = (blockIdx.x / xtiles) * CMP_ROWS;  // CMP_ROWS canvas rows per block (one row per block: 54 k blocks of 120 busy threads for C4)
     const uint32_t cx0 = ((blockIdx.x % xtiles) * TX + threadIdx.x) * 4;
     if (cx0 >= cw) return;
     const uint32_t c_mem = d.c_mem, C = d.c, c_out = d.c_out, epi = d.epi & EPI_MASK, fill = d.fill, color_op = d.color_op;  // (EPI_RGB8: c_out = 3 bytes of the packed pixel leave)
     const uint32_t dst_x = d.dst_x, dst_y = d.dst_y, n_cols = d.n_cols, n_rows = d.n_rows;
-    const bool row_in = cy >= dst_y && cy - dst_y < n_rows;
     const bool gather = d.v_tab != NO_TABLE;
+    for (uint32_t cy = cy0; cy < min(cy0 + CMP_ROWS, ch); cy++) {
+    const bool row_in = cy >= dst_y && cy - dst_y < n_rows;
     const uint32_t sy = !row_in ? 0u : gather ? tab[d.v_tab + d.oy0 + (cy - dst_y)].left : d.oy0 + (cy - dst_y);
     const uint8_t *srow = d.src + size_t(sy) * d.src_pitch;
     const uint32_t ox0 = d.ox0, h_tab = d.h_tab;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
     } else {
         for (uint32_t k = 0; k < n; k++)
             for (uint32_t b = 0; b < c_out; b++) q[k * c_out + b] = uint8_t(out[k] >> (8 * b));
+    }
     }
 }
 
@@ -215,11 +218,51 @@ __global__ void __launch_bounds__(256) color_pass_kernel(const StageDesc *__rest
 __global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restrict__ descs) {
     const StageDesc &d = descs[blockIdx.y];
     const uint32_t n = d.canvas_w * d.canvas_h, c = d.c_mem;
-    for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const bool planes = d.epi != 0;  // FANLIN_TO_YCBCR: three planes of n bytes instead of interleaved RGB
+    // four pixels per thread through whole words (one byte per access made this pass cost as much as the resample of a
+    // C1 image: 0.35 us); the tail, unaligned buffers and planes of a size that is not a multiple of four go pixel by pixel
+    const bool vec = (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.dst) & 3) == 0 && (!planes || (n & 3) == 0);
+    const uint32_t n4 = vec ? n / 4 : 0;
+    for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n4; t += gridDim.x * 256) {
+        uint32_t px[4];  // r | g << 8 | b << 16 of pixels 4 t .. 4 t + 3
+        if (c == 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(d.src) + t);
+            px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+        } else if (c == 3) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(d.src) + 3 * size_t(t);
+            const uint32_t a0 = __ldg(w), a1 = __ldg(w + 1), a2 = __ldg(w + 2);
+            px[0] = a0; px[1] = a0 >> 24 | a1 << 8; px[2] = a1 >> 16 | a2 << 16; px[3] = a2 >> 8;
+        } else if (c == 2) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(d.src) + t);
+            px[0] = (v.x & 0xffu) * 0x010101u; px[1] = ((v.x >> 16) & 0xffu) * 0x010101u;
+            px[2] = (v.y & 0xffu) * 0x010101u; px[3] = ((v.y >> 16) & 0xffu) * 0x010101u;
+        } else {
+            const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(d.src) + t);
+#pragma unroll
+            for (int k = 0; k < 4; k++) px[k] = ((v >> (8 * k)) & 0xffu) * 0x010101u;
+        }
+        if (planes) {
+            uint32_t wy = 0, wb = 0, wr = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint8_t y, cb, cr;
+                rgb_to_ycbcr_u8(px[k] & 0xffu, (px[k] >> 8) & 0xffu, (px[k] >> 16) & 0xffu, &y, &cb, &cr);
+                wy |= uint32_t(y) << (8 * k); wb |= uint32_t(cb) << (8 * k); wr |= uint32_t(cr) << (8 * k);
+            }
+            uint32_t *o = reinterpret_cast<uint32_t *>(d.dst);
+            o[t] = wy; o[n / 4 + t] = wb; o[n / 2 + t] = wr;
+        } else {
+            uint32_t *o = reinterpret_cast<uint32_t *>(d.dst) + 3 * size_t(t);
+            o[0] = (px[0] & 0xffffffu) | px[1] << 24;
+            o[1] = ((px[1] >> 8) & 0xffffu) | px[2] << 16;
+            o[2] = ((px[2] >> 16) & 0xffu) | px[3] << 8;
+        }
+    }
+    for (uint32_t i = 4 * n4 + blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const uint8_t *p = d.src + size_t(i) * c;
         uint8_t *o = d.dst + size_t(i) * 3;
         const uint8_t r = p[0], g = c <= 2 ? r : p[1], b = c <= 2 ? r : p[2];
-        if (d.epi) { rgb_to_ycbcr_u8(r, g, b, d.dst + i, d.dst + n + i, d.dst + 2 * size_t(n) + i); continue; }  // FANLIN_TO_YCBCR: planes
+        if (planes) { rgb_to_ycbcr_u8(r, g, b, d.dst + i, d.dst + n + i, d.dst + 2 * size_t(n) + i); continue; }
         o[0] = r; o[1] = g; o[2] = b;
     }
 }
@@ -353,7 +396,9 @@ int launch_ycck_to_cmyk(const uint8_t *d_src, uint8_t *d_dst, size_t n_px, Launc
 
 int launch_to_rgb8(const StageDesc *d_descs, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0 || !g.max_canvas_w || !g.max_canvas_h) return 0;
-    const uint32_t blocks = std::min<uint32_t>(1024, (g.max_canvas_w * g.max_canvas_h + 255) / 256);
+    // four pixels per thread and about four steps per thread: a 300x200 output is 15 blocks (one pixel per thread and step
+    // made the pass a quarter of a million tiny blocks per 1024 images)
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>(256, (g.max_canvas_w * g.max_canvas_h + 4095) / 4096));
     lc.begin("to_rgb8_kernel");
     to_rgb8_kernel<<<dim3(blocks, g.n_jobs), 256, 0, lc.st>>>(d_descs);
     lc.end();
@@ -391,7 +436,7 @@ int launch_sep_exact(const StageDesc *d_descs, const TapEntry *d_tab, const floa
 
 int launch_compose(const StageDesc *d_descs, const TapEntry *d_tab, const LaunchGeom &g, LaunchCtx &lc) {
     if (g.n_jobs == 0) return 0;
-    const uint32_t hx = g.max_canvas_h * ((g.max_canvas_w + 4 * TX - 1) / (4 * TX));  // four pixels per thread
+    const uint32_t hx = ((g.max_canvas_h + CMP_ROWS - 1) / CMP_ROWS) * ((g.max_canvas_w + 4 * TX - 1) / (4 * TX));  // four pixels per thread, CMP_ROWS rows per block
     if (!hx) return 0;
     lc.begin("compose_kernel");
     compose_kernel<<<dim3(hx, g.n_jobs), TX, 0, lc.st>>>(d_descs, d_tab);
