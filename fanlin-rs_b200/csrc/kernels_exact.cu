@@ -92,13 +92,13 @@ __device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t colo
 // GIF frames (handler.rs:338,340), which is a gather: with tables (v_tab != NO_TABLE) the source
 // pixel of an output is (h_tab[x].left, v_tab[y].left), its single tap.  Four consecutive canvas
 // pixels of a row per thread; RGBA output leaves as one 16-byte store when the row allows.
-constexpr uint32_t CMP_ROWS = 4;
+constexpr uint32_t CMP_ROWS = 1;  // canvas rows per block (4 measured slower on C4: 0.100 vs 0.091 ms per 200 frames -- the rows of a thread are a serial chain of loads)
 __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs, const TapEntry *__restrict__ tab) {
     const StageDesc &d = descs[blockIdx.y];
     const uint32_t cw = d.canvas_w, ch = d.canvas_h;
     const uint32_t xtiles = (cw + 4 * TX - 1) / (4 * TX);
     if (blockIdx.x >= ((ch + CMP_ROWS - 1) / CMP_ROWS) * xtiles) return;
-    const uint32_t cy0 = (blockIdx.x / xtiles) * CMP_ROWS;  // CMP_ROWS canvas rows per block (one row per block: 54 k blocks of 120 busy threads for C4)
+    const uint32_t cy0 = (blockIdx.x / xtiles) * CMP_ROWS;  // CMP_ROWS canvas rows per block
     const uint32_t cx0 = ((blockIdx.x % xtiles) * TX + threadIdx.x) * 4;
     if (cx0 >= cw) return;
     const uint32_t c_mem = d.c_mem, C = d.c, c_out = d.c_out, epi = d.epi & EPI_MASK, fill = d.fill, color_op = d.color_op;  // (EPI_RGB8: c_out = 3 bytes of the packed pixel leave)
