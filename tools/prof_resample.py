@@ -12,7 +12,8 @@ import __graft_entry__ as G  # noqa: E402
 import torch  # noqa: E402
 
 SHAPES = {"c1": (512, 512, 3, "w=300&h=200&rgb=32,32,32"), "c2": (1080, 1920, 3, "w=300&h=200"), "c3": (2160, 3840, 4, "w=1618&h=1000&crop=true"),
-          "c5": (3000, 4000, 1, "w=1618&h=1000&crop=true")}
+          "c5": (3000, 4000, 1, "w=1618&h=1000&crop=true"),
+          "c1crop": (512, 512, 3, "w=300&h=200&crop=true"), "c2crop": (1080, 1920, 3, "w=300&h=200&crop=true")}  # plain RGB out (the JPEG crop request)
 which = sys.argv[1] if len(sys.argv) > 1 else "c3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 rgb8 = "--rgb8" in sys.argv  # FANLIN_TO_RGB8: the JPEG branch's layout from the kernel's epilogue
