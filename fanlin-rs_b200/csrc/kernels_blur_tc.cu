@@ -231,6 +231,7 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
         // segment leave as bytes.
         const uint32_t my_stage = stage_u + warp * BT_STAGE_WARP + 16u;  // 16 bytes in front: "word -1" of row 0 is readable
         const bool words_ok = ((reinterpret_cast<uintptr_t>(dst0) | dst_pitch) & 3) == 0;  // every row segment starts on a word
+        const bool direct_ok = ((reinterpret_cast<uintptr_t>(dst0) | dst_pitch) & 7) == 0;  // every row starts on an 8-byte boundary (c0s is a multiple of 16)
         const bool halves_ok = ((reinterpret_cast<uintptr_t>(dst0) | dst_pitch | n_e) & 1) == 0;  // ... on a 2-byte boundary, and ends on one
         const uint32_t c_lo = it.c_lo, c_hi = it.c_hi;  // output bytes [c_lo, c_hi) have the whole window inside the row: factor 1 / 16
         auto drain_h = [&](uint32_t jj) {
@@ -274,6 +275,25 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
                             round_u8(__uint_as_float(v[4 * k + 2]) * c4.z) << 16 | round_u8(__uint_as_float(v[4 * k + 3]) * c4.w) << 24;
                 }
             }
+#ifndef BT_NO_DIRECT
+            // whole, 8-byte aligned segments of rows on an 8-byte stride leave straight from the registers: a thread holds the
+            // 32 bytes of ITS row, i.e. one whole sector -- two 16-byte or four 8-byte stores per thread instead of 8 staging
+            // stores, 8 staged loads and 8 word stores per warp
+            if (direct_ok && lo_b == 0 && hi_b == 32) {
+                uint8_t *g = dst0 + size_t(row) * dst_pitch + c0s;
+                if (row < band_rows) {
+                    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+                        *reinterpret_cast<uint4 *>(g) = make_uint4(w8[0], w8[1], w8[2], w8[3]);
+                        *reinterpret_cast<uint4 *>(g + 16) = make_uint4(w8[4], w8[5], w8[6], w8[7]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) *reinterpret_cast<uint2 *>(g + 8 * k) = make_uint2(w8[2 * k], w8[2 * k + 1]);
+                    }
+                }
+                BT_ACC(p_h);
+                return;
+            }
+#endif
             __syncwarp();  // the previous segment's words have left the staging tile
             const uint32_t sw = my_stage + lane * 36u;
 #pragma unroll
