@@ -14,6 +14,11 @@ enum Epilogue : uint32_t { EPI_PLAIN = 0, EPI_BLEND_FILL = 1, EPI_TO_RGBA = 2 };
 // runtime.cpp sets it only where one of them writes the final image.
 constexpr uint32_t EPI_RGB8 = 4u;
 constexpr uint32_t EPI_MASK = 3u;
+// Flag on EPI_BLEND_FILL for a one-channel image on a GRAY fill colour with a blur behind it: the canvas holds one byte per
+// pixel (c_out = 1) -- the luma where the image lies (an opaque pixel blended onto the fill is the pixel), the fill's gray value
+// in the bars; the blur runs on that plane and a last pass expands it to (l, l, l, 255).  All four channels of the Rgba<u8>
+// canvas the reference blurs are this plane or the constant 255, so the result is the same and the blur moves a quarter of the bytes.
+constexpr uint32_t EPI_GRAY = 8u;
 enum FilterKind : uint32_t { KIND_NEAREST = 0, KIND_LANCZOS3 = 1, KIND_GAUSSIAN = 100 };
 
 // Subpixel types (enum fanlin_sample) and their size in bytes.

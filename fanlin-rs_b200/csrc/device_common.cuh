@@ -87,7 +87,7 @@ __device__ __forceinline__ void store_rgba(uint8_t *q, uint32_t px) {
 // Writes one produced pixel (channel values v[0..d.c)) to canvas position (cx, cy).
 __device__ __forceinline__ void store_px(const StageDesc &d, uint32_t cx, uint32_t cy, const uint32_t v[4]) {
     uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx) * d.c_out;
-    if (d.epi == EPI_PLAIN) {
+    if (d.epi == EPI_PLAIN || (d.epi & EPI_GRAY)) {  // (gray canvas: the opaque one-channel pixel itself)
         for (uint32_t k = 0; k < d.c; k++) q[k] = uint8_t(v[k]);
     } else {
         uint32_t px = to_rgba_packed(v, d.c);
@@ -114,6 +114,7 @@ __device__ __forceinline__ void store_fill(const StageDesc &d, uint32_t cx, uint
         q[0] = uint8_t(d.fill); q[1] = uint8_t(d.fill >> 8); q[2] = uint8_t(d.fill >> 16);
         return;
     }
+    if (d.epi & EPI_GRAY) { d.dst[size_t(cy) * d.dst_pitch + cx] = uint8_t(d.fill); return; }
     store_rgba(d.dst + size_t(cy) * d.dst_pitch + size_t(cx) * 4, d.fill);
 }
 

@@ -71,6 +71,20 @@ __device__ __forceinline__ void emit_px(const ITEM &it, uint32_t cx, uint32_t cy
 template <typename ITEM>
 __device__ __forceinline__ void fill_bars(const ITEM &it, uint32_t warp, uint32_t lane, uint32_t n_warps) {
     if ((it.epi & EPI_MASK) != EPI_BLEND_FILL) return;
+    if (it.epi & EPI_GRAY) {  // one-byte canvas: the fill's gray value
+        uint8_t *const dst = it.dst;
+        const uint32_t pitch = it.dst_pitch, cw = it.canvas_w, v = it.fill & 0xffu;
+        const uint32_t iy0 = it.dst_y + it.band_r0, iy1 = iy0 + it.band_rows;
+        const uint32_t ya = it.first_band ? 0u : iy0, yb = it.last_band ? it.canvas_h : iy1;
+        const uint32_t x0 = it.dst_x, x1 = it.dst_x + it.n_cols;
+        for (uint32_t y = ya + warp; y < yb; y += n_warps) {
+            uint8_t *row = dst + size_t(y) * pitch;
+            const bool img_row = y >= iy0 && y < iy1;
+            for (uint32_t x = lane; x < cw; x += 32)
+                if (!(img_row && x >= x0 && x < x1)) row[x] = uint8_t(v);
+        }
+        return;
+    }
     if (it.epi & EPI_RGB8) {  // RGB8 canvas: the fill colour without its alpha byte
         uint8_t *const dst = it.dst;
         const uint32_t pitch = it.dst_pitch, cw = it.canvas_w, fill = it.fill;

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restric
     const bool planes = d.epi != 0;  // FANLIN_TO_YCBCR: three planes of n bytes instead of interleaved RGB
     // four pixels per thread through whole words (one byte per access made this pass cost as much as the resample of a
     // C1 image: 0.35 us); the tail, unaligned buffers and planes of a size that is not a multiple of four go pixel by pixel
-    const bool vec = (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.dst) & 3) == 0 && (!planes || (n & 3) == 0);
+    const uint32_t c_out = d.c_out;  // 3, or 4 = (l, l, l, 255) of a one-channel image (the expansion behind a gray canvas, EPI_GRAY)
+    const bool vec = (reinterpret_cast<uintptr_t>(d.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.dst) & (c_out == 4 ? 15 : 3)) == 0 && (!planes || (n & 3) == 0);
     const uint32_t n4 = vec ? n / 4 : 0;
     for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n4; t += gridDim.x * 256) {
         uint32_t px[4];  // r | g << 8 | b << 16 of pixels 4 t .. 4 t + 3
@@ -241,7 +242,10 @@ __global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restric
 #pragma unroll
             for (int k = 0; k < 4; k++) px[k] = ((v >> (8 * k)) & 0xffu) * 0x010101u;
         }
-        if (planes) {
+        if (c_out == 4) {  // behind a gray canvas: (l, l, l, 255)
+            uint4 o4 = make_uint4(px[0] | 0xff000000u, px[1] | 0xff000000u, px[2] | 0xff000000u, px[3] | 0xff000000u);
+            reinterpret_cast<uint4 *>(d.dst)[t] = o4;
+        } else if (planes) {
             uint32_t wy = 0, wb = 0, wr = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -262,6 +266,7 @@ __global__ void __launch_bounds__(256) to_rgb8_kernel(const StageDesc *__restric
         const uint8_t *p = d.src + size_t(i) * c;
         uint8_t *o = d.dst + size_t(i) * 3;
         const uint8_t r = p[0], g = c <= 2 ? r : p[1], b = c <= 2 ? r : p[2];
+        if (c_out == 4) { uint8_t *o4 = d.dst + size_t(i) * 4; o4[0] = r; o4[1] = g; o4[2] = b; o4[3] = 255; continue; }
         if (planes) { rgb_to_ycbcr_u8(r, g, b, d.dst + i, d.dst + n + i, d.dst + 2 * size_t(n) + i); continue; }
         o[0] = r; o[1] = g; o[2] = b;
     }

@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
 #pragma unroll
                         for (int c = 0; c < C; c++) u[c] = round_u8(a[k][c] * (1.0f / TC2_WSCALE));
                         const uint32_t sq = sp + d * h_cout;
-                        if (h_epi == EPI_PLAIN) {
+                        if (h_epi == EPI_PLAIN || (h_epi & EPI_GRAY)) {  // (gray canvas: C = 1, the luma byte)
 #pragma unroll
                             for (int c = 0; c < C; c++) sts8(sq + c, u[c]);
                         } else {

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     for (int c = 0; c < C; c++) {
                         u[c] = round_u8(__uint_as_float(v[i * C + c]) * (1.0f / TC2_WSCALE));
                     }
-                    if (h_epi == EPI_PLAIN) {
+                    if (h_epi == EPI_PLAIN || (h_epi & EPI_GRAY)) {  // (gray canvas: C = 1, the luma byte)
                         px[i] = u[0] | u[1] << 8 | u[2] << 16 | u[3] << 24;  // the pixel's c bytes, low byte first
                     } else {
                         px[i] = to_rgba_packed(u, C);

@@ -71,6 +71,7 @@ struct JobPlan {
     OrientPlan pre;
     uint32_t post_c_in = 0;  // FANLIN_TO_RGB8: channels of the final image before to_rgb8 (0: no conversion pass)
     uint32_t post_s_in = SAMPLE_U8;  // ... and its subpixel type
+    uint32_t post_c_out = 3;         // channels that pass writes: 3 (to_rgb8), or 4 = (l, l, l, 255) behind a gray canvas (EPI_GRAY)
     bool post_ycbcr = false;         // FANLIN_TO_YCBCR: that pass writes the planes Y, Cb, Cr of to_rgb8() of the final image
     StagePlan a;  // colour op + resample + letterbox (+ to_rgba8), or compose
     StagePlan b;  // blur

@@ -357,6 +357,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
     // the oriented stage had a letterbox / to_rgba8 epilogue, composed onto the canvas.  late_a = the oriented stage A.
     std::vector<uint8_t> late(n_jobs, 0);
     std::vector<StagePlan> late_a(n_jobs);
+    static const bool no_gray_canvas = [] { const char *e = std::getenv("FANLIN_GRAY_CANVAS"); return e && e[0] == '0'; }();  // (A/B switch)
     static const bool no_rgb8_epilogue = [] { const char *e = std::getenv("FANLIN_RGB8_EPILOGUE"); return e && e[0] == '0'; }();  // (A/B switch: 0 keeps the to_rgb8 pass)
     static const bool late_orient_on = [] { const char *e = std::getenv("FANLIN_LATE_ORIENT"); return !(e && e[0] == '0'); }();
     FusedTcCache *const tcache_p = gen->tcache;
@@ -388,7 +389,32 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
         const int rc = plan_job(jobs[i], &b->plans[i], true);
         if (rc != FANLIN_OK) return rc;
         if (b->plans[i].pre.present) ej[i] = b->plans[i].pre.job;  // src: its scratch image, set once the scratch is laid out
-        if (b->plans[i].a.present && b->plans[i].b.present) {  // the canvas between the stages: rows on a 16-byte stride (TMA reads it)
+        // Gray canvas (EPI_GRAY, common.h): a one-channel image letterboxed onto a gray fill colour with a blur behind it -- the
+        // default fill is (32, 32, 32), so every grayscale + fit + blur request -- is blurred as ONE plane and expanded to
+        // (l, l, l, 255) by the last pass.  Tried first, taken back where stage A falls to a kernel without the epilogue.
+        const bool gray_try = [&] {
+            const JobPlan &p = b->plans[i];
+            if (no_gray_canvas || exact || !use_tc || jobs[i].orientation >= 2 || jobs[i].src_sample != SAMPLE_U8) return false;
+            if (!p.a.present || !p.b.present || !p.a.separable || p.a.epi != EPI_BLEND_FILL || p.a.c != 1 || p.a.v_kind != KIND_LANCZOS3) return false;
+            if (p.b.epi != EPI_PLAIN || p.b.c != 4 || p.b.color_op != COLOR_NONE) return false;
+            const uint32_t f = p.a.fill;
+            return (f & 0xffu) == ((f >> 8) & 0xffu) && (f & 0xffu) == ((f >> 16) & 0xffu);
+        }();
+        const uint32_t post_c_in_keep = b->plans[i].post_c_in;
+        auto set_gray = [&](bool on) {
+            JobPlan &p = b->plans[i];
+            p.a.c_out = on ? 1u : 4u;
+            p.a.epi = on ? uint32_t(EPI_BLEND_FILL) | EPI_GRAY : uint32_t(EPI_BLEND_FILL);
+            p.b.c_mem = p.b.c = p.b.c_out = on ? 1u : 4u;
+            p.post_c_in = on ? 1u : post_c_in_keep;                      // FANLIN_TO_RGB8 / _YCBCR: the pass they have anyway reads the plane
+            p.post_c_out = on && !post_c_in_keep ? 4u : 3u;              // else it writes (l, l, l, 255)
+            if (p.a.present && p.b.present) {  // the canvas between the stages: rows on a 16-byte stride (TMA reads it)
+                p.a.canvas_pitch = uint32_t(align_up(size_t(p.a.canvas_w) * p.a.c_out * sample_bytes(p.a.s_out), 16));
+                p.b.in_pitch = p.a.canvas_pitch;
+            }
+        };
+        if (gray_try) set_gray(true);
+        else if (b->plans[i].a.present && b->plans[i].b.present) {  // the canvas between the stages: rows on a 16-byte stride (TMA reads it)
             StagePlan &sa = b->plans[i].a;
             sa.canvas_pitch = uint32_t(align_up(size_t(sa.canvas_w) * sa.c_out * sample_bytes(sa.s_out), 16));
             b->plans[i].b.in_pitch = sa.canvas_pitch;
@@ -466,6 +492,13 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
             }
         }
         if (!fused_a[i] && !gather_a[i] && !deep_a[i]) fused_a[i] = !exact && fused_eligible(p.a, ej[i]) && fused_geometry_ok(p.a, fcache_p, &ftabs);
+        if (attempt == 0 && gray_try) {
+            const StagePlan &ta = a_pre[i].present ? a_pre[i] : p.a;
+            const bool both_passes_tc = fused_a[i] == 2 && (fused_tc_uses_hmma(ta, tcache_p, &ftabs, &tctabs) || fused_tc_uses_ring(ta, tcache_p, &ftabs, &tctabs));
+            if (fused_a[i] == 0 || both_passes_tc) break;  // generic / both-passes kernels: they know the one-byte canvas
+            set_gray(false);
+            continue;
+        }
         if (attempt == 0 && rgb8_try) {
             const StagePlan &ta = a_pre[i].present ? a_pre[i] : p.a;
             const bool both_passes_tc = fused_a[i] == 2 && (fused_tc_uses_hmma(ta, tcache_p, &ftabs, &tctabs) || fused_tc_uses_ring(ta, tcache_p, &ftabs, &tctabs));
@@ -767,7 +800,7 @@ static int prepare_on_stream(fanlin_ctx *ctx, int device_index, const fanlin_job
                 std::memset(&d, 0, sizeof(d));
                 d.src = ej[i].dst; d.dst = jobs[i].dst;
                 d.s_in = p.post_s_in; d.s_out = SAMPLE_U8;
-                d.c_mem = p.post_c_in; d.c = 3; d.c_out = 3;
+                d.c_mem = p.post_c_in; d.c = 3; d.c_out = p.post_ycbcr ? 3u : p.post_c_out;
                 d.epi = p.post_ycbcr ? 1u : 0u;  // (this pass only: 1 = planar Y, Cb, Cr instead of interleaved RGB)
                 d.canvas_w = p.pub.out_w; d.canvas_h = p.pub.out_h;
                 d.v_tab = d.h_tab = NO_TABLE;

@@ -324,6 +324,37 @@ def test_to_rgb8_is_an_epilogue(fanlin, dev, dev_exact, h, w, c, qs, launches):
         assert g2.shape == want.shape and h2[">=2"] == 0, (vp, h2)
 
 
+# A one-channel image letterboxed onto a GRAY fill colour with a blur behind it is blurred as one plane (EPI_GRAY, runtime.cpp);
+# the default fill (32, 32, 32) makes that every grayscale + fit + blur request.  h, w, c, request, kwargs
+GRAY_CANVAS_CASES = [
+    (750, 1000, 3, "w=404&h=250&grayscale=true&blur=10", {}),                 # C5 fit shape, default fill
+    (750, 1000, 3, "w=404&h=250&rgb=7,7,7&grayscale=true&blur=20", {}),
+    (600, 301, 1, "w=200&h=200&rgb=200,200,200&blur=12", {}),                  # L8 source, bars left and right
+    (300, 900, 3, "w=333&h=333&grayscale=true&blur=10", dict(to_rgb8=True)),   # the pass writes RGB8 from the plane
+    (300, 900, 3, "w=333&h=333&grayscale=true&blur=10", dict(to_ycbcr=True)),
+    (300, 900, 3, "w=333&h=333&grayscale=true&blur=10", dict(orientation=6)),  # (not applied: orientation behind the resample)
+    (300, 900, 3, "w=333&h=333&rgb=1,2,3&grayscale=true&blur=10", {}),          # (not applied: the fill is not gray)
+    (300, 900, 4, "w=333&h=333&grayscale=true&blur=10", {}),                   # (not applied: La8 has an alpha channel)
+    (40, 31, 1, "w=64&h=64&blur=10", {}),                                      # upscale of a tiny image
+]
+
+
+@pytest.mark.parametrize("h,w,c,qs,kw", GRAY_CANVAS_CASES, ids=[f"{p[0]}x{p[1]}x{p[2]}-{p[3]}-{'-'.join(p[4])}" for p in GRAY_CANVAS_CASES])
+def test_gray_canvas_blur(fanlin, dev, h, w, c, qs, kw):
+    img = synth_image(905 + c, h, w, c)
+    q = fanlin.Query(qs)
+    okw = dict(grayscale=q.grayscale(), inverse=q.inverse(), crop=q.cropping(), blur=q.blur(), rgb=q.fill_color())
+    okw["w"], okw["h"] = q.dimensions()
+    want = O.process_deep(img, **okw, **kw)
+    got = fanlin.process_image(dev, img, q, **kw)
+    assert got.shape == want.shape
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    bar = 2 if kw.get("to_ycbcr") else 1  # a 1-LSB RGB difference moves a plane by <= 1 (+ truncation)
+    assert d.max() <= bar, (int(d.max()), int((d > 0).sum()))
+    if not kw and c != 4 and "rgb=1,2,3" not in qs:
+        assert got.shape[2] == 4 and (got[..., 3] == 255).all() and (got[..., 0] == got[..., 1]).all() and (got[..., 1] == got[..., 2]).all()
+
+
 # ---- same-shaped images in one launch --------------------------------------------------------
 
 @pytest.mark.parametrize("h,w,c,qs", [(1080, 1920, 3, "w=300&h=200&rgb=32,32,32"), (600, 800, 3, "w=200&h=200&crop=true"),
