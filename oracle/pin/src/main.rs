@@ -10,7 +10,7 @@
 //! the resulting raw pixels in golden.json's schema.  `tests/test_oracle.py::test_oracle_matches_reference_golden`
 //! compares the C oracle with that file whenever it exists: that is what turns "parity unpinned" into "pinned".
 use image::imageops::FilterType;
-use image::{DynamicImage, GrayAlphaImage, GrayImage, ImageBuffer, Rgba, RgbImage, RgbaImage};
+use image::{DynamicImage, GrayAlphaImage, GrayImage, ImageBuffer, Luma, LumaA, Rgb, Rgba, RgbImage, RgbaImage};
 use serde::{Deserialize, Serialize};
 use sha2::{Digest, Sha256};
 use std::{env, fs, path::Path};
@@ -34,6 +34,8 @@ struct Params {
     orientation: u8, // EXIF value; 0 / 1 = none
     #[serde(default)]
     to_rgb8: bool,
+    #[serde(default)]
+    to_rgba8: bool, // the WebP branch: img.into_rgba8(), src/handler.rs:287
 }
 
 #[derive(Deserialize)]
@@ -42,6 +44,8 @@ struct CaseIn {
     width: u32,
     height: u32,
     channels: u32,
+    #[serde(default)]
+    sample: String, // "u8" (default), "u16", "f32": the subpixel type of the DynamicImage variant (golden_deep.json)
     params: Params,
 }
 
@@ -51,6 +55,7 @@ struct CaseOut {
     out_h: u32,
     out_w: u32,
     out_c: u32,
+    out_dtype: &'static str, // "uint8" | "uint16" | "float32": subpixel type of the variant the stage ended in
     sha256: String,
 }
 
@@ -63,6 +68,29 @@ struct Golden {
 
 fn load(dir: &Path, c: &CaseIn) -> DynamicImage {
     let raw = fs::read(dir.join(format!("{}.raw", c.name))).expect("raw input");
+    let (w, h) = (c.width, c.height);
+    if c.sample == "u16" {
+        // ImageLuma16 .. ImageRgba16: what a 16-bit PNG / TIFF decodes to (src/handler.rs:219)
+        assert_eq!(raw.len() as u32, w * h * c.channels * 2);
+        let v: Vec<u16> = raw.chunks_exact(2).map(|b| u16::from_le_bytes([b[0], b[1]])).collect();
+        return match c.channels {
+            1 => DynamicImage::ImageLuma16(ImageBuffer::<Luma<u16>, _>::from_raw(w, h, v).unwrap()),
+            2 => DynamicImage::ImageLumaA16(ImageBuffer::<LumaA<u16>, _>::from_raw(w, h, v).unwrap()),
+            3 => DynamicImage::ImageRgb16(ImageBuffer::<Rgb<u16>, _>::from_raw(w, h, v).unwrap()),
+            4 => DynamicImage::ImageRgba16(ImageBuffer::<Rgba<u16>, _>::from_raw(w, h, v).unwrap()),
+            n => panic!("channels {n}"),
+        };
+    }
+    if c.sample == "f32" {
+        // ImageRgb32F / ImageRgba32F: HDR / EXR
+        assert_eq!(raw.len() as u32, w * h * c.channels * 4);
+        let v: Vec<f32> = raw.chunks_exact(4).map(|b| f32::from_le_bytes([b[0], b[1], b[2], b[3]])).collect();
+        return match c.channels {
+            3 => DynamicImage::ImageRgb32F(ImageBuffer::<Rgb<f32>, _>::from_raw(w, h, v).unwrap()),
+            4 => DynamicImage::ImageRgba32F(ImageBuffer::<Rgba<f32>, _>::from_raw(w, h, v).unwrap()),
+            n => panic!("channels {n}"),
+        };
+    }
     assert_eq!(raw.len() as u32, c.width * c.height * c.channels);
     match c.channels {
         1 => DynamicImage::ImageLuma8(GrayImage::from_raw(c.width, c.height, raw).unwrap()),
@@ -108,6 +136,9 @@ fn stage(mut img: DynamicImage, p: &Params) -> DynamicImage {
     if p.to_rgb8 {
         img = DynamicImage::ImageRgb8(img.to_rgb8()); // the JPEG branch, src/handler.rs:274-278
     }
+    if p.to_rgba8 && !p.gif {
+        img = DynamicImage::ImageRgba8(img.into_rgba8()); // the WebP branch, src/handler.rs:287
+    }
     img
 }
 
@@ -120,6 +151,11 @@ fn main() {
     for c in &manifest {
         let out = stage(load(dir, c), &c.params);
         let ch = u32::from(out.color().channel_count());
+        let out_dtype = match out.color().bytes_per_pixel() / out.color().channel_count() {
+            1 => "uint8",
+            2 => "uint16",
+            _ => "float32",
+        };
         let mut h = Sha256::new();
         h.update(out.as_bytes());
         cases.push(CaseOut {
@@ -127,6 +163,7 @@ fn main() {
             out_h: out.height(),
             out_w: out.width(),
             out_c: ch,
+            out_dtype,
             sha256: h.finalize().iter().map(|b| format!("{b:02x}")).collect(),
         });
     }
