@@ -87,6 +87,14 @@ __device__ __forceinline__ void tc_source_role(const TcPipe &p, const CUtensorMa
         }
         if (gg >= p.n_a) mbar_wait_wd(p.mbar + 8 * ((gg - p.n_a) % NRT), ((gg - p.n_a) / NRT) & 1);  // the slot was read by the MMAs of group gg - n_a
         const uint32_t bar = p.a_full + 8 * slot;
+#ifdef TC_EXP_SKIP_A  // TIMING EXPERIMENT ONLY (wrong results): the kernel without any source traffic (HBM, L2 -> SM, the TMA writes)
+        if (gg >= 2 * p.n_groups) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            if (++slot == p.n_a) slot = 0;
+            if (++g == p.n_groups) { g = 0; chunk++; }
+            continue;
+        }
+#endif
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(p.kg_max * TC_M) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                          p.sA_u + slot * p.kg_max * TC_M),
@@ -106,6 +114,13 @@ __device__ __forceinline__ void tc_weight_role(const TcPipe &p, const uint8_t *t
         if (gg >= NB) mbar_wait_wd(p.mbar + 8 * ((gg - NB) % NRT), ((gg - NB) / NRT) & 1);  // the slot's previous tile was read by the MMAs of group gg - NB
         const uint32_t kg = p.grp[4 * g + 1], b_off = p.grp[4 * g + 2];
         const uint32_t bar = p.b_full + 8 * (gg % NB);
+#ifdef TC_EXP_SKIP_B  // TIMING EXPERIMENT ONLY (wrong results): what the kernel costs without the weight tiles' L2 -> SM traffic
+        if (gg >= 2 * p.n_groups) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+            if (++g == p.n_groups) g = 0;
+            continue;
+        }
+#endif
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kg * TC_N) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          p.sB_u + (gg % NB) * TC_N * p.kg_max),
