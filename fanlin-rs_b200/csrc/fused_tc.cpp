@@ -335,7 +335,7 @@ static bool build_hmma(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
 // taps ended in the chunk.  The ring only has to hold the outputs a chunk touches, so ratios near 2 (C1, C3) fit.
 // Per chunk: one f16 tile pair hi | lo [n_total][128] (K-major core matrices; row n = window column n) and a record of
 // 8 words {tile offset, first output finished (relative to ox0), outputs finished, window column, window columns,
-// ring slot of the first finished output, 0, 0}.
+// ring slot of the first finished output, K-step ranges of the two window pieces (4 bytes: lo, hi, lo, hi), 0}.
 static uint32_t ring_slot_align(uint32_t c) { return c == 4 ? 4u : c == 2 ? 8u : 16u; }  // RP * c is a multiple of 16
 
 static bool build_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTcTables *tct) {
@@ -413,10 +413,25 @@ static bool build_ring(const StagePlan &s, TcGeom &g, FusedTables *tabs, FusedTc
                 }
             }
         }
+        // K steps (16 tile columns each) in which the two pieces of the window -- rows [0, n1) in front of the ring's end, rows
+        // [n1, n_total) wrapped to its start -- have any weight: outputs and tile columns both run left to right, so the first
+        // piece needs the leading steps only and the wrapped piece the trailing ones.  The kernel skips the rest (they would
+        // add zeros, at the price of re-reading the T tile).
+        const uint32_t n1 = std::min(n_total, RINGC - w0);
+        uint32_t klo[2] = {8, 8}, khi[2] = {0, 0};
+        for (uint32_t n = 0; n < n_total; n++) {
+            const uint32_t pc = n < n1 ? 0u : 1u;
+            for (uint32_t k = 0; k < 128; k++) {
+                const size_t at = (size_t(n / 8) * 16 + k / 8) * 64 + (n % 8) * 8 + k % 8;
+                if (hi[at] | lo[at]) { klo[pc] = std::min(klo[pc], k / 16); khi[pc] = std::max(khi[pc], k / 16 + 1); }
+            }
+        }
+        for (int pc = 0; pc < 2; pc++) if (khi[pc] == 0) klo[pc] = 0;  // no weight at all: an empty range
         const uint32_t first = fin;
         while (fin < touch && (t.entries[fin].left + t.entries[fin].count) * C <= b1) fin++;
         uint32_t *r = &rec[size_t(8) * ch];
         r[0] = uint32_t(off); r[1] = first - o0; r[2] = fin - first; r[3] = w0; r[4] = n_total; r[5] = (first - o0) % RP;
+        r[6] = klo[0] | khi[0] << 8 | klo[1] << 16 | khi[1] << 24;
     }
     g.wh_bytes = n_max * 512;
     g.hrec_off = uint32_t(tabs->info.size());

@@ -213,17 +213,19 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
             long long w_wh = 0, w_tr = 0, w_df = 0, w_wf = 0;
             const long long t_start = clock64();
             // window piece: accumulator columns [col, col + n) += T . W[brow .. brow + n), combos [c_a, c_b) of hi x hi, lo x hi, hi x lo
-            auto piece = [&](uint32_t mt, uint32_t col, uint32_t n, uint32_t brow, uint32_t b_hi0, uint32_t b_lo0, int c_a, int c_b) {
+            // K steps [k_lo, k_hi) only: the others hold no weight for this piece (host record word 6)
+            auto piece = [&](uint32_t mt, uint32_t col, uint32_t n, uint32_t brow, uint32_t b_hi0, uint32_t b_lo0, int c_a, int c_b, uint32_t k_lo, uint32_t k_hi) {
                 const uint32_t idesc = (1u << 4) | (1u << 15) | ((n >> 3) << 17) | ((TC_M >> 4) << 24);  // f16 x f16 -> f32, A MN-major, B K-major
                 const uint32_t d_tmem = tmem_base + mt * ring_cols + col;
                 const uint32_t a_hi = sT_u + mt * 32768u, a_lo = a_hi + t_bytes;
 #pragma unroll
                 for (int combo = 0; combo < 3; combo++) {
                     if (combo < c_a || combo >= c_b) continue;
-                    uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048);
-                    uint64_t db = umma_desc((combo == 2 ? b_lo0 : b_hi0) + (brow >> 3) * 2048u, 128, 2048);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ks++) {
+                    // (a loop with a uniform trip count: a predicate on the instruction itself broke the back-to-back issue -- C3 + 4 %)
+                    uint64_t da = umma_desc(combo == 1 ? a_lo : a_hi, 128, 2048) + k_lo * (256 >> 4);
+                    uint64_t db = umma_desc((combo == 2 ? b_lo0 : b_hi0) + (brow >> 3) * 2048u, 128, 2048) + k_lo * (256 >> 4);
+#pragma unroll 1
+                    for (uint32_t ks = k_lo; ks < k_hi; ks++) {
                         asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
                                      "l"(da), "l"(db), "r"(idesc)
                                      : "memory");
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                 load_half(0, 0);
                 load_half(0, 1);
                 for (uint32_t ch = 0; ch < n_chunks; ch++) {
-                    const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
+                    const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4), kr = __ldg(hrec + 8 * ch + 6);
                     const uint32_t n1 = min(n_total, ring_cols - w0);
                     const uint32_t b_hi0 = sWh_u, b_lo0 = b_hi0 + (wh_bytes >> 1);
                     for (uint32_t mt = 0; mt < n_mt; mt++) {
@@ -259,12 +261,12 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                         if (ch > 0) T3WR(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
                         if (mt == 0) T3WR(w_wh, smem_u32(&wh_full[0]), ch & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        piece(mt, w0, n1, 0, b_hi0, b_lo0, 0, 2);
-                        if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 0, 2);
+                        piece(mt, w0, n1, 0, b_hi0, b_lo0, 0, 2, kr & 255u, (kr >> 8) & 255u);
+                        if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 0, 2, (kr >> 16) & 255u, kr >> 24);
                         if (last) commit(&wh_free[0]);
                         if (mt == 0) { T3WR(w_wh, smem_u32(&wh_full[1]), ch & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-                        piece(mt, w0, n1, 0, b_hi0, b_lo0, 2, 3);
-                        if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 2, 3);
+                        piece(mt, w0, n1, 0, b_hi0, b_lo0, 2, 3, kr & 255u, (kr >> 8) & 255u);
+                        if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 2, 3, (kr >> 16) & 255u, kr >> 24);
                         commit(&d2_full[mt]);
                         if (last) commit(&wh_free[1]);
                     }
@@ -284,15 +286,15 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     load_wh(ch + 1);
                 }
                 T3WR(w_wh, smem_u32(&wh_full[slot]), (ch >> 1) & 1);
-                const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4);
+                const uint32_t w0 = __ldg(hrec + 8 * ch + 3), n_total = __ldg(hrec + 8 * ch + 4), kr = __ldg(hrec + 8 * ch + 6);
                 const uint32_t n1 = min(n_total, ring_cols - w0);
                 const uint32_t b_hi0 = sWh_u + slot * wh_bytes, b_lo0 = b_hi0 + n_total * 256u;
                 for (uint32_t mt = 0; mt < n_mt; mt++) {
                     T3WR(w_tr, smem_u32(&t_ready[mt]), ch & 1);                     // the consumers have written the tile's rows
                     if (ch > 0) T3WR(w_df, smem_u32(&d2_free[mt]), (ch - 1) & 1);   // ... and drained and zeroed what the previous chunk finished
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    piece(mt, w0, n1, 0, b_hi0, b_lo0, 0, 3);
-                    if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 0, 3);
+                    piece(mt, w0, n1, 0, b_hi0, b_lo0, 0, 3, kr & 255u, (kr >> 8) & 255u);
+                    if (n1 < n_total) piece(mt, 0, n_total - n1, n1, b_hi0, b_lo0, 0, 3, (kr >> 16) & 255u, kr >> 24);
                     commit(&d2_full[mt]);
                     if (mt + 1 == n_mt) commit(&wh_free[slot]);
                 }
@@ -477,32 +479,50 @@ __global__ void __launch_bounds__(T3_NT_ALL, 1) fused_resample_tc3_kernel(const 
                     }
                 }
             } else {
-                const uint32_t nw_max = (nb + 3 + 3) / 4;  // words a segment can span, whatever its alignment
-                uint32_t sh = 0;
-                while ((1u << sh) < nw_max && sh < 5) sh++;
-                const uint32_t lpr = 1u << sh, rpi = 32u >> sh, k0 = lane & (lpr - 1);
-                for (uint32_t rr = lane >> sh; rr < rows_here; rr += rpi) {
-                    uint8_t *a = seg0 + size_t(rr) * h_pitch;
-                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
-                    const uint32_t nw = (ph + nb + 3) / 4;
-                    for (uint32_t k = k0; k < nw; k += lpr) {
-                        const uint32_t s0 = my_stage + rr * stride4 + 4u * k;
-                        const uint32_t wa = lds_u32(s0 - 4), wb = lds_u32(s0);
-                        const uint32_t val = ph ? __funnelshift_r(wa, wb, 8 * (4 - ph)) : wb;
-                        const int b0 = int(4 * k) - int(ph);
-                        uint8_t *gw = a + b0;
-                        const int va = max(-b0, 0), vb = min(int(nb) - b0, 4);
-                        if (va == 0 && vb == 4) {
-                            *reinterpret_cast<uint32_t *>(gw) = val;
-                        } else if (va == 2 && vb == 4) {
-                            *reinterpret_cast<uint16_t *>(gw + 2) = uint16_t(val >> 16);
-                        } else if (va == 0 && vb == 2) {
-                            *reinterpret_cast<uint16_t *>(gw) = uint16_t(val);
-                        } else {
+                // Row segments at any byte address (three-byte pixels, L8 / LA, odd pitches).  Whole words first: the (row, word)
+                // pairs flattened over the lanes, four per lane with their staged words fetched up front; then the partial
+                // words at the two ends of every segment, one row per lane.  (One row per iteration -- 21 words of a 25-pixel
+                // RGB segment on 32 lanes, a chain of load, shift and a store down one of four paths -- took 11 k clk per
+                // drain: a C1-sized crop request ran four times slower than the letterboxed one.)
+                const uint32_t nw_max = (nb + 6) >> 2;  // words a segment can span, whatever its alignment
+                const uint32_t items = rows_here * nw_max;
+                const float inv = 1.0f / float(nw_max);
+                for (uint32_t base = 0; base < items; base += 128) {
+                    uint32_t wa[4], wb[4], rr[4], kk[4];
 #pragma unroll
-                            for (int bb = 0; bb < 4; bb++)
-                                if (bb >= va && bb < vb) gw[bb] = uint8_t(val >> (8 * bb));
-                        }
+                    for (uint32_t i = 0; i < 4; i++) {
+                        const uint32_t item = min(base + 32 * i + lane, items - 1);
+                        rr[i] = uint32_t((float(item) + 0.5f) * inv);
+                        kk[i] = item - rr[i] * nw_max;
+                        const uint32_t s0 = my_stage + rr[i] * stride4 + 4u * kk[i];
+                        wa[i] = lds_u32(s0 - 4);
+                        wb[i] = lds_u32(s0);
+                    }
+#pragma unroll
+                    for (uint32_t i = 0; i < 4; i++) {
+                        uint8_t *a = seg0 + size_t(rr[i]) * h_pitch;
+                        const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
+                        const int b0 = int(4 * kk[i]) - int(ph);  // segment byte of the word's byte 0
+                        if (base + 32 * i + lane < items && b0 >= 0 && b0 + 4 <= int(nb))
+                            *reinterpret_cast<uint32_t *>(a + b0) = ph ? __funnelshift_r(wa[i], wb[i], 8 * (4 - ph)) : wb[i];
+                    }
+                }
+                if (lane < rows_here) {  // the partial words: the head (ph bytes missing in front) and the tail of this lane's row
+                    uint8_t *a = seg0 + size_t(lane) * h_pitch;
+                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
+                    const uint32_t nw = (ph + nb + 3) >> 2;
+                    const uint32_t s0 = my_stage + lane * stride4;
+#pragma unroll
+                    for (uint32_t e = 0; e < 2; e++) {
+                        const uint32_t k = e ? nw - 1 : 0u;
+                        const int b0 = int(4 * k) - int(ph);
+                        const int va = max(-b0, 0), vb = min(int(nb) - b0, 4);
+                        if ((e && nw < 2) || (va == 0 && vb == 4)) continue;  // (a one-word segment is the head; whole words went above)
+                        const uint32_t w0 = lds_u32(s0 + 4u * k - 4), w1 = lds_u32(s0 + 4u * k);
+                        const uint32_t val = ph ? __funnelshift_r(w0, w1, 8 * (4 - ph)) : w1;
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++)
+                            if (bb >= va && bb < vb) a[b0 + bb] = uint8_t(val >> (8 * bb));
                     }
                 }
             }
