@@ -327,31 +327,47 @@ __global__ void __launch_bounds__(BT_NT_ALL, 1) blur_tc2_kernel(const BlurTcItem
                         *reinterpret_cast<uint16_t *>(seg0 + size_t(rr) * dst_pitch + 2 * hk) = uint16_t(val);
                 }
             } else {
-                // rows at any address: 9 lanes per row (words 0..8 of the segment as the row's address aligns them), three
-                // rows per store; the partial words at the two ends leave as one 2-byte store where that is what is left
-                // of them (rows of even width), else byte by byte
-                const uint32_t sub = lane / 9, k = lane - 9 * sub;
+                // rows at any address (odd widths, odd pitches).  Whole words first: the 32 x 9 (row, word) slots -- words 0..8 of the
+                // segment as the row's address aligns them -- flattened over the lanes, three per lane with their staged words
+                // fetched up front; then the partial words at the two ends of the segment, one row per lane.  (Nine lanes per
+                // row and a store down one of four paths per word took ~3.2 k clk per segment.)
 #pragma unroll 1
-                for (uint32_t rr = sub; rr < 32 && lane < 27; rr += 3) {
-                    uint8_t *a = seg0 + size_t(rr) * dst_pitch;
-                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
-                    const uint32_t s0 = my_stage + rr * 36u + 4u * k;
-                    const uint32_t wa = lds_u32(s0 - 4), wb = lds_u32(s0);  // staged words k - 1 and k (k = 8: the pad word, masked below)
-                    if ((k == 8 && ph == 0) || q * 32u + rr >= band_rows) continue;
-                    const uint32_t val = ph ? __funnelshift_r(wa, wb, 8 * (4 - ph)) : wb;
-                    const int b0 = int(4 * k) - int(ph);  // segment byte of the word's byte 0
-                    uint8_t *gw = a + b0;
-                    const int va = max(lo_b - b0, 0), vb = min(hi_b - b0, 4);  // valid bytes [va, vb) of the word
-                    if (va == 0 && vb == 4) {
-                        *reinterpret_cast<uint32_t *>(gw) = val;
-                    } else if (va == 2 && vb == 4) {
-                        *reinterpret_cast<uint16_t *>(gw + 2) = uint16_t(val >> 16);
-                    } else if (va == 0 && vb == 2) {
-                        *reinterpret_cast<uint16_t *>(gw) = uint16_t(val);
-                    } else {
+                for (uint32_t base = 0; base < 288; base += 96) {
+                    uint32_t wa[3], wb[3], rr[3], kk[3];
 #pragma unroll
-                        for (int b = 0; b < 4; b++)
-                            if (b >= va && b < vb) gw[b] = uint8_t(val >> (8 * b));
+                    for (uint32_t i = 0; i < 3; i++) {
+                        const uint32_t item = base + 32 * i + lane;
+                        rr[i] = item / 9;
+                        kk[i] = item - 9 * rr[i];
+                        const uint32_t s0 = my_stage + rr[i] * 36u + 4u * kk[i];
+                        wa[i] = lds_u32(s0 - 4);  // staged words k - 1 and k (k = 8: the pad word, never a whole word of the segment)
+                        wb[i] = lds_u32(s0);
+                    }
+#pragma unroll
+                    for (uint32_t i = 0; i < 3; i++) {
+                        uint8_t *a = seg0 + size_t(rr[i]) * dst_pitch;
+                        const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
+                        const int b0 = int(4 * kk[i]) - int(ph);  // segment byte of the word's byte 0
+                        if (b0 >= lo_b && b0 + 4 <= hi_b && q * 32u + rr[i] < band_rows)
+                            *reinterpret_cast<uint32_t *>(a + b0) = ph ? __funnelshift_r(wa[i], wb[i], 8 * (4 - ph)) : wb[i];
+                    }
+                }
+                if (q * 32u + lane < band_rows) {  // the partial words of this lane's row: the one that holds byte lo_b, the one that holds byte hi_b - 1
+                    uint8_t *a = seg0 + size_t(lane) * dst_pitch;
+                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(a)) & 3u;
+                    const uint32_t k_h = (uint32_t(lo_b) + ph) >> 2, k_t = (uint32_t(hi_b) - 1 + ph) >> 2;
+#pragma unroll
+                    for (uint32_t e = 0; e < 2; e++) {
+                        const uint32_t k = e ? k_t : k_h;
+                        const int b0 = int(4 * k) - int(ph);
+                        const int va = max(lo_b - b0, 0), vb = min(hi_b - b0, 4);  // valid bytes [va, vb) of the word
+                        if ((e && k_t == k_h) || (va == 0 && vb == 4)) continue;
+                        const uint32_t s0 = my_stage + lane * 36u + 4u * k;
+                        const uint32_t w0 = lds_u32(s0 - 4), w1 = lds_u32(s0);
+                        const uint32_t val = ph ? __funnelshift_r(w0, w1, 8 * (4 - ph)) : w1;
+#pragma unroll
+                        for (int bb = 0; bb < 4; bb++)
+                            if (bb >= va && bb < vb) a[b0 + bb] = uint8_t(val >> (8 * bb));
                     }
                 }
             }

@@ -15,7 +15,7 @@ pkg = G.load_package()
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = pkg.Device([0])
 device = torch.device("cuda", 0)
-for (h, w, c, sigma) in [(1000, 1618, 4, 10.0), (1000, 1618, 1, 10.0), (1000, 1618, 3, 10.0)]:
+for (h, w, c, sigma) in [(1000, 1618, 4, 10.0), (1000, 1618, 1, 10.0), (1000, 1618, 3, 10.0), (1000, 1617, 1, 10.0), (1000, 1617, 3, 10.0)]:  # (1617: rows at odd addresses)
     pitch = (w * c + 15) // 16 * 16
     src = torch.randint(0, 256, (n, h, pitch), dtype=torch.uint8, device=device)
     dst = torch.zeros((n, h, w * c), dtype=torch.uint8, device=device)
