@@ -792,21 +792,30 @@ __global__ void __launch_bounds__(NT_ALL2, 1) fused_resample_tc2_kernel(const Fu
                 for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8, gq += g_step, sq += s_step)
                     for (uint32_t k = tid & 7; k < o_count; k += 8) gq[k - (tid & 7)] = sq[k - (tid & 7)];
             } else if (nb) {
-                for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8) {  // 8 lanes per row segment
+                // whole words, 8 lanes per row segment (the staged words are the canvas words: a segment keeps its alignment phase) ...
+                for (uint32_t r = tid >> 3; r < h_rows; r += NT / 8) {
                     uint8_t *g0 = h_row0 + size_t(r) * h_pitch + size_t(o_first) * h_cout;
                     const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(g0)) & 3u;
-                    const uint32_t nw = (ph + nb + 3) >> 2;
-                    for (uint32_t k = tid & 7; k < nw; k += 8) {
+                    const uint32_t k_a = ph ? 1u : 0u, k_b = (ph + nb) >> 2;  // words [k_a, k_b) of the segment are whole
+                    for (uint32_t k = k_a + (tid & 7); k < k_b; k += 8)
+                        *reinterpret_cast<uint32_t *>(g0 - ph + 4 * k) = out_s[r * out_stride + k];
+                }
+                // ... then the partial words at the two ends, one row per thread (in the loop above they put every warp through a
+                // byte-store path for the sake of two of its lanes)
+                for (uint32_t r = tid; r < h_rows; r += NT) {
+                    uint8_t *g0 = h_row0 + size_t(r) * h_pitch + size_t(o_first) * h_cout;
+                    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(g0)) & 3u;
+                    const uint32_t k_t = (ph + nb - 1) >> 2;  // the word that holds the last byte
+#pragma unroll
+                    for (uint32_t e = 0; e < 2; e++) {
+                        const uint32_t k = e ? k_t : 0u;
+                        const int lo = int(ph) - int(4 * k), hi = int(ph + nb) - int(4 * k);  // the word's valid bytes: [lo, hi)
+                        if ((e && k_t == 0) || (lo <= 0 && hi >= 4)) continue;
                         const uint32_t wv = out_s[r * out_stride + k];
                         uint8_t *gw = g0 - ph + 4 * k;
-                        const int lo = int(ph) - int(4 * k), hi = int(ph + nb) - int(4 * k);  // the word's valid bytes: [lo, hi)
-                        if (lo <= 0 && hi >= 4) {
-                            *reinterpret_cast<uint32_t *>(gw) = wv;
-                        } else {
 #pragma unroll
-                            for (int b = 0; b < 4; b++)
-                                if (b >= lo && b < hi) gw[b] = uint8_t(wv >> (8 * b));
-                        }
+                        for (int b = 0; b < 4; b++)
+                            if (b >= lo && b < hi) gw[b] = uint8_t(wv >> (8 * b));
                     }
                 }
             }
