@@ -1140,16 +1140,26 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
             if (stage_out) f.h_out = static_cast<uint8_t *>(ctx->pinned.alloc(out_bytes + 256));
             if ((stage_in && !f.h_in) || (stage_out && !f.h_out)) { set_error("fanlin: pinned staging allocation failed"); rc = FANLIN_ENOMEM; break; }
         }
+        // Only the source rows the output depends on cross the link (fanlin_plan.src_y0 .. src_y1: a crop=true request on a
+        // 4000x3000 image reads 2484 of its 3000 rows): they land at their own place in the device image, the rows around
+        // them stay unwritten and unread.  Stored-rotated images (EXIF >= 2) are copied whole.
+        auto rows_of = [&](uint32_t idx, uint32_t *y0, uint32_t *y1) {
+            const fanlin_job &j = jobs[idx];
+            *y0 = 0; *y1 = j.src_h;
+            if (j.orientation < 2 && pl[idx].src_y1 > pl[idx].src_y0 && pl[idx].src_y1 <= j.src_h) { *y0 = pl[idx].src_y0; *y1 = pl[idx].src_y1; }
+        };
         if (stage_in) {  // caller rows -> pinned staging, in the layout of the device buffer (rows on a 16-byte stride)
             std::vector<CopyOp> ops;
             for (uint32_t i = 0; i < m; i++) {
                 const fanlin_job &j = jobs[begin + i];
                 const size_t row = size_t(j.src_w) * j.src_channels * sample_bytes(j.src_sample);
                 const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
+                uint32_t y0, y1;
+                rows_of(begin + i, &y0, &y1);
                 if (pitch == row && dpitch == row) {
-                    ops.push_back(CopyOp{f.h_in + in_off[i], j.src, row * j.src_h});
+                    ops.push_back(CopyOp{f.h_in + in_off[i] + y0 * row, j.src + y0 * row, row * (y1 - y0)});
                 } else {
-                    for (uint32_t y = 0; y < j.src_h; y++) ops.push_back(CopyOp{f.h_in + in_off[i] + y * dpitch, j.src + y * pitch, row});
+                    for (uint32_t y = y0; y < y1; y++) ops.push_back(CopyOp{f.h_in + in_off[i] + y * dpitch, j.src + y * pitch, row});
                 }
             }
             parallel_copy(ops, copy_threads);
@@ -1160,16 +1170,18 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
             const fanlin_job &j = jobs[begin + i];
             const size_t row = size_t(j.src_w) * j.src_channels * sample_bytes(j.src_sample);
             const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
+            uint32_t y0, y1;
+            rows_of(begin + i, &y0, &y1);
             const cudaError_t e = stage_in ? cudaSuccess
                                   : pitch == row && dpitch == row
-                                      ? cudaMemcpyAsync(f.d_in + in_off[i], j.src, row * j.src_h, cudaMemcpyHostToDevice, f.st)
-                                      : cudaMemcpy2DAsync(f.d_in + in_off[i], dpitch, j.src, pitch, row, j.src_h, cudaMemcpyHostToDevice, f.st);
+                                      ? cudaMemcpyAsync(f.d_in + in_off[i] + y0 * row, j.src + y0 * row, row * (y1 - y0), cudaMemcpyHostToDevice, f.st)
+                                      : cudaMemcpy2DAsync(f.d_in + in_off[i] + y0 * dpitch, dpitch, j.src + y0 * pitch, pitch, row, y1 - y0, cudaMemcpyHostToDevice, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; }
             djobs[i].src = f.d_in + in_off[i];
             djobs[i].src_pitch = uint32_t(dpitch);
             djobs[i].dst = f.d_out + out_off[i];
             djobs[i].dst_capacity = pl[begin + i].out_bytes;
-            ctx->h2d_bytes += row * j.src_h;
+            ctx->h2d_bytes += row * (y1 - y0);
         }
         if (rc != FANLIN_OK) break;
         rc = prepare_on_stream(ctx, dev_index, djobs.data(), m, nullptr, &f.batch, f.st);

@@ -355,6 +355,25 @@ def test_gray_canvas_blur(fanlin, dev, h, w, c, qs, kw):
         assert got.shape[2] == 4 and (got[..., 3] == 255).all() and (got[..., 0] == got[..., 1]).all() and (got[..., 1] == got[..., 2]).all()
 
 
+def test_only_the_needed_source_rows_cross_the_link(fanlin, dev):
+    """fanlin_run copies the rows fanlin_plan.src_y0 .. src_y1 (what a crop=true request depends on), not the image."""
+    img = synth_image(77, 900, 300, 3)  # tall: w=200&h=100&crop=true keeps the middle rows
+    q = fanlin.Query("w=200&h=100&crop=true")
+    j = fanlin.make_job(img, q)
+    pl = fanlin.plan_job(j)
+    assert 0 < pl.src_y0 < pl.src_y1 < 900
+    before = dev.stats()["h2d_bytes"]
+    got = fanlin.process_image(dev, img, q)
+    assert dev.stats()["h2d_bytes"] - before == (pl.src_y1 - pl.src_y0) * 300 * 3
+    hh = hist(got, O.process(img, w=200, h=100, crop=True))
+    assert hh[">=2"] == 0 and hh[1] <= 0.002 * got.size + 2, hh
+    # a stored-rotated image is copied whole (the window is in oriented coordinates)
+    before = dev.stats()["h2d_bytes"]
+    got = fanlin.process_image(dev, img, q, orientation=6)
+    assert dev.stats()["h2d_bytes"] - before == 900 * 300 * 3
+    assert hist(got, O.process(img, w=200, h=100, crop=True, orientation=6))[">=2"] == 0
+
+
 # ---- same-shaped images in one launch --------------------------------------------------------
 
 @pytest.mark.parametrize("h,w,c,qs", [(1080, 1920, 3, "w=300&h=200&rgb=32,32,32"), (600, 800, 3, "w=200&h=200&crop=true"),
