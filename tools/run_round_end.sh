@@ -10,3 +10,7 @@ ncu --set full --clock-control none --import-source on -k regex:fused_resample_t
 python tools/prof_resample.py c1 1024 > gpurun_out/prof_c1_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:fused_resample_tc3 -c 1 -o gpurun_out/ncu_tc3_c1_r02b -f python tools/prof_resample.py c1 1024 > gpurun_out/ncu_tc3_c1_r02b.log 2>&1
 ls -la gpurun_out/*.ncu-rep | tail -3
+python tools/prof_blur.py 148 > gpurun_out/prof_blur_plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:blur_tc2 -c 1 -o gpurun_out/ncu_blur_r02b -f python tools/prof_blur.py 148 > gpurun_out/ncu_blur_r02b.log 2>&1
+python tools/latency.py > gpurun_out/latency.jsonl 2> gpurun_out/latency.err
+python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
