@@ -1172,16 +1172,28 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
             const size_t pitch = j.src_pitch ? j.src_pitch : row, dpitch = align_up(row, 16);
             uint32_t y0, y1;
             rows_of(begin + i, &y0, &y1);
+            // ... and of those rows only the columns it depends on (src_x0 .. src_x1), where that saves at least a twentieth of
+            // the row: a 2-D copy to the same place in the device image (what lies around it is read with zero weights or not at all)
+            size_t xb0 = 0, xb1 = row;
+            {
+                const fanlin_plan &pp = pl[begin + i];
+                const size_t pxb = size_t(j.src_channels) * sample_bytes(j.src_sample);
+                if (!stage_in && j.orientation < 2 && pp.src_x1 > pp.src_x0 && pp.src_x1 <= j.src_w && (size_t(pp.src_x1 - pp.src_x0) * pxb) * 20 <= row * 19) {
+                    xb0 = size_t(pp.src_x0) * pxb;
+                    xb1 = size_t(pp.src_x1) * pxb;
+                }
+            }
+            const bool whole_rows = xb0 == 0 && xb1 == row;
             const cudaError_t e = stage_in ? cudaSuccess
-                                  : pitch == row && dpitch == row
+                                  : whole_rows && pitch == row && dpitch == row
                                       ? cudaMemcpyAsync(f.d_in + in_off[i] + y0 * row, j.src + y0 * row, row * (y1 - y0), cudaMemcpyHostToDevice, f.st)
-                                      : cudaMemcpy2DAsync(f.d_in + in_off[i] + y0 * dpitch, dpitch, j.src + y0 * pitch, pitch, row, y1 - y0, cudaMemcpyHostToDevice, f.st);
+                                      : cudaMemcpy2DAsync(f.d_in + in_off[i] + y0 * dpitch + xb0, dpitch, j.src + y0 * pitch + xb0, pitch, xb1 - xb0, y1 - y0, cudaMemcpyHostToDevice, f.st);
             if (e != cudaSuccess) { set_error(std::string("fanlin: H2D failed: ") + cudaGetErrorString(e)); rc = FANLIN_ECUDA; }
             djobs[i].src = f.d_in + in_off[i];
             djobs[i].src_pitch = uint32_t(dpitch);
             djobs[i].dst = f.d_out + out_off[i];
             djobs[i].dst_capacity = pl[begin + i].out_bytes;
-            ctx->h2d_bytes += row * (y1 - y0);
+            ctx->h2d_bytes += (xb1 - xb0) * (y1 - y0);
         }
         if (rc != FANLIN_OK) break;
         rc = prepare_on_stream(ctx, dev_index, djobs.data(), m, nullptr, &f.batch, f.st);

@@ -367,6 +367,16 @@ def test_only_the_needed_source_rows_cross_the_link(fanlin, dev):
     assert dev.stats()["h2d_bytes"] - before == (pl.src_y1 - pl.src_y0) * 300 * 3
     hh = hist(got, O.process(img, w=200, h=100, crop=True))
     assert hh[">=2"] == 0 and hh[1] <= 0.002 * got.size + 2, hh
+    # a wide image cropped to a tall request: only the middle columns cross the link (a 2-D copy)
+    wide = synth_image(78, 200, 1500, 4)
+    qw = fanlin.Query("w=100&h=150&crop=true")
+    pw = fanlin.plan_job(fanlin.make_job(wide, qw))
+    assert 0 < pw.src_x0 < pw.src_x1 < 1500 and (pw.src_x1 - pw.src_x0) < 1400
+    before = dev.stats()["h2d_bytes"]
+    gotw = fanlin.process_image(dev, wide, qw)
+    assert dev.stats()["h2d_bytes"] - before == (pw.src_x1 - pw.src_x0) * 4 * (pw.src_y1 - pw.src_y0)
+    hw = hist(gotw, O.process(wide, w=100, h=150, crop=True))
+    assert hw[">=2"] == 0 and hw[1] <= 0.002 * gotw.size + 2, hw
     # a stored-rotated image is copied whole (the window is in oriented coordinates)
     before = dev.stats()["h2d_bytes"]
     got = fanlin.process_image(dev, img, q, orientation=6)
