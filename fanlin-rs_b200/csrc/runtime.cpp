@@ -1097,7 +1097,10 @@ int run_on_device(fanlin_ctx *ctx, int dev_index, const fanlin_job *jobs, uint32
     // Pageable callers (the Vec<u8> of a decoder, src/handler.rs:219): batches stage through pinned buffers of the context's
     // pool -- the host copy of sub-batch k + 1 runs while sub-batch k is on the link.  Judged on the first job (a batch comes
     // from one producer); single requests keep the driver's own staging, which costs the same as ours for one image.
-    const unsigned copy_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency() / unsigned(std::max<size_t>(1, ctx->devs.size()))));
+    // (FANLIN_COPY_THREADS: experiments)
+    static const unsigned copy_threads_env = [] { const char *e = std::getenv("FANLIN_COPY_THREADS"); const long v = e ? std::atol(e) : 0; return unsigned(v > 0 ? v : 0); }();
+    const unsigned copy_threads = copy_threads_env ? copy_threads_env
+                                                   : std::max(1u, std::min(16u, std::thread::hardware_concurrency() / unsigned(std::max<size_t>(1, ctx->devs.size()))));
     const bool stage_in = n >= BATCH_STAGING_MIN_JOBS && !is_pinned(ctx, jobs[0].src, 1);
     const bool stage_out = n >= BATCH_STAGING_MIN_JOBS && !is_pinned(ctx, jobs[0].dst, 1);
     if (stage_in) max_bytes = size_t(256) << 20;  // staged sub-batches: small enough that two of them stay in the pinned pool's cache
