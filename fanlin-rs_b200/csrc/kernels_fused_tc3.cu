@@ -7,10 +7,12 @@
 // store and zero only the slots whose taps ended in the chunk.  The ring has to hold what ONE chunk touches (not what
 // fits a thread's registers), so downscales near 2 (BASELINE C1: 512 -> 200, C3: 3840 -> 1778 RGBA) take this kernel.
 //
-// Roles (1 CTA / SM, 12 warps): source TMA thread, vertical-weight TMA thread, vertical MMA thread, horizontal thread
-// (weight tiles + MMAs), 8 consumer warps.  A consumer warp owns 32 band rows of ONE row tile for the drain (warp = tile *
-// 4 + lane quarter when the band has two tiles; with one tile the two warps of a quarter split the finished pixels), stages
-// its pixels in its own shared-memory tile and stores them as aligned words of a few rows per store.
+// Roles (1 CTA / SM, 16 warps; the kernel needs ~100 registers): source TMA thread, vertical-weight TMA thread, vertical MMA
+// thread, horizontal thread (weight tiles -- the hi and the lo half fetched separately, each as early as its readers allow --
+// and the MMAs, of which only the K steps with any weight for the window piece are issued), 12 consumer warps in three sets of
+// one warp per TMEM lane quarter.  In chunk k set (k + t) mod 3 drains what chunk k - 1 finished in row tile t (TMEM -> rounded
+// bytes -> the staging tile of (tile, lane quarter) -> aligned words of a few rows per store), and the tile's groups are
+// converted to T by the other two sets (t3_owner): a tile goes back to the tensor core after max(drain, two conversions).
 // Reference call sites: src/handler.rs:229-248 (resize / resize_to_fill + letterbox), image-0.25.6 imageops::resize.
 #include <cuda.h>
 
