@@ -219,3 +219,24 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_output_layout_flags_in_the_plan(fanlin):
+    """fanlin_plan_job (pure host): FANLIN_TO_RGB8 / _TO_RGBA8 / _TO_YCBCR describe the layout the caller gets and exclude
+    each other; the source window of a crop request is what fanlin_run copies."""
+    img = synth_image(5, 60, 90, 4)
+    q = fanlin.Query("w=40&h=40")
+    plain = fanlin.plan_job(fanlin.make_job(img, q))
+    assert (plain.out_w, plain.out_h, plain.out_channels, plain.out_sample) == (40, 40, 4, 0) and plain.out_bytes == 40 * 40 * 4
+    rgb = fanlin.plan_job(fanlin.make_job(img, q, to_rgb8=True))
+    assert rgb.out_channels == 3 and rgb.out_bytes == 40 * 40 * 3 and rgb.stages & 32
+    ycc = fanlin.plan_job(fanlin.make_job(img, q, to_ycbcr=True))
+    assert ycc.out_channels == 3 and ycc.out_bytes == 40 * 40 * 3 and ycc.stages & 64 and not ycc.stages & 32
+    gray = fanlin.plan_job(fanlin.make_job(synth_image(6, 60, 90, 3), fanlin.Query("w=40&h=30&crop=true&grayscale=true"), to_rgba8=True))
+    assert gray.out_channels == 4 and gray.stages & 16
+    for a, b in (("to_rgb8", "to_rgba8"), ("to_rgb8", "to_ycbcr"), ("to_rgba8", "to_ycbcr")):
+        with pytest.raises(fanlin.FanlinError):
+            fanlin.plan_job(fanlin.make_job(img, q, **{a: True, b: True}))
+    tall = fanlin.plan_job(fanlin.make_job(synth_image(7, 900, 300, 3), fanlin.Query("w=200&h=100&crop=true")))
+    assert 0 < tall.src_y0 < tall.src_y1 < 900 and (tall.src_x0, tall.src_x1) == (0, 300)
+    assert tall.algorithmic_bytes == (tall.src_y1 - tall.src_y0) * 300 * 3 + tall.out_bytes
