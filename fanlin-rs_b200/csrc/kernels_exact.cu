@@ -88,11 +88,18 @@ __device__ __forceinline__ uint32_t fetch_packed(const uint8_t *p, uint32_t colo
     return b[0] | b[1] << 8 | b[2] << 16 | b[3] << 24;
 }
 
+// fetch_packed<4> of a pixel that is already in a register (r | g << 8 | b << 16 | a << 24)
+__device__ __forceinline__ uint32_t op_packed4(uint32_t px, uint32_t color_op) {
+    if (color_op == COLOR_GRAY) return luma_u8(px & 255u, (px >> 8) & 255u, (px >> 16) & 255u) | (px >> 24) << 8;
+    if (color_op == COLOR_INVERT) return px ^ 0x00ffffffu;  // alpha stays
+    return px;
+}
+
 // Compose-only: colour op on load, crop copy, letterbox, to_rgba8 -- and the Nearest resample of
 // GIF frames (handler.rs:338,340), which is a gather: with tables (v_tab != NO_TABLE) the source
 // pixel of an output is (h_tab[x].left, v_tab[y].left), its single tap.  Four consecutive canvas
 // pixels of a row per thread; RGBA output leaves as one 16-byte store when the row allows.
-constexpr uint32_t CMP_ROWS = 1;  // canvas rows per block (4 measured slower on C4: 0.100 vs 0.091 ms per 200 frames -- the rows of a thread are a serial chain of loads)
+constexpr uint32_t CMP_ROWS = 4;  // canvas rows per block: one row per block is 54 k blocks of 120 busy threads for C4 (A/B on one box: 0.129 -> 0.095 ms per 200 frames with four rows and the 16-byte loads below)
 __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict__ descs, const TapEntry *__restrict__ tab) {
     const StageDesc &d = descs[blockIdx.y];
     const uint32_t cw = d.canvas_w, ch = d.canvas_h;
@@ -114,6 +121,14 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
     const uint32_t orient = gather ? 0u : d.orient, SW = d.src_w, SH = d.src_h, yo = d.oy0 + (cy - dst_y);
     uint8_t *q = d.dst + size_t(cy) * d.dst_pitch + size_t(cx0) * c_out;
     uint32_t out[4];
+    // four consecutive RGBA source pixels on a 16-byte boundary (GIF frames: 200 x 480x270 of them is C4) come as ONE load
+    // instead of sixteen byte loads
+    uint4 quad = make_uint4(0, 0, 0, 0);
+    bool have_quad = false;
+    if (c_mem == 4 && !gather && orient < 2 && row_in && cx0 >= dst_x && cx0 - dst_x + 4 <= n_cols && cx0 + 4 <= cw) {
+        const uint8_t *p4 = srow + size_t(ox0 + cx0 - dst_x) * 4;
+        if ((reinterpret_cast<uintptr_t>(p4) & 15) == 0) { quad = __ldg(reinterpret_cast<const uint4 *>(p4)); have_quad = true; }
+    }
 #pragma unroll
     for (uint32_t k = 0; k < 4; k++) {
         const uint32_t cx = cx0 + k, lx = cx - dst_x;
@@ -133,7 +148,8 @@ __global__ void __launch_bounds__(TX) compose_kernel(const StageDesc *__restrict
                 }
                 p = d.src + size_t(uy) * d.src_pitch + size_t(ux) * c_mem;
             }
-            const uint32_t v = c_mem == 4 ? fetch_packed<4>(p, color_op) : c_mem == 3 ? fetch_packed<3>(p, color_op)
+            const uint32_t v = have_quad ? op_packed4(k == 0 ? quad.x : k == 1 ? quad.y : k == 2 ? quad.z : quad.w, color_op)
+                             : c_mem == 4 ? fetch_packed<4>(p, color_op) : c_mem == 3 ? fetch_packed<3>(p, color_op)
                              : c_mem == 1 ? fetch_packed<1>(p, color_op) : fetch_packed<2>(p, color_op);
             if (epi == EPI_PLAIN) {
                 out[k] = v;
