@@ -240,3 +240,48 @@ def test_output_layout_flags_in_the_plan(fanlin):
     tall = fanlin.plan_job(fanlin.make_job(synth_image(7, 900, 300, 3), fanlin.Query("w=200&h=100&crop=true")))
     assert 0 < tall.src_y0 < tall.src_y1 < 900 and (tall.src_x0, tall.src_x1) == (0, 300)
     assert tall.algorithmic_bytes == (tall.src_y1 - tall.src_y0) * 300 * 3 + tall.out_bytes
+
+
+# ---- the Rust binding on paper must agree with the header and the Makefile (nobody can compile it here) ----
+
+def _c_struct_fields(hdr, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        first, *rest = decl.split(",")
+        out.append(re.search(r"(\w+)(\[\d+\])?$", first.strip()).group(1))
+        out += [re.search(r"(\w+)", r).group(1) for r in rest]
+    return out
+
+
+def _rust_struct_fields(md, name):
+    body = re.search(r"pub struct %s \{(.*?)\}\n" % name, md, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    body = re.sub(r"//[^\n]*", "", body)
+    return re.findall(r"pub (\w+)\s*:", body)
+
+
+def test_integration_md_agrees_with_header_and_makefile():
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(ROOT, "include", "fanlin_device.h")).read()
+    mk = open(os.path.join(ROOT, "fanlin-rs_b200", "csrc", "Makefile")).read()
+    # build.rs compiles exactly the Makefile's sources
+    srcs = re.search(r"^SRCS := (.*)$", mk, re.M).group(1).split()
+    rs = re.findall(r'"(\w+\.(?:cpp|cu))"', re.search(r"let src = \[(.*?)\];", md, re.S).group(1))
+    assert sorted(rs) == sorted(srcs)
+    # every struct crosses the boundary with the header's fields in the header's order
+    for c_name, rust_name in (("fanlin_job", "FanlinJob"), ("fanlin_plan", "FanlinPlan"), ("fanlin_config", "FanlinConfig")):
+        assert _rust_struct_fields(md, rust_name) == _c_struct_fields(hdr, c_name), rust_name
+    # every extern "C" fn of the binding is declared by the header
+    declared = set(re.findall(r"FANLIN_API [^;(]*?\b(fanlin_\w+)\(", hdr))
+    bound = re.findall(r"^\s*fn (fanlin_\w+)\(", md, re.M)
+    assert len(bound) >= 8 and set(bound) <= declared
+    # the flag / enum constants carry the header's values
+    enums = dict((k, int(v, 0)) for k, v in re.findall(r"FANLIN_(\w+)\s*=\s*(0x[0-9a-fA-F]+|\d+)", hdr))
+    enums.update((k, 1 << int(v)) for k, v in re.findall(r"FANLIN_(\w+)\s*=\s*1u?\s*<<\s*(\d+)", hdr))
+    for k, v in re.findall(r"pub const (\w+): u32 = (\d+);", md):
+        assert enums.get(k, enums.get("FILTER_" + k)) == int(v), (k, v)
