@@ -14,7 +14,7 @@
 // filter weights as three signed base-128 digits of round(w * 2^s) (columns 0-31 hi,
 // 32-63 mid, 64-95 lo); the epilogue recombines the three s32 sums exactly.  Integer
 // arithmetic is exact; the only deviation from the f32 recipe is the 2^-s weight
-// quantisation (s >= 21), below the rounding noise of the f32 accumulation it replaces.
+// quantisation (s >= 20), below the rounding noise of the f32 accumulation it replaces.
 //
 // Where the outputs a 128-byte chunk touches fit a ring of accumulator columns (fused_tc.cpp
 // build_hmma), the horizontal pass runs on the tensor cores too (fused_resample_tc2_kernel):
