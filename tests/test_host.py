@@ -285,3 +285,67 @@ def test_integration_md_agrees_with_header_and_makefile():
     enums.update((k, 1 << int(v)) for k, v in re.findall(r"FANLIN_(\w+)\s*=\s*1u?\s*<<\s*(\d+)", hdr))
     for k, v in re.findall(r"pub const (\w+): u32 = (\d+);", md):
         assert enums.get(k, enums.get("FILTER_" + k)) == int(v), (k, v)
+
+
+def test_planner_fuzz_against_the_oracle(fanlin):
+    """400 random requests (every flag, EXIF value, channel count, up- and downscales, requests equal to the image in one
+    or both axes): the plan's output dims / channels are the oracle's, and the plan is consistent with itself -- the crop
+    rectangle lies inside the resized image, the overlay inside the canvas, the source window inside the oriented image,
+    out_bytes and algorithmic_bytes follow from the rest.  Host code only: the CUDA library plans without a device."""
+    rng = np.random.default_rng(2024)
+    TO_RGBA8, TO_RGB8 = 1 << 4, 1 << 5
+    for it in range(400):
+        c = int(rng.integers(1, 5))
+        w, h = int(rng.integers(1, 48)), int(rng.integers(1, 48))
+        gif = bool(rng.random() < 0.15)
+        if gif:
+            c = 4  # process_gif composites every frame to RGBA8 first (handler.rs:325-328)
+        kw = {}
+        parts = []
+        r = rng.random()
+        if r < 0.85:
+            rw = w if rng.random() < 0.1 else int(rng.integers(1, 80))
+            rh = h if rng.random() < 0.1 else int(rng.integers(1, 80))
+            kw.update(w=rw, h=rh)
+            parts += [f"w={rw}", f"h={rh}"]
+        if rng.random() < 0.4:
+            kw["crop"] = True
+            parts.append("crop=true")
+        if rng.random() < 0.3:
+            kw["grayscale"] = True
+            parts.append("grayscale=true")
+        if rng.random() < 0.3:
+            kw["inverse"] = True
+            parts.append("inverse=true")
+        if rng.random() < 0.3:
+            rgb = tuple(int(x) for x in rng.integers(0, 256, 3))
+            kw["rgb"] = rgb
+            parts.append("rgb=%d,%d,%d" % rgb)
+        if not gif and rng.random() < 0.25:
+            kw["blur"] = float(rng.integers(10, 21))
+            parts.append("blur=%d" % kw["blur"])
+        exif = 0 if gif else int(rng.integers(0, 9))
+        to_rgb8 = bool(not gif and rng.random() < 0.2)
+        j = _job(fanlin, w, h, c, "&".join(parts), gif=gif)
+        j.orientation = exif
+        if to_rgb8:
+            j.flags |= TO_RGB8
+        p = fanlin.plan_job(j)
+        img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+        want = O.process(img, gif=gif, orientation=max(exif, 1), to_rgb8=to_rgb8, **kw)
+        tag = (it, w, h, c, parts, exif, gif, to_rgb8)
+        assert (p.out_h, p.out_w, p.out_channels) == want.shape, tag
+        assert p.out_bytes == want.size and p.out_sample == 0, tag
+        ow, oh = (h, w) if exif >= 5 else (w, h)  # the oriented image
+        assert p.src_x0 <= p.src_x1 <= ow and p.src_y0 <= p.src_y1 <= oh, tag
+        assert p.algorithmic_bytes == (p.src_x1 - p.src_x0) * (p.src_y1 - p.src_y0) * c + p.out_bytes, tag
+        rw, rh = p.resized_w or ow, p.resized_h or oh  # the image behind the resample (resized_* = 0: none happened)
+        if p.stages & 4:  # letterbox: resize() fits inside the request, the result sits centred on the canvas (handler.rs:244-245)
+            assert rw <= p.out_w and rh <= p.out_h and (rw < p.out_w or rh < p.out_h), tag
+            assert (p.overlay_x, p.overlay_y) == ((p.out_w - rw) // 2, (p.out_h - rh) // 2) and (p.crop_x, p.crop_y) == (0, 0), tag
+        else:  # the output is the (cropped) image: the crop rectangle lies inside it
+            assert p.crop_x + p.out_w <= rw and p.crop_y + p.out_h <= rh, tag
+            if not kw.get("crop"):
+                assert (p.crop_x, p.crop_y) == (0, 0) and (p.out_w, p.out_h) == (rw, rh), tag
+        assert bool(p.stages & 8) == bool(kw.get("blur")), tag
+        assert (not (p.stages & 32) or to_rgb8) and (not to_rgb8 or p.out_channels == 3), tag  # bit 5 only where a conversion is needed
