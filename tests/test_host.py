@@ -99,6 +99,40 @@ def test_query_blur_clamps_and_rgb_quirks(fanlin):
     assert Q("rgb=10%2C20%2C30").fill_color() == (10, 20, 30)
 
 
+def test_query_deserialisation_edge_cases(fanlin):
+    """What axum's Query<T> extractor (serde_urlencoded over form_urlencoded; Rust's FromStr for u32 / u8 / bool) does
+    with inputs the reference's table (src/query.rs:108-381) does not hold: '+' is a space, only '&' separates pairs, a
+    repeated field is an error, unknown and empty keys are ignored, bools are exactly "true" / "false", integers are
+    plain decimal digits within the type's range."""
+    Q = fanlin.Query
+    bad = ["w=+5&h=7", "w=-1", "w=%205", "crop=TRUE", "crop=1", "w=5&w=6", "blur=300", "quality=256", "w=4294967296", "w", "w&h=5",
+           "w=5;h=6", "rgb=1,2,3&rgb=4,5,6", "crop=true&crop=false", "w=1e3", "w=0x10", "blur=+12", "blur=12.0", "crop=true+", "w="]
+    for qs in bad:
+        assert Q.try_from_uri("?" + qs)[0] is None, qs
+    ok = {
+        "w=05&h=7": dict(dimensions=(5, 7)),
+        "w=%35&h=1": dict(dimensions=(5, 1)),
+        "w=4294967295&h=1": dict(dimensions=(4294967295, 1)),
+        "&&w=5&&h=6&": dict(dimensions=(5, 6)),
+        "=5": dict(dimensions=None, as_is=True),
+        "foo=bar&w=3&h=4": dict(dimensions=(3, 4)),
+        "rgb=1,2": dict(fill_color=(32, 32, 32)),      # fewer than three parts: the default (query.rs:44-46)
+        "rgb=1,2,3,4": dict(fill_color=(1, 2, 3)),     # take(3)
+        "rgb=+1,2,3": dict(fill_color=(32, 2, 3)),     # " 1" is not a u8
+        "rgb=": dict(fill_color=(32, 32, 32)),
+        "rgb=1,,3": dict(fill_color=(1, 32, 3)),
+        "rgb=%31,2,3": dict(fill_color=(1, 2, 3)),
+        "quality=0": dict(quality=0, as_is=True),
+        "blur=0": dict(blur=10.0, as_is=False),        # Some(0) clamps to 10: blur=0 is NOT "off" (query.rs:59-62)
+        "grayscale=false&inverse=false": dict(grayscale=False, inverse=False, as_is=True),
+        "avif=true": dict(use_avif=True, as_is=False),
+    }
+    for qs, want in ok.items():
+        q = Q(qs)
+        for name, val in want.items():
+            assert getattr(q, name)() == val, (qs, name)
+
+
 # ---- planner vs oracle geometry -------------------------------------------------------
 
 GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["cases"]
