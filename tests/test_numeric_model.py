@@ -145,9 +145,9 @@ def test_noise_image_worst_case_for_the_f16_split():
 
 
 def test_gaussian_weights_through_the_same_arithmetic():
-    # the blur's contraction (blur_tc.cpp: same digit rule and x16 f16 halves) with the table's normalised weights;
-    # the kernel itself factors the border normalisation out (interior weights x a per-pixel factor), which the
-    # -m gpu tests cover -- here only the scheme: digits + f16 halves on 41- and 81-tap Gaussians
+    # the blur's contraction (blur_tc.cpp: same digit rule and x16 f16 halves) with the table's normalised weights in
+    # both passes: digits + f16 halves on 41- and 81-tap Gaussians (the kernel's own horizontal form -- interior weights
+    # times a per-column border factor -- is model_blur_tc2 below)
     img = synth_image(9, 90, 110, 3)
     for sigma in (10.0, 20.0):
         got, pre, exact = model_resize(img, 110, 90, O.GAUSSIAN_BLUR, sigma)
@@ -155,6 +155,56 @@ def test_gaussian_weights_through_the_same_arithmetic():
         assert np.abs(pre - exact).max() < 2e-3
         diff = np.abs(got.astype(int) - want.astype(int))
         assert diff.max() <= 1 and (diff == 1).mean() < 1e-3
+
+
+def model_blur_tc2(img, sigma):
+    """blur_tc2_kernel's arithmetic (blur_tc.cpp / blur.cpp blur_build): vertical pass with the table's own (border-
+    renormalised) taps as digits, horizontal pass against ONE Toeplitz tile of the INTERIOR weights u (x 16, f16 halves),
+    the border renormalisation as one f32 factor per output column, corr[j] = w_table(j, centre tap) / u_centre."""
+    h, w, c = img.shape
+    radius = int(np.ceil(2.0 * sigma - 0.5))
+    n_ref = 4 * radius + 4
+    rl, rc, rw = O.weight_table(O.GAUSSIAN_BLUR, n_ref, n_ref, sigma)
+    o_ref = 2 * radius + 2
+    assert rc[o_ref] == 2 * radius + 1
+    u = rw[o_ref, :rc[o_ref]].astype(np.float32)
+    vl, vc, vw = O.weight_table(O.GAUSSIAN_BLUR, h, h, sigma)
+    hl, hc, hw = O.weight_table(O.GAUSSIAN_BLUR, w, w, sigma)
+    sh = _weight_shift(vw)
+    q = _dense(vl, vc, _lround(vw.astype(np.float64) * 2.0 ** sh), h, np.int64)
+    dh, dm, dl = _digits(q)
+    src = img.reshape(h, w * c).astype(np.int64)
+    s_hi, s_mid, s_lo = dh @ src, dm @ src, dl @ src
+    scale, scale_hi = np.float32(2.0 ** -sh), np.float32(2.0 ** (14 - sh))
+    v = ((s_mid * 128 + s_lo).astype(np.float32).astype(np.float64) * np.float64(scale)).astype(np.float32)
+    v = (s_hi.astype(np.float32).astype(np.float64) * np.float64(scale_hi) + v.astype(np.float64)).astype(np.float32)
+    t_hi, t_lo = _f16_split(v)
+    toe = np.zeros((w, w), np.float32)  # Toeplitz: output j takes u[k - j + R] from source k (zeros outside the image)
+    for j in range(w):
+        k0, k1 = max(0, j - radius), min(w, j + radius + 1)
+        toe[j, k0:k1] = u[k0 - j + radius:k1 - j + radius]
+    w_hi, w_lo = _f16_split((toe * np.float32(TC2_WSCALE)).astype(np.float32))
+    T_hi, T_lo = t_hi.astype(np.float64).reshape(h, w, c), t_lo.astype(np.float64).reshape(h, w, c)
+    d = (np.einsum("ok,rkc->roc", w_hi.astype(np.float64), T_hi) + np.einsum("ok,rkc->roc", w_hi.astype(np.float64), T_lo)
+         + np.einsum("ok,rkc->roc", w_lo.astype(np.float64), T_hi)).astype(np.float32)
+    corr = np.array([hw[j, j - hl[j]] for j in range(w)], np.float32) / u[radius]   # f32 division, as the host does
+    corr16 = (corr * np.float32(1.0 / TC2_WSCALE)).astype(np.float32)
+    pre = (d * corr16[None, :, None]).astype(np.float32)
+    out = np.clip(np.trunc(pre.astype(np.float64) + 0.5), 0, 255).astype(np.uint8)
+    exact = np.einsum("ok,rkc->roc", _dense(hl, hc, hw, w, np.float64),
+                      (_dense(vl, vc, vw, h, np.float64) @ src.astype(np.float64)).reshape(h, w, c))
+    return out, pre.astype(np.float64), exact
+
+
+@pytest.mark.parametrize("sigma,h,w,c", [(10.0, 70, 95, 4), (20.0, 100, 130, 1), (10.3, 50, 64, 3), (12.0, 30, 25, 2)])
+def test_modelled_blur_with_interior_weights_and_border_factors(sigma, h, w, c):
+    # images narrower than the window too (25 columns under 49 taps): every column is a border column there
+    img = synth_image(int(sigma * 10) + c, h, w, c)
+    got, pre, exact = model_blur_tc2(img, sigma)
+    want = O.blur(img, sigma)
+    assert np.abs(pre - exact).max() < 2e-3
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert diff.max() <= 1 and (diff == 1).mean() < 1e-3
 
 
 def test_shift_rule_leaves_headroom_for_every_lanczos3_and_gaussian_table():
