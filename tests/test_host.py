@@ -383,3 +383,39 @@ def test_planner_fuzz_against_the_oracle(fanlin):
                 assert (p.crop_x, p.crop_y) == (0, 0) and (p.out_w, p.out_h) == (rw, rh), tag
         assert bool(p.stages & 8) == bool(kw.get("blur")), tag
         assert (not (p.stages & 32) or to_rgb8) and (not to_rgb8 or p.out_channels == 3), tag  # bit 5 only where a conversion is needed
+
+
+def test_header_is_plain_c_and_the_ctypes_mirror_has_its_layout(fanlin, tmp_path):
+    """include/fanlin_device.h is the boundary a cgo / Rust / ctypes binding reads: it must compile as C99 (and as C++)
+    on its own, and the ctypes structures of fanlin-rs_b200/device.py -- what every test and the bench call through -- must
+    have the size and the field offsets the C compiler gives the header's structs."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    pairs = [("fanlin_job", fanlin.device.Job), ("fanlin_plan", fanlin.device.Plan), ("fanlin_config", fanlin.device.Config),
+             ("fanlin_stats", fanlin.device.Stats), ("fanlin_query", fanlin.device.QueryStruct)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fanlin_device.h"', "int main(void) {"]
+    for c_name, cls in pairs:
+        lines.append(f'  printf("{c_name} %zu\\n", sizeof({c_name}));')
+        for f, _ in cls._fields_:
+            lines.append(f'  printf("{c_name}.{f} %zu\\n", offsetof({c_name}, {f}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for c_name, cls in pairs:
+        assert int(got[c_name]) == C.sizeof(cls), c_name
+        for f, _ in cls._fields_:
+            assert int(got[f"{c_name}.{f}"]) == getattr(cls, f).offset, (c_name, f)
+    # and as C++ (the header wraps its declarations in extern "C")
+    gxx = shutil.which("g++")
+    if gxx:
+        cpp = tmp_path / "hdr.cpp"
+        cpp.write_text('#include "fanlin_device.h"\nint main() { return sizeof(fanlin_job) ? 0 : 1; }\n')
+        subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
